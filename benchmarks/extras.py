@@ -1,0 +1,135 @@
+"""Secondary measurements printed under "extra" in bench.py's JSON line: the other BASELINE.json configs.
+
+C1  f32 4096^2 contiguous  a = b*c + a  and sum_axis (buffers rotated so the 64 MiB arrays do not sit in L2)
+C3  16384^2 f64 sum/mean/var_axis and i64 sum_axis / fold_axis(min), both axes
+C4  general_mat_mul f64 / f32 at 8192^3 (C- and F-order operands)
+C5  (N > 1) per-rank f32 elementwise + global sum() finished by an NCCL all-reduce
+All timed with CUDA events on the context stream after warm-up; algorithmic bytes per SURVEY.md §8d.
+"""
+from __future__ import annotations
+
+import statistics
+
+import numpy as np
+
+
+def _time(ctx, fn, iters, warm=2):
+    for _ in range(warm):
+        fn()
+    ctx.sync()
+    evs = [(ctx.event(), ctx.event()) for _ in range(iters)]
+    for a, b in evs:
+        ctx.record(a)
+        fn()
+        ctx.record(b)
+    ctx.sync()
+    ms = [ctx.elapsed_ms(a, b) for a, b in evs]
+    return statistics.median(ms), min(ms)
+
+
+def run_extras(nd, ctx, torch, dist, rank, world, local, peak_gbs):
+    from ndarray_b200 import Array, Axis, Zip
+    dev = torch.device("cuda", local)
+    out = {}
+
+    def tarr(t, shape=None, order="C"):
+        dt = {torch.float32: np.float32, torch.float64: np.float64, torch.int64: np.int64, torch.int32: np.int32}[t.dtype]
+        return Array.borrow(t.data_ptr(), tuple(t.shape) if shape is None else shape, dt, order, ctx, owner=t)
+
+    def gbs(nbytes, ms):
+        return nbytes / (ms * 1e-3) / 1e9
+
+    def rec(name, nbytes, med, best):
+        out[name] = {"GB/s": round(gbs(nbytes, med), 1), "best_GB/s": round(gbs(nbytes, best), 1), "ms": round(med, 4),
+                     "frac_of_measured_peak": round(gbs(nbytes, med) / peak_gbs, 3)}
+
+    # ---- C1 ---------------------------------------------------------------------------------------
+    n = 4096
+    sets = []
+    for _ in range(4):  # 4 sets x 3 arrays x 64 MiB = 768 MiB  >> L2
+        ts = [torch.rand(n, n, device=dev) * 2 - 1 for _ in range(3)]
+        sets.append([tarr(t) for t in ts])
+    torch.cuda.synchronize(dev)
+    it = [0]
+
+    def c1_zip():
+        a, b, c = sets[it[0] % 4]
+        it[0] += 1
+        Zip.from_(a).and_(b).and_(c).for_each("a=b*c+a")
+
+    med, best = _time(ctx, c1_zip, 40, 4)
+    rec("C1_zip_a=b*c+a_f32_4096^2", 4 * 4 * n * n, med, best)
+    for ax in (0, 1):
+        def c1_sum(ax=ax):
+            a = sets[it[0] % 4][0]
+            it[0] += 1
+            a.sum_axis(Axis(ax))
+        med, best = _time(ctx, c1_sum, 40, 4)
+        rec(f"C1_sum_axis{ax}_f32_4096^2", 4 * n * n + 4 * n, med, best)
+    del sets
+    # ---- C3 ---------------------------------------------------------------------------------------
+    n = 16384
+    tf = torch.randn(n, n, device=dev, dtype=torch.float64)
+    f = tarr(tf)
+    nb = 8 * n * n + 8 * n
+    for ax in (0, 1):
+        for name, fn in (("sum_axis", lambda ax=ax: f.sum_axis(Axis(ax))), ("mean_axis", lambda ax=ax: f.mean_axis(Axis(ax))),
+                         ("var_axis", lambda ax=ax: f.var_axis(Axis(ax), 1.0))):
+            med, best = _time(ctx, fn, 10, 2)
+            rec(f"C3_{name}{ax}_f64_16384^2", nb, med, best)
+    med, best = _time(ctx, lambda: f.sum(), 10, 2)
+    rec("C3_sum_f64_16384^2", 8 * n * n, med, best)
+    del f, tf
+    ti = torch.randint(-2 ** 62, 2 ** 62, (n, n), device=dev, dtype=torch.int64)
+    a = tarr(ti)
+    for ax in (0, 1):
+        med, best = _time(ctx, lambda ax=ax: a.sum_axis(Axis(ax)), 10, 2)
+        rec(f"C3_sum_axis{ax}_i64_16384^2", nb, med, best)
+        med, best = _time(ctx, lambda ax=ax: a.fold_axis(Axis(ax), np.iinfo(np.int64).max, "min"), 10, 2)
+        rec(f"C3_fold_axis{ax}_min_i64_16384^2", nb, med, best)
+    del a, ti
+    torch.cuda.empty_cache()
+    # ---- C4 ---------------------------------------------------------------------------------------
+    n = 8192
+    flops = 2.0 * n ** 3
+    for tdt, name in ((torch.float64, "f64"), (torch.float32, "f32")):
+        ta, tb, tc = (torch.randn(n, n, device=dev, dtype=tdt) for _ in range(3))
+        for orders in ("CCC", "FFC"):
+            A, B, Cm = (tarr(t, order=o) for t, o in zip((ta, tb, tc), orders))
+            med, best = _time(ctx, lambda: nd.general_mat_mul(1.0, A, B, 0.0, Cm), 3, 1)
+            out[f"C4_gemm_{name}_8192^3_{orders}"] = {"TFLOP/s": round(flops / (med * 1e-3) / 1e12, 2),
+                                                      "best_TFLOP/s": round(flops / (best * 1e-3) / 1e12, 2), "ms": round(med, 3)}
+        # library comparator (cuBLAS through torch), never on the product path
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.matmul(ta, tb)
+        e0.record()
+        for _ in range(3):
+            torch.matmul(ta, tb)
+        e1.record()
+        torch.cuda.synchronize(dev)
+        out[f"C4_comparator_cublas_{name}_8192^3"] = {"TFLOP/s": round(flops / (e0.elapsed_time(e1) / 3 * 1e-3) / 1e12, 2)}
+        del ta, tb, tc
+    torch.cuda.empty_cache()
+    # ---- C5: sharded elementwise + global sum with an all-reduce ----------------------------------------
+    if dist is not None:
+        rows = 65536 // 8  # per-rank shard of the [65536, 65536] f32 problem at 8 GPUs; weak-scaled below that
+        ts = [torch.rand(rows, 65536, device=dev) * 2 - 1 for _ in range(3)]
+        a, b, c = (tarr(t) for t in ts)
+        acc = torch.zeros(1, device=dev, dtype=torch.float32)
+        accv = tarr(acc, shape=())
+        stream = torch.cuda.ExternalStream(ctx.stream_ptr(), device=dev)
+
+        def c5():
+            Zip.from_(a).and_(b).and_(c).for_each("a=b*c+a")
+            a.sum_to_device(accv)
+            with torch.cuda.stream(stream):
+                dist.all_reduce(acc)
+
+        med, best = _time(ctx, c5, 10, 2)
+        t = torch.tensor([med], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        nbytes = (4 * 4 + 4) * rows * 65536 * world
+        out["C5_zip+global_sum_f32"] = {"GB/s_aggregate": round(gbs(nbytes, float(t.item())), 1), "ms": round(float(t.item()), 3),
+                                        "per_rank_elems": rows * 65536, "collective": "ncclAllReduce(sum, 1 elt) on the ctx stream"}
+    return out

@@ -1,0 +1,270 @@
+/*
+ * ndb200.h — C ABI of libndb200, the B200 (sm_100a) data-parallel core for ndarray.
+ *
+ * This is the drop-in boundary.  A Rust companion crate (or any FFI host) binds
+ * exactly these symbols; nothing here mentions torch, C++ or CUDA types.
+ *
+ * Every view is described the way ndarray's `NdProducer` exposes it
+ * (reference src/zip/ndproducer.rs:57-100, src/lib.rs:1304-1346):
+ *   ptr    — DEVICE pointer to the *logical first element* (may be the highest
+ *            address when strides are negative, src/lib.rs:1322-1328)
+ *   dim    — axis lengths
+ *   stride — SIGNED strides, counted in ELEMENTS (not bytes)
+ *
+ * Error convention: every entry point returns an `int` status.  0 = ok,
+ * 1..6 mirror ndarray's `ErrorKind` (src/error.rs:43-57), the rest are ours.
+ * Where ndarray panics, we return a status and the host wrapper raises with
+ * ndarray's own message (`ndb_last_error()`).  Nothing aborts across the ABI.
+ *
+ * Threading: a context owns one device + one stream + a workspace.  Calls are
+ * asynchronous on the context stream unless documented otherwise; a context
+ * is not re-entrant, distinct contexts are independent.
+ *
+ * There is NO CPU fallback behind any of the compute entry points: if no CUDA
+ * device is usable they return NDB_ERR_CUDA.
+ */
+#ifndef NDB200_H
+#define NDB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NDB_MAX_NDIM 8 /* IxDyn views of higher rank are rejected with NDB_ERR_UNSUPPORTED */
+#define NDB_MAX_PARTS 9 /* Zip takes 1..9 producers (reference src/zip/mod.rs:918-928, tests/azip.rs:481) */
+
+/* ---- status codes ------------------------------------------------------ */
+enum {
+    NDB_OK = 0,
+    NDB_ERR_INCOMPATIBLE_SHAPE = 1,  /* ErrorKind::IncompatibleShape  (src/error.rs:46) */
+    NDB_ERR_INCOMPATIBLE_LAYOUT = 2, /* ErrorKind::IncompatibleLayout */
+    NDB_ERR_RANGE_LIMITED = 3,       /* ErrorKind::RangeLimited */
+    NDB_ERR_OUT_OF_BOUNDS = 4,       /* ErrorKind::OutOfBounds */
+    NDB_ERR_UNSUPPORTED = 5,         /* ErrorKind::Unsupported */
+    NDB_ERR_OVERFLOW = 6,            /* ErrorKind::Overflow */
+    NDB_ERR_INVALID_ARG = 7,         /* ddof out of range etc. — ndarray panics (src/numeric/impl_numeric.rs:408) */
+    NDB_ERR_EMPTY = 8,               /* result is `None` in ndarray (mean_axis of a 0-length axis, impl_numeric.rs:349) */
+    NDB_ERR_DIV_BY_ZERO = 9,         /* integer / or % by zero, or MIN / -1: Rust panics */
+    NDB_ERR_ALIASING = 10,           /* a written producer overlaps itself (dimension/mod.rs:58 dim_stride_overlap) */
+    NDB_ERR_CUDA = 100               /* CUDA runtime failure; text in ndb_last_error() */
+};
+
+/* ---- element types ------------------------------------------------------ */
+typedef enum {
+    NDB_F32 = 0,
+    NDB_F64 = 1,
+    NDB_I32 = 2,
+    NDB_I64 = 3
+} ndb_dtype;
+
+/* ---- a strided view (== what NdProducer exposes) ------------------------ */
+typedef struct {
+    void *ptr;                    /* device pointer to logical element [0,0,...] */
+    int32_t ndim;                 /* 0..NDB_MAX_NDIM */
+    int32_t dtype;                /* ndb_dtype */
+    int64_t dim[NDB_MAX_NDIM];    /* axis lengths */
+    int64_t stride[NDB_MAX_NDIM]; /* signed, in elements */
+} ndb_view;
+
+/* ---- elementwise op vocabulary ------------------------------------------
+ * Closures cannot cross an FFI, so Zip::for_each / map_collect take an op from
+ * this vocabulary: the closures the reference itself passes to Zip (operator
+ * overloads src/impl_ops.rs:53-438,597-712; assign/fill src/impl_methods.rs:
+ * 2796-2823; scaled_add src/linalg/impl_linalg.rs:399-405; the n-ary sums of
+ * tests/azip.rs:481-497; config-1's a = b*c + a).
+ * Parts are ordered OUTPUT FIRST: parts[0] is written, parts[1..] are read
+ * (an input may be the same view as the output: `a += b` is ADD on (a; a, b)).
+ * Float arithmetic is IEEE with every operation rounded separately (Rust never
+ * contracts a*b+c); integers wrap; integer / and % follow Rust (truncating,
+ * NDB_ERR_DIV_BY_ZERO where Rust would panic).
+ */
+typedef enum {
+    NDB_OP_COPY = 0,     /* out = in0                     (assign, impl_methods.rs:2796) */
+    NDB_OP_FILL = 1,     /* out = s0                      (fill,   impl_methods.rs:2819) */
+    NDB_OP_ADD = 2,      /* out = in0 + in1 */
+    NDB_OP_SUB = 3,      /* out = in0 - in1 */
+    NDB_OP_MUL = 4,      /* out = in0 * in1 */
+    NDB_OP_DIV = 5,      /* out = in0 / in1 */
+    NDB_OP_REM = 6,      /* out = in0 % in1               (fmod for floats) */
+    NDB_OP_MUL_ADD = 7,  /* out = in0 * in1 + in2         (two roundings; BASELINE config 1) */
+    NDB_OP_ADD_S = 8,    /* out = in0 + s0                (array op scalar, impl_ops.rs:183) */
+    NDB_OP_SUB_S = 9,    /* out = in0 - s0 */
+    NDB_OP_MUL_S = 10,   /* out = in0 * s0 */
+    NDB_OP_DIV_S = 11,   /* out = in0 / s0 */
+    NDB_OP_REM_S = 12,   /* out = in0 % s0 */
+    NDB_OP_RSUB_S = 13,  /* out = s0 - in0                (scalar op array, impl_ops.rs:348) */
+    NDB_OP_RDIV_S = 14,  /* out = s0 / in0 */
+    NDB_OP_NEG = 15,     /* out = -in0                    (impl_ops.rs Neg) */
+    NDB_OP_AXPY = 16,    /* out = in0 + s0 * in1          (scaled_add, impl_linalg.rs:399) */
+    NDB_OP_ADD_N = 17,   /* out = in0 + in1 + ... (left to right, 2..8 inputs; tests/azip.rs:492) */
+    NDB_OP_ABS = 18,     /* out = |in0| */
+    NDB_OP_SQRT = 19,    /* out = sqrt(in0)               (floats only; correctly rounded) */
+    NDB_OP_MIN = 20,     /* out = min(in0, in1) */
+    NDB_OP_MAX = 21,     /* out = max(in0, in1) */
+    NDB_OP_SCALE_ADD = 22, /* out = in0 * s0 + in1 * s1   (gemv/gemm-style alpha/beta combine, two products one sum) */
+    NDB_OP__COUNT
+} ndb_op;
+
+/* ---- axis-reduction vocabulary -------------------------------------------
+ * sum_axis / product_axis / mean_axis / var_axis / std_axis
+ * (src/numeric/impl_numeric.rs:268,305,342,401,471) and the associative folds
+ * fold_axis is used with (src/impl_methods.rs:3130).
+ */
+typedef enum {
+    NDB_RED_SUM = 0,
+    NDB_RED_PROD = 1,
+    NDB_RED_MIN = 2,
+    NDB_RED_MAX = 3,
+    NDB_RED_MEAN = 4, /* sum / n in the element type (integer division truncates) */
+    NDB_RED_VAR = 5,  /* Welford, result M2 / (n - ddof)            (floats only) */
+    NDB_RED_STD = 6,  /* sqrt(var)                                   (floats only) */
+    NDB_RED__COUNT
+} ndb_redop;
+
+/* kernel classes the planner can choose (reported by ndb_zip_plan) */
+typedef enum {
+    NDB_KERNEL_NOOP = 0,      /* some axis has length 0 */
+    NDB_KERNEL_FLAT_VEC = 1,  /* every producer is one dense unit-stride run: 128-bit vector kernel */
+    NDB_KERNEL_FLAT = 2,      /* same, but a base pointer is not 16-byte aligned: scalar coalesced */
+    NDB_KERNEL_ROWS_VEC = 3,  /* collapsed N-d, unit (or 0) inner strides, aligned rows: vector kernel */
+    NDB_KERNEL_ROWS = 4,      /* collapsed N-d, arbitrary signed strides, coalesced along the output's fastest axis */
+    NDB_KERNEL_TILE = 5       /* producers disagree on the fastest axis: shared-memory tile transpose */
+} ndb_kernel_class;
+
+typedef struct {
+    int32_t kernel;               /* ndb_kernel_class */
+    int32_t ndim;                 /* collapsed rank */
+    int64_t dim[NDB_MAX_NDIM];    /* collapsed axis lengths, slowest first */
+    int64_t stride[NDB_MAX_PARTS][NDB_MAX_NDIM]; /* per producer collapsed strides */
+    int64_t offset[NDB_MAX_PARTS]; /* element offset applied to each producer's ptr (axis flips) */
+    int32_t tile_axis;            /* NDB_KERNEL_TILE: collapsed axis staged through shared memory, else -1 */
+    uint32_t staged_mask;         /* NDB_KERNEL_TILE: bit p set = producer p is transposed through shared memory */
+} ndb_zip_plan_t;
+
+typedef struct ndb_ctx ndb_ctx;
+
+/* ---- library / context --------------------------------------------------- */
+const char *ndb_version(void);
+/* Thread-local text of the last failure on this thread ("" if none). */
+const char *ndb_last_error(void);
+/* Number of kernels this library has launched in the calling process (all contexts). */
+uint64_t ndb_launch_count(void);
+int ndb_device_count(int *count);
+
+int ndb_ctx_create(int device, ndb_ctx **out);
+int ndb_ctx_destroy(ndb_ctx *ctx);
+/* Use a caller-owned cudaStream_t (passed as void*) instead of the context's own. NULL restores it. */
+int ndb_ctx_set_stream(ndb_ctx *ctx, void *cuda_stream);
+void *ndb_ctx_stream(ndb_ctx *ctx);
+int ndb_sync(ndb_ctx *ctx);
+
+/* ---- device memory (DeviceArray storage; analogue of OwnedRepr, src/data_repr.rs:24) */
+int ndb_alloc(ndb_ctx *ctx, size_t bytes, void **dptr);
+int ndb_free(ndb_ctx *ctx, void *dptr);
+int ndb_memset(ndb_ctx *ctx, void *dptr, int byte, size_t bytes);
+int ndb_h2d(ndb_ctx *ctx, void *dst_dev, const void *src_host, size_t bytes); /* async on ctx stream */
+int ndb_d2h(ndb_ctx *ctx, void *dst_host, const void *src_dev, size_t bytes); /* async on ctx stream */
+int ndb_d2d(ndb_ctx *ctx, void *dst_dev, const void *src_dev, size_t bytes);
+int ndb_host_alloc(size_t bytes, void **hptr); /* pinned host memory */
+int ndb_host_free(void *hptr);
+/* event timing on the context stream, for harnesses */
+int ndb_event_create(void **ev);
+int ndb_event_destroy(void *ev);
+int ndb_event_record(ndb_ctx *ctx, void *ev);
+int ndb_event_elapsed_ms(void *start, void *stop, float *ms); /* synchronises on `stop` */
+
+/* ---- view arithmetic: pure host code, identical to ndarray's ---------------
+ * All of these only rewrite (ptr, dim, stride); `elem_size` comes from dtype.
+ */
+/* Slice one axis with start/end/step exactly like `Slice{start,end,step}`
+ * (src/slice.rs:42, src/dimension/mod.rs:390-495 do_slice).  `has_end == 0` means `end = None`.
+ * Out-of-range → NDB_ERR_OUT_OF_BOUNDS, step == 0 → NDB_ERR_INVALID_ARG (both panic in ndarray). */
+int ndb_view_slice_axis(ndb_view *v, int axis, int64_t start, int64_t end, int has_end, int64_t step);
+/* index_axis / collapse: fix `axis` at `index` and remove it (src/impl_methods.rs:1009). */
+int ndb_view_index_axis(ndb_view *v, int axis, int64_t index);
+/* broadcast to `ndim`/`dim` (src/impl_methods.rs:2371-2430 upcast): NDB_ERR_INCOMPATIBLE_SHAPE if impossible (ndarray returns None). */
+int ndb_view_broadcast(const ndb_view *v, int ndim, const int64_t *dim, ndb_view *out);
+/* permuted_axes (src/impl_methods.rs:2522): out axis i = in axis perm[i]. */
+int ndb_view_permute(const ndb_view *v, const int *perm, ndb_view *out);
+/* invert_axis (src/impl_methods.rs:2676). */
+int ndb_view_invert_axis(ndb_view *v, int axis);
+/* split_at (src/impl_raw_views.rs:113-135): the sharding primitive. */
+int ndb_view_split_at(const ndb_view *v, int axis, int64_t index, ndb_view *left, ndb_view *right);
+/* Layout bitset of src/layout/mod.rs:9-16 as computed by array_layout (src/zip/mod.rs:54-77):
+ * bit0 CORDER, bit1 FORDER, bit2 CPREFER, bit3 FPREFER. */
+uint32_t ndb_view_layout(const ndb_view *v);
+/* 1 if the view is one dense block in some axis order with any stride signs (dimension_trait.rs:294). */
+int ndb_view_is_contiguous(const ndb_view *v);
+/* min_stride_axis (dimension_trait.rs:343; Ix2 special case :715) — decides sum_axis' fast path. */
+int ndb_view_min_stride_axis(const ndb_view *v);
+
+/* ---- Zip: n-ary lock-step elementwise traversal -----------------------------
+ * Replaces Zip::from(..).and(..).for_each(closure) (src/zip/mod.rs:212,704,585,309-424)
+ * and its rayon form par_for_each (src/parallel/impl_par_methods.rs:64).
+ * parts[0] is the output producer, parts[1..n_parts) the inputs; all shapes must be equal
+ * (NDB_ERR_INCOMPATIBLE_SHAPE — ndarray panics "Zip: Producer dimension mismatch", zip/mod.rs:252).
+ * `scalars` points at 0..2 values of the element type (FILL, *_S, AXPY, SCALE_ADD).
+ */
+int ndb_zip(ndb_ctx *ctx, int op, const void *scalars, int n_parts, const ndb_view *parts);
+/* The plan ndb_zip would execute; pure host code (no device needed). */
+int ndb_zip_plan(int op, int n_parts, const ndb_view *parts, ndb_zip_plan_t *plan);
+/* Zip::map_collect's output-order rule (src/zip/mod.rs:278-281,764-789): returns 1 if the fresh
+ * output must be F-order, 0 for C-order, given the INPUT producers only. */
+int ndb_zip_prefer_f(int n_inputs, const ndb_view *inputs);
+
+/* ---- reductions ------------------------------------------------------------- */
+/* ArrayRef::sum / product (src/numeric/impl_numeric.rs:32,83): reduce every element, result
+ * written to HOST memory `out` (element type); synchronises the context stream. op ∈ {SUM, PROD, MIN, MAX}. */
+int ndb_reduce_all(ndb_ctx *ctx, int redop, const ndb_view *in, void *out_host);
+/* Same, but the scalar stays on the device (`out_dev`, element type) and nothing synchronises:
+ * used by the multi-GPU path so the NCCL allreduce can follow on the same stream. */
+int ndb_reduce_all_dev(ndb_ctx *ctx, int redop, const ndb_view *in, void *out_dev);
+/* sum_axis / product_axis / mean_axis / var_axis / std_axis / fold_axis(min|max|sum|prod).
+ * `out` must have `in`'s shape with `axis` removed (any strides).  `ddof` is used by VAR/STD only
+ * and must satisfy 0 <= ddof <= n (NDB_ERR_INVALID_ARG otherwise; NaN passes, as in ndarray). */
+int ndb_reduce_axis(ndb_ctx *ctx, int redop, int axis, const ndb_view *in, const ndb_view *out, double ddof);
+/* Partial Welford state for the multi-GPU var_axis: writes mean and M2 (sum of squared deviations)
+ * of this shard along `axis` into `mean_out` / `m2_out`, and merges shards with Chan's formula. */
+int ndb_welford_axis(ndb_ctx *ctx, int axis, const ndb_view *in, const ndb_view *mean_out, const ndb_view *m2_out);
+int ndb_welford_merge(ndb_ctx *ctx, int n_shards, const int64_t *counts, const ndb_view *means, const ndb_view *m2s,
+                      double ddof, int want_std, const ndb_view *out);
+/* 1-D dot product (src/linalg/impl_linalg.rs:74-133, numeric_util.rs:56), result to host. */
+int ndb_dot(ndb_ctx *ctx, const ndb_view *x, const ndb_view *y, void *out_host);
+
+/* ---- linalg ------------------------------------------------------------------
+ * general_mat_mul(alpha, &a, &b, beta, &mut c) (src/linalg/impl_linalg.rs:633): C <- alpha*A*B + beta*C,
+ * any signed strides like matrixmultiply::{s,d}gemm (impl_linalg.rs:512-546). alpha/beta point at HOST
+ * scalars of the element type. With beta == 0, C is never read (impl_linalg.rs:323-329).
+ * f64 uses FP64 tensor-core DMMA, f32 uses 3xTF32 on tcgen05 with fp32-class accuracy. */
+int ndb_gemm(ndb_ctx *ctx, const void *alpha, const ndb_view *a, const ndb_view *b, const void *beta, const ndb_view *c);
+/* general_mat_vec_mul (impl_linalg.rs:657): y <- alpha*A*x + beta*y */
+int ndb_gemv(ndb_ctx *ctx, const void *alpha, const ndb_view *a, const ndb_view *x, const void *beta, const ndb_view *y);
+
+/* ---- CBLAS drop-in: ndarray's one real plugin boundary -------------------------
+ * ndarray built with feature "blas" calls these with HOST pointers
+ * (src/linalg/impl_linalg.rs:466-491 gemm, :116-122 dot); crates/blas-mock-tests/src/lib.rs
+ * shows a foreign `extern "C" cblas_dgemm` is a legitimate provider.  These stage H2D/D2H around
+ * ndb_gemm on a process-global context (device NDB_DEVICE or 0).
+ */
+enum { NdbCblasRowMajor = 101, NdbCblasColMajor = 102 };
+enum { NdbCblasNoTrans = 111, NdbCblasTrans = 112, NdbCblasConjTrans = 113 };
+void cblas_sgemm(int layout, int transa, int transb, int m, int n, int k, float alpha, const float *a, int lda,
+                 const float *b, int ldb, float beta, float *c, int ldc);
+void cblas_dgemm(int layout, int transa, int transb, int m, int n, int k, double alpha, const double *a, int lda,
+                 const double *b, int ldb, double beta, double *c, int ldc);
+float cblas_sdot(int n, const float *x, int incx, const float *y, int incy);
+double cblas_ddot(int n, const double *x, int incx, const double *y, int incy);
+
+/* ---- host-buffer convenience (end-to-end path) ----------------------------------
+ * Same semantics as ndb_zip but every view's `ptr` is a HOST pointer (pinned for full speed);
+ * inputs are copied H2D, the op runs, the output is copied D2H, chunked along the outermost
+ * axis so copies in both directions overlap the kernel.  Synchronous. */
+int ndb_zip_host(ndb_ctx *ctx, int op, const void *scalars, int n_parts, const ndb_view *parts);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NDB200_H */

@@ -1,0 +1,99 @@
+// Internal declarations shared by the translation units of libndb200.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include <atomic>
+#include <string>
+
+#include "../../include/ndb200.h"
+
+namespace ndb {
+
+// ---- error plumbing ---------------------------------------------------------
+void set_error(const char *fmt, ...);
+void clear_error();
+extern std::atomic<uint64_t> g_launches;
+
+inline int cuda_fail(cudaError_t e, const char *what, const char *file, int line)
+{
+    set_error("CUDA error %d (%s) at %s:%d: %s", (int)e, cudaGetErrorString(e), file, line, what);
+    return NDB_ERR_CUDA;
+}
+
+#define NDB_CUDA(call)                                                     \
+    do {                                                                   \
+        cudaError_t e_ = (call);                                           \
+        if (e_ != cudaSuccess) return ::ndb::cuda_fail(e_, #call, __FILE__, __LINE__); \
+    } while (0)
+
+#define NDB_CHECK_LAUNCH()                                                 \
+    do {                                                                   \
+        ::ndb::g_launches.fetch_add(1, std::memory_order_relaxed);         \
+        cudaError_t e_ = cudaGetLastError();                               \
+        if (e_ != cudaSuccess) return ::ndb::cuda_fail(e_, "kernel launch", __FILE__, __LINE__); \
+    } while (0)
+
+#define NDB_TRY(expr)                  \
+    do {                               \
+        int st_ = (expr);              \
+        if (st_ != NDB_OK) return st_; \
+    } while (0)
+
+inline size_t dtype_size(int dt)
+{
+    switch (dt) {
+    case NDB_F32: return 4;
+    case NDB_F64: return 8;
+    case NDB_I32: return 4;
+    case NDB_I64: return 8;
+    default: return 0;
+    }
+}
+
+inline bool dtype_is_float(int dt) { return dt == NDB_F32 || dt == NDB_F64; }
+
+// number of *input* producers an op consumes (ADD_N: variable, returns -1)
+int op_arity(int op);
+// number of scalars the op reads
+int op_scalars(int op);
+
+int validate_view(const ndb_view *v, const char *what);
+
+}  // namespace ndb
+
+// ---- context ------------------------------------------------------------------
+struct ndb_ctx {
+    int device = 0;
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t stream = nullptr;  // the one in use
+    void *workspace = nullptr;      // device scratch for reduction partials
+    size_t workspace_bytes = 0;
+    int *dev_flag = nullptr;        // device int: set by kernels that detect a Rust-panic condition
+    int *host_flag = nullptr;       // pinned mirror
+    void *host_scalar = nullptr;    // pinned 64-byte buffer for scalar results
+    int sm_count = 148;
+    // staging buffers for the host-pointer (end-to-end / cblas) entry points
+    void *stage[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    size_t stage_bytes[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    cudaStream_t copy_in = nullptr, copy_out = nullptr;
+};
+
+namespace ndb {
+int ensure_workspace(ndb_ctx *ctx, size_t bytes);
+int ensure_stage(ndb_ctx *ctx, int slot, size_t bytes);
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = true;
+    explicit DeviceGuard(int dev)
+    {
+        if (cudaGetDevice(&prev) != cudaSuccess) { ok = false; return; }
+        if (prev != dev && cudaSetDevice(dev) != cudaSuccess) ok = false;
+    }
+    ~DeviceGuard()
+    {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+}  // namespace ndb

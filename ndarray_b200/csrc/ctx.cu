@@ -1,0 +1,304 @@
+// Context, memory, events and error plumbing of libndb200.
+#include <stdarg.h>
+
+#include "common.h"
+
+namespace ndb {
+
+static thread_local char tl_error[1024] = "";
+std::atomic<uint64_t> g_launches{0};
+
+void set_error(const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(tl_error, sizeof(tl_error), fmt, ap);
+    va_end(ap);
+}
+
+void clear_error() { tl_error[0] = 0; }
+
+int op_arity(int op)
+{
+    switch (op) {
+    case NDB_OP_FILL: return 0;
+    case NDB_OP_COPY:
+    case NDB_OP_ADD_S:
+    case NDB_OP_SUB_S:
+    case NDB_OP_MUL_S:
+    case NDB_OP_DIV_S:
+    case NDB_OP_REM_S:
+    case NDB_OP_RSUB_S:
+    case NDB_OP_RDIV_S:
+    case NDB_OP_NEG:
+    case NDB_OP_ABS:
+    case NDB_OP_SQRT: return 1;
+    case NDB_OP_ADD:
+    case NDB_OP_SUB:
+    case NDB_OP_MUL:
+    case NDB_OP_DIV:
+    case NDB_OP_REM:
+    case NDB_OP_AXPY:
+    case NDB_OP_MIN:
+    case NDB_OP_MAX:
+    case NDB_OP_SCALE_ADD: return 2;
+    case NDB_OP_MUL_ADD: return 3;
+    case NDB_OP_ADD_N: return -1;
+    default: return -2;
+    }
+}
+
+int op_scalars(int op)
+{
+    switch (op) {
+    case NDB_OP_FILL:
+    case NDB_OP_ADD_S:
+    case NDB_OP_SUB_S:
+    case NDB_OP_MUL_S:
+    case NDB_OP_DIV_S:
+    case NDB_OP_REM_S:
+    case NDB_OP_RSUB_S:
+    case NDB_OP_RDIV_S:
+    case NDB_OP_AXPY: return 1;
+    case NDB_OP_SCALE_ADD: return 2;
+    default: return 0;
+    }
+}
+
+int validate_view(const ndb_view *v, const char *what)
+{
+    if (!v) {
+        set_error("%s: null view", what);
+        return NDB_ERR_INVALID_ARG;
+    }
+    if (v->ndim < 0 || v->ndim > NDB_MAX_NDIM) {
+        set_error("%s: ndim %d outside 0..%d", what, v->ndim, NDB_MAX_NDIM);
+        return NDB_ERR_UNSUPPORTED;
+    }
+    if (dtype_size(v->dtype) == 0) {
+        set_error("%s: unknown dtype %d", what, v->dtype);
+        return NDB_ERR_UNSUPPORTED;
+    }
+    for (int i = 0; i < v->ndim; ++i) {
+        if (v->dim[i] < 0) {
+            set_error("%s: negative axis length", what);
+            return NDB_ERR_INVALID_ARG;
+        }
+    }
+    return NDB_OK;
+}
+
+int ensure_workspace(ndb_ctx *ctx, size_t bytes)
+{
+    if (ctx->workspace_bytes >= bytes) return NDB_OK;
+    // Growing must not race with kernels still using the old buffer.
+    NDB_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (ctx->workspace) NDB_CUDA(cudaFree(ctx->workspace));
+    ctx->workspace = nullptr;
+    ctx->workspace_bytes = 0;
+    size_t want = bytes < (size_t(8) << 20) ? (size_t(8) << 20) : bytes;
+    NDB_CUDA(cudaMalloc(&ctx->workspace, want));
+    ctx->workspace_bytes = want;
+    return NDB_OK;
+}
+
+int ensure_stage(ndb_ctx *ctx, int slot, size_t bytes)
+{
+    if (ctx->stage_bytes[slot] >= bytes) return NDB_OK;
+    NDB_CUDA(cudaDeviceSynchronize());
+    if (ctx->stage[slot]) NDB_CUDA(cudaFree(ctx->stage[slot]));
+    ctx->stage[slot] = nullptr;
+    ctx->stage_bytes[slot] = 0;
+    NDB_CUDA(cudaMalloc(&ctx->stage[slot], bytes));
+    ctx->stage_bytes[slot] = bytes;
+    return NDB_OK;
+}
+
+}  // namespace ndb
+
+using namespace ndb;
+
+extern "C" {
+
+const char *ndb_version(void) { return "ndb200 0.1.0 (sm_100a)"; }
+
+const char *ndb_last_error(void) { return tl_error; }
+
+uint64_t ndb_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+int ndb_device_count(int *count)
+{
+    if (!count) return NDB_ERR_INVALID_ARG;
+    *count = 0;
+    NDB_CUDA(cudaGetDeviceCount(count));
+    return NDB_OK;
+}
+
+int ndb_ctx_create(int device, ndb_ctx **out)
+{
+    if (!out) return NDB_ERR_INVALID_ARG;
+    *out = nullptr;
+    int n = 0;
+    NDB_CUDA(cudaGetDeviceCount(&n));
+    if (device < 0 || device >= n) {
+        set_error("ndb_ctx_create: device %d not in 0..%d (no CPU fallback exists)", device, n);
+        return NDB_ERR_CUDA;
+    }
+    NDB_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    NDB_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) {
+        set_error("ndb_ctx_create: device %d is sm_%d%d; this library carries sm_100a code only", device, prop.major,
+                  prop.minor);
+        return NDB_ERR_CUDA;
+    }
+    ndb_ctx *ctx = new ndb_ctx();
+    ctx->device = device;
+    ctx->sm_count = prop.multiProcessorCount;
+    NDB_CUDA(cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking));
+    NDB_CUDA(cudaStreamCreateWithFlags(&ctx->copy_in, cudaStreamNonBlocking));
+    NDB_CUDA(cudaStreamCreateWithFlags(&ctx->copy_out, cudaStreamNonBlocking));
+    ctx->stream = ctx->own_stream;
+    NDB_CUDA(cudaMalloc((void **)&ctx->dev_flag, sizeof(int)));
+    NDB_CUDA(cudaMemset(ctx->dev_flag, 0, sizeof(int)));
+    NDB_CUDA(cudaMallocHost((void **)&ctx->host_flag, sizeof(int)));
+    NDB_CUDA(cudaMallocHost(&ctx->host_scalar, 64));
+    *ctx->host_flag = 0;
+    int st = ensure_workspace(ctx, size_t(8) << 20);
+    if (st != NDB_OK) return st;
+    *out = ctx;
+    return NDB_OK;
+}
+
+int ndb_ctx_destroy(ndb_ctx *ctx)
+{
+    if (!ctx) return NDB_OK;
+    DeviceGuard g(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    if (ctx->workspace) cudaFree(ctx->workspace);
+    for (int i = 0; i < 8; ++i)
+        if (ctx->stage[i]) cudaFree(ctx->stage[i]);
+    if (ctx->dev_flag) cudaFree(ctx->dev_flag);
+    if (ctx->host_flag) cudaFreeHost(ctx->host_flag);
+    if (ctx->host_scalar) cudaFreeHost(ctx->host_scalar);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+    if (ctx->copy_in) cudaStreamDestroy(ctx->copy_in);
+    if (ctx->copy_out) cudaStreamDestroy(ctx->copy_out);
+    delete ctx;
+    return NDB_OK;
+}
+
+int ndb_ctx_set_stream(ndb_ctx *ctx, void *cuda_stream)
+{
+    if (!ctx) return NDB_ERR_INVALID_ARG;
+    ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+    return NDB_OK;
+}
+
+void *ndb_ctx_stream(ndb_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
+
+int ndb_sync(ndb_ctx *ctx)
+{
+    if (!ctx) return NDB_ERR_INVALID_ARG;
+    DeviceGuard g(ctx->device);
+    NDB_CUDA(cudaStreamSynchronize(ctx->stream));
+    return NDB_OK;
+}
+
+int ndb_alloc(ndb_ctx *ctx, size_t bytes, void **dptr)
+{
+    if (!ctx || !dptr) return NDB_ERR_INVALID_ARG;
+    DeviceGuard g(ctx->device);
+    *dptr = nullptr;
+    if (bytes == 0) bytes = 16;  // a valid, dereferenceable-by-nobody pointer for empty arrays
+    NDB_CUDA(cudaMalloc(dptr, bytes));
+    return NDB_OK;
+}
+
+int ndb_free(ndb_ctx *ctx, void *dptr)
+{
+    if (!ctx) return NDB_ERR_INVALID_ARG;
+    if (!dptr) return NDB_OK;
+    DeviceGuard g(ctx->device);
+    NDB_CUDA(cudaFree(dptr));
+    return NDB_OK;
+}
+
+int ndb_memset(ndb_ctx *ctx, void *dptr, int byte, size_t bytes)
+{
+    if (!ctx) return NDB_ERR_INVALID_ARG;
+    DeviceGuard g(ctx->device);
+    if (bytes) NDB_CUDA(cudaMemsetAsync(dptr, byte, bytes, ctx->stream));
+    return NDB_OK;
+}
+
+int ndb_h2d(ndb_ctx *ctx, void *dst_dev, const void *src_host, size_t bytes)
+{
+    if (!ctx) return NDB_ERR_INVALID_ARG;
+    DeviceGuard g(ctx->device);
+    if (bytes) NDB_CUDA(cudaMemcpyAsync(dst_dev, src_host, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    return NDB_OK;
+}
+
+int ndb_d2h(ndb_ctx *ctx, void *dst_host, const void *src_dev, size_t bytes)
+{
+    if (!ctx) return NDB_ERR_INVALID_ARG;
+    DeviceGuard g(ctx->device);
+    if (bytes) NDB_CUDA(cudaMemcpyAsync(dst_host, src_dev, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    return NDB_OK;
+}
+
+int ndb_d2d(ndb_ctx *ctx, void *dst_dev, const void *src_dev, size_t bytes)
+{
+    if (!ctx) return NDB_ERR_INVALID_ARG;
+    DeviceGuard g(ctx->device);
+    if (bytes) NDB_CUDA(cudaMemcpyAsync(dst_dev, src_dev, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+    return NDB_OK;
+}
+
+int ndb_host_alloc(size_t bytes, void **hptr)
+{
+    if (!hptr) return NDB_ERR_INVALID_ARG;
+    *hptr = nullptr;
+    NDB_CUDA(cudaMallocHost(hptr, bytes ? bytes : 16));
+    return NDB_OK;
+}
+
+int ndb_host_free(void *hptr)
+{
+    if (hptr) NDB_CUDA(cudaFreeHost(hptr));
+    return NDB_OK;
+}
+
+int ndb_event_create(void **ev)
+{
+    if (!ev) return NDB_ERR_INVALID_ARG;
+    cudaEvent_t e;
+    NDB_CUDA(cudaEventCreate(&e));
+    *ev = (void *)e;
+    return NDB_OK;
+}
+
+int ndb_event_destroy(void *ev)
+{
+    if (ev) NDB_CUDA(cudaEventDestroy((cudaEvent_t)ev));
+    return NDB_OK;
+}
+
+int ndb_event_record(ndb_ctx *ctx, void *ev)
+{
+    if (!ctx || !ev) return NDB_ERR_INVALID_ARG;
+    DeviceGuard g(ctx->device);
+    NDB_CUDA(cudaEventRecord((cudaEvent_t)ev, ctx->stream));
+    return NDB_OK;
+}
+
+int ndb_event_elapsed_ms(void *start, void *stop, float *ms)
+{
+    if (!start || !stop || !ms) return NDB_ERR_INVALID_ARG;
+    NDB_CUDA(cudaEventSynchronize((cudaEvent_t)stop));
+    NDB_CUDA(cudaEventElapsedTime(ms, (cudaEvent_t)start, (cudaEvent_t)stop));
+    return NDB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,376 @@
+// general_mat_mul / general_mat_vec_mul front-end (reference src/linalg/impl_linalg.rs:633-743) and the
+// CBLAS drop-in symbols (impl_linalg.rs:466-491, :116-122).
+//
+// Dispatch:
+//   f64, large      -> gemm_f64.cu  (FP64 tensor-core DMMA, cp.async pipeline)
+//   f32, large      -> gemm_f32.cu  (3xTF32 on tcgen05 / TMEM)
+//   everything else -> gemm_any below: a shared-memory tiled kernel that takes ANY signed strides and
+//                      element type (ndarray's own fallback for non-BLAS types is a naive i,j,k loop,
+//                      impl_linalg.rs:601-617; integers wrap).
+#include <mutex>
+
+#include "gemm.h"
+#include "zip_kernels.cuh"
+
+namespace ndb {
+
+template <typename T>
+__device__ __forceinline__ T mul_add(T a, T b, T c)
+{
+    if constexpr (std::is_same<T, float>::value) return fmaf(a, b, c);
+    else if constexpr (std::is_same<T, double>::value) return fma(a, b, c);
+    else return w_add(w_mul(a, b), c);
+}
+
+// 64x64 output tile, K step 16, 256 threads, 4x4 outputs per thread.
+template <typename T>
+__global__ void __launch_bounds__(256) gemm_any(GemmArgs g, T alpha, T beta)
+{
+    constexpr int BM = 64, BN = 64, BK = 16;
+    __shared__ T As[BK][BM + 1];
+    __shared__ T Bs[BK][BN + 1];
+    const T *A = reinterpret_cast<const T *>(g.a);
+    const T *B = reinterpret_cast<const T *>(g.b);
+    T *Cm = reinterpret_cast<T *>(g.c);
+    const int64_t m0 = (int64_t)blockIdx.y * BM, n0 = (int64_t)blockIdx.x * BN;
+    const int tid = threadIdx.x;
+    const int tr = tid / 16, tc = tid % 16;  // thread's 4x4 block: rows tr*4.., cols tc*4..
+    T acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = T(0);
+    // loader index maps: walk whichever axis of the operand is denser with consecutive threads
+    const bool a_k_fast = llabs(g.csa) <= llabs(g.rsa);
+    const bool b_n_fast = llabs(g.csb) <= llabs(g.rsb);
+    for (int64_t k0 = 0; k0 < g.k; k0 += BK) {
+#pragma unroll
+        for (int l = 0; l < 4; ++l) {
+            const int e = tid + l * 256;  // 0..1023
+            int mm, kk;
+            if (a_k_fast) {
+                kk = e % BK;
+                mm = e / BK;
+            } else {
+                mm = e % BM;
+                kk = e / BM;
+            }
+            const int64_t gm = m0 + mm, gk = k0 + kk;
+            As[kk][mm] = (gm < g.m && gk < g.k) ? A[gm * g.rsa + gk * g.csa] : T(0);
+            int nn, kb;
+            if (b_n_fast) {
+                nn = e % BN;
+                kb = e / BN;
+            } else {
+                kb = e % BK;
+                nn = e / BK;
+            }
+            const int64_t gn = n0 + nn, gkb = k0 + kb;
+            Bs[kb][nn] = (gn < g.n && gkb < g.k) ? B[gkb * g.rsb + gn * g.csb] : T(0);
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < BK; ++kk) {
+            T av[4], bv[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) av[i] = As[kk][tr * 4 + i];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) bv[j] = Bs[kk][tc * 4 + j];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = mul_add(av[i], bv[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int64_t gm = m0 + tr * 4 + i;
+        if (gm >= g.m) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int64_t gn = n0 + tc * 4 + j;
+            if (gn >= g.n) continue;
+            T *dst = Cm + gm * g.rsc + gn * g.csc;
+            // beta == 0: C is never read (impl_linalg.rs:323-329 hands in uninitialised memory)
+            if (beta == T(0)) *dst = w_mul(alpha, acc[i][j]);
+            else *dst = w_add(w_mul(alpha, acc[i][j]), w_mul(beta, *dst));
+        }
+    }
+}
+
+// C <- beta * C  (k == 0, or alpha == 0)
+template <typename T>
+__global__ void __launch_bounds__(256) scale_c(GemmArgs g, T beta)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= g.m * g.n) return;
+    const int64_t r = i / g.n, c = i - r * g.n;
+    T *dst = reinterpret_cast<T *>(g.c) + r * g.rsc + c * g.csc;
+    *dst = beta == T(0) ? T(0) : w_mul(beta, *dst);
+}
+
+template <typename T>
+static int gemm_any_launch(ndb_ctx *ctx, const GemmArgs &g, T alpha, T beta)
+{
+    if (g.k == 0) {
+        scale_c<T><<<(unsigned)((g.m * g.n + 255) / 256), 256, 0, ctx->stream>>>(g, beta);
+        NDB_CHECK_LAUNCH();
+        return NDB_OK;
+    }
+    dim3 grid((unsigned)((g.n + 63) / 64), (unsigned)((g.m + 63) / 64), 1);
+    if (grid.y > 65535) {
+        set_error("gemm: m = %lld exceeds the fallback kernel's grid", (long long)g.m);
+        return NDB_ERR_UNSUPPORTED;
+    }
+    gemm_any<T><<<grid, 256, 0, ctx->stream>>>(g, alpha, beta);
+    NDB_CHECK_LAUNCH();
+    return NDB_OK;
+}
+
+static int gemm_impl(ndb_ctx *ctx, const void *alpha, const ndb_view *a, const ndb_view *b, const void *beta,
+                     const ndb_view *c)
+{
+    if (!ctx) {
+        set_error("gemm: null context (no CPU fallback exists)");
+        return NDB_ERR_INVALID_ARG;
+    }
+    if (!alpha || !beta) return NDB_ERR_INVALID_ARG;
+    NDB_TRY(validate_view(a, "gemm lhs"));
+    NDB_TRY(validate_view(b, "gemm rhs"));
+    NDB_TRY(validate_view(c, "gemm out"));
+    if (a->ndim != 2 || b->ndim != 2 || c->ndim != 2) {
+        set_error("general_mat_mul: operands must be 2-d");
+        return NDB_ERR_INCOMPATIBLE_SHAPE;
+    }
+    const int64_t m = a->dim[0], k = a->dim[1], k2 = b->dim[0], n = b->dim[1];
+    if (k != k2 || c->dim[0] != m || c->dim[1] != n) {
+        // general_dot_shape_error (impl_linalg.rs:351-355)
+        set_error("ndarray: inputs %lld × %lld, %lld × %lld, and output %lld × %lld are not compatible for matrix "
+                  "multiplication",
+                  (long long)m, (long long)k, (long long)k2, (long long)n, (long long)c->dim[0], (long long)c->dim[1]);
+        return NDB_ERR_INCOMPATIBLE_SHAPE;
+    }
+    if (a->dtype != b->dtype || a->dtype != c->dtype) {
+        set_error("general_mat_mul: mixed element types");
+        return NDB_ERR_UNSUPPORTED;
+    }
+    if (m == 0 || n == 0) return NDB_OK;  // zero-sized output (tests/oper.rs:464-483)
+    // the written operand may not alias itself
+    if ((m > 1 && c->stride[0] == 0) || (n > 1 && c->stride[1] == 0)) {
+        set_error("general_mat_mul: output has a zero stride");
+        return NDB_ERR_ALIASING;
+    }
+    GemmArgs g;
+    g.a = (const char *)a->ptr;
+    g.b = (const char *)b->ptr;
+    g.c = (char *)c->ptr;
+    g.m = m;
+    g.n = n;
+    g.k = k;
+    g.rsa = a->stride[0];
+    g.csa = a->stride[1];
+    g.rsb = b->stride[0];
+    g.csb = b->stride[1];
+    g.rsc = c->stride[0];
+    g.csc = c->stride[1];
+    DeviceGuard guard(ctx->device);
+    switch (a->dtype) {
+    case NDB_F64: {
+        const double al = *(const double *)alpha, be = *(const double *)beta;
+        if (k > 0 && gemm_f64_eligible(g)) return gemm_f64_launch(ctx, g, al, be);
+        return gemm_any_launch<double>(ctx, g, al, be);
+    }
+    case NDB_F32: {
+        const float al = *(const float *)alpha, be = *(const float *)beta;
+        if (k > 0 && gemm_f32_eligible(g)) return gemm_f32_launch(ctx, g, al, be);
+        return gemm_any_launch<float>(ctx, g, al, be);
+    }
+    case NDB_I32: return gemm_any_launch<int32_t>(ctx, g, *(const int32_t *)alpha, *(const int32_t *)beta);
+    case NDB_I64: return gemm_any_launch<int64_t>(ctx, g, *(const int64_t *)alpha, *(const int64_t *)beta);
+    }
+    return NDB_ERR_UNSUPPORTED;
+}
+
+// ---- process-global context for the CBLAS symbols ------------------------------------------------
+static std::mutex g_blas_mu;
+static ndb_ctx *g_blas_ctx = nullptr;
+
+static ndb_ctx *blas_ctx()
+{
+    std::lock_guard<std::mutex> lk(g_blas_mu);
+    if (!g_blas_ctx) {
+        int dev = 0;
+        if (const char *e = getenv("NDB_DEVICE")) dev = atoi(e);
+        if (ndb_ctx_create(dev, &g_blas_ctx) != NDB_OK) {
+            fprintf(stderr, "libndb200: cblas entry point called but no usable B200: %s\n", ndb_last_error());
+            g_blas_ctx = nullptr;
+        }
+    }
+    return g_blas_ctx;
+}
+
+// One matrix operand as CBLAS describes it -> (rows, cols, row stride, col stride) of op(X)
+struct BlasMat {
+    int64_t rows, cols, rs, cs;
+    int64_t span;  // elements to move
+};
+
+static BlasMat blas_operand(int layout, int trans, int64_t rows, int64_t cols, int64_t ld)
+{
+    // stored matrix before op(): op(X) is rows x cols
+    const bool t = trans != NdbCblasNoTrans;
+    const int64_t sr = t ? cols : rows, sc = t ? rows : cols;  // stored dims
+    int64_t rs, cs;
+    if (layout == NdbCblasRowMajor) {
+        rs = ld;
+        cs = 1;
+    } else {
+        rs = 1;
+        cs = ld;
+    }
+    BlasMat o;
+    o.rows = rows;
+    o.cols = cols;
+    if (t) {
+        o.rs = cs;
+        o.cs = rs;
+    } else {
+        o.rs = rs;
+        o.cs = cs;
+    }
+    const int64_t major = layout == NdbCblasRowMajor ? sr : sc;
+    const int64_t minor = layout == NdbCblasRowMajor ? sc : sr;
+    o.span = major > 0 ? (major - 1) * ld + minor : 0;
+    return o;
+}
+
+template <typename T>
+static void cblas_gemm_impl(int dtype, int layout, int transa, int transb, int m, int n, int k, T alpha, const T *a, int lda,
+                            const T *b, int ldb, T beta, T *c, int ldc)
+{
+    ndb_ctx *ctx = blas_ctx();
+    if (!ctx) abort();  // a void CBLAS call has no error channel; never compute wrong results silently
+    std::lock_guard<std::mutex> lk(g_blas_mu);
+    DeviceGuard guard(ctx->device);
+    const BlasMat A = blas_operand(layout, transa, m, k, lda);
+    const BlasMat B = blas_operand(layout, transb, k, n, ldb);
+    const BlasMat Cm = blas_operand(layout, NdbCblasNoTrans, m, n, ldc);
+    if (m == 0 || n == 0) return;
+    bool ok = ensure_stage(ctx, 0, std::max<size_t>(16, A.span * sizeof(T))) == NDB_OK &&
+              ensure_stage(ctx, 1, std::max<size_t>(16, B.span * sizeof(T))) == NDB_OK &&
+              ensure_stage(ctx, 2, std::max<size_t>(16, Cm.span * sizeof(T))) == NDB_OK;
+    if (ok && A.span) ok = cudaMemcpyAsync(ctx->stage[0], a, A.span * sizeof(T), cudaMemcpyHostToDevice, ctx->stream) == cudaSuccess;
+    if (ok && B.span) ok = cudaMemcpyAsync(ctx->stage[1], b, B.span * sizeof(T), cudaMemcpyHostToDevice, ctx->stream) == cudaSuccess;
+    // C travels up even for beta == 0 when it has padding (ldc > minor), so the padding survives the trip back
+    const bool c_dense = (layout == NdbCblasRowMajor ? ldc == n : ldc == m);
+    if (ok && (beta != T(0) || !c_dense))
+        ok = cudaMemcpyAsync(ctx->stage[2], c, Cm.span * sizeof(T), cudaMemcpyHostToDevice, ctx->stream) == cudaSuccess;
+    ndb_view va, vb, vc;
+    memset(&va, 0, sizeof(va));
+    memset(&vb, 0, sizeof(vb));
+    memset(&vc, 0, sizeof(vc));
+    va.ptr = ctx->stage[0]; va.ndim = 2; va.dtype = dtype; va.dim[0] = m; va.dim[1] = k; va.stride[0] = A.rs; va.stride[1] = A.cs;
+    vb.ptr = ctx->stage[1]; vb.ndim = 2; vb.dtype = dtype; vb.dim[0] = k; vb.dim[1] = n; vb.stride[0] = B.rs; vb.stride[1] = B.cs;
+    vc.ptr = ctx->stage[2]; vc.ndim = 2; vc.dtype = dtype; vc.dim[0] = m; vc.dim[1] = n; vc.stride[0] = Cm.rs; vc.stride[1] = Cm.cs;
+    if (ok) ok = gemm_impl(ctx, &alpha, &va, &vb, &beta, &vc) == NDB_OK;
+    if (ok) ok = cudaMemcpyAsync(c, ctx->stage[2], Cm.span * sizeof(T), cudaMemcpyDeviceToHost, ctx->stream) == cudaSuccess;
+    if (ok) ok = cudaStreamSynchronize(ctx->stream) == cudaSuccess;
+    if (!ok) {
+        fprintf(stderr, "libndb200: cblas gemm failed: %s\n", ndb_last_error());
+        abort();
+    }
+}
+
+template <typename T>
+static T cblas_dot_impl(int dtype, int n, const T *x, int incx, const T *y, int incy)
+{
+    ndb_ctx *ctx = blas_ctx();
+    if (!ctx) abort();
+    if (n <= 0) return T(0);
+    std::lock_guard<std::mutex> lk(g_blas_mu);
+    DeviceGuard guard(ctx->device);
+    // CBLAS passes the lowest address; a negative increment walks it from the far end (blas_1d_params,
+    // impl_linalg.rs:142-154 hands ndarray's views over in exactly this form).
+    const int64_t ax = llabs((int64_t)incx), ay = llabs((int64_t)incy);
+    const size_t sx = ((size_t)(n - 1) * ax + 1) * sizeof(T), sy = ((size_t)(n - 1) * ay + 1) * sizeof(T);
+    bool ok = ensure_stage(ctx, 0, sx) == NDB_OK && ensure_stage(ctx, 1, sy) == NDB_OK;
+    if (ok) ok = cudaMemcpyAsync(ctx->stage[0], x, sx, cudaMemcpyHostToDevice, ctx->stream) == cudaSuccess;
+    if (ok) ok = cudaMemcpyAsync(ctx->stage[1], y, sy, cudaMemcpyHostToDevice, ctx->stream) == cudaSuccess;
+    ndb_view vx, vy;
+    memset(&vx, 0, sizeof(vx));
+    memset(&vy, 0, sizeof(vy));
+    vx.ndim = vy.ndim = 1;
+    vx.dtype = vy.dtype = dtype;
+    vx.dim[0] = vy.dim[0] = n;
+    vx.stride[0] = incx;
+    vy.stride[0] = incy;
+    vx.ptr = (char *)ctx->stage[0] + (incx < 0 ? (int64_t)(n - 1) * ax * (int64_t)sizeof(T) : 0);
+    vy.ptr = (char *)ctx->stage[1] + (incy < 0 ? (int64_t)(n - 1) * ay * (int64_t)sizeof(T) : 0);
+    T out = T(0);
+    if (ok) ok = ndb_dot(ctx, &vx, &vy, &out) == NDB_OK;
+    if (!ok) {
+        fprintf(stderr, "libndb200: cblas dot failed: %s\n", ndb_last_error());
+        abort();
+    }
+    return out;
+}
+
+}  // namespace ndb
+
+using namespace ndb;
+
+extern "C" {
+
+int ndb_gemm(ndb_ctx *ctx, const void *alpha, const ndb_view *a, const ndb_view *b, const void *beta, const ndb_view *c)
+{
+    clear_error();
+    return gemm_impl(ctx, alpha, a, b, beta, c);
+}
+
+// general_mat_vec_mul (impl_linalg.rs:657-743): y <- alpha*A*x + beta*y, as the n == 1 case.
+int ndb_gemv(ndb_ctx *ctx, const void *alpha, const ndb_view *a, const ndb_view *x, const void *beta, const ndb_view *y)
+{
+    clear_error();
+    NDB_TRY(validate_view(a, "gemv matrix"));
+    NDB_TRY(validate_view(x, "gemv x"));
+    NDB_TRY(validate_view(y, "gemv y"));
+    if (a->ndim != 2 || x->ndim != 1 || y->ndim != 1 || a->dim[1] != x->dim[0] || a->dim[0] != y->dim[0]) {
+        set_error("ndarray: inputs %lld × %lld and %lld × 1 and output %lld × 1 are not compatible for matrix multiplication",
+                  (long long)(a->ndim == 2 ? a->dim[0] : -1), (long long)(a->ndim == 2 ? a->dim[1] : -1),
+                  (long long)(x->ndim == 1 ? x->dim[0] : -1), (long long)(y->ndim == 1 ? y->dim[0] : -1));
+        return NDB_ERR_INCOMPATIBLE_SHAPE;
+    }
+    ndb_view xb = *x, yc = *y;
+    xb.ndim = 2;
+    xb.dim[1] = 1;
+    xb.stride[1] = 1;
+    yc.ndim = 2;
+    yc.dim[1] = 1;
+    yc.stride[1] = 1;
+    return gemm_impl(ctx, alpha, a, &xb, beta, &yc);
+}
+
+void cblas_sgemm(int layout, int transa, int transb, int m, int n, int k, float alpha, const float *a, int lda,
+                 const float *b, int ldb, float beta, float *c, int ldc)
+{
+    cblas_gemm_impl<float>(NDB_F32, layout, transa, transb, m, n, k, alpha, a, lda, b, ldb, beta, c, ldc);
+}
+
+void cblas_dgemm(int layout, int transa, int transb, int m, int n, int k, double alpha, const double *a, int lda,
+                 const double *b, int ldb, double beta, double *c, int ldc)
+{
+    cblas_gemm_impl<double>(NDB_F64, layout, transa, transb, m, n, k, alpha, a, lda, b, ldb, beta, c, ldc);
+}
+
+float cblas_sdot(int n, const float *x, int incx, const float *y, int incy)
+{
+    return cblas_dot_impl<float>(NDB_F32, n, x, incx, y, incy);
+}
+
+double cblas_ddot(int n, const double *x, int incx, const double *y, int incy)
+{
+    return cblas_dot_impl<double>(NDB_F64, n, x, incx, y, incy);
+}
+
+}  // extern "C"

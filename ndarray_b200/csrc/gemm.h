@@ -1,0 +1,21 @@
+#pragma once
+#include "common.h"
+
+namespace ndb {
+
+// C[m,n] <- alpha * A[m,k] * B[k,n] + beta * C, signed element strides (row stride, column stride),
+// exactly the parameter set of matrixmultiply::{s,d}gemm (reference src/linalg/impl_linalg.rs:512-546).
+struct GemmArgs {
+    const char *a;
+    const char *b;
+    char *c;
+    int64_t m, n, k;
+    int64_t rsa, csa, rsb, csb, rsc, csc;
+};
+
+bool gemm_f64_eligible(const GemmArgs &g);
+int gemm_f64_launch(ndb_ctx *ctx, const GemmArgs &g, double alpha, double beta);
+bool gemm_f32_eligible(const GemmArgs &g);
+int gemm_f32_launch(ndb_ctx *ctx, const GemmArgs &g, float alpha, float beta);
+
+}  // namespace ndb

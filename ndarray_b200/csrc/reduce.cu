@@ -1,0 +1,1056 @@
+// Reductions for sm_100a: sum / product / min / max over a whole view, and along one axis
+// (sum_axis, product_axis, mean_axis, var_axis, std_axis, fold_axis with an associative closure).
+//
+// ndarray (src/numeric/impl_numeric.rs:32-47,268-283,342-355,401-425; src/impl_methods.rs:3130-3141) runs
+// these on one core: an 8-accumulator unrolled fold per contiguous lane, or a sequential pass over
+// subviews.  Here every reduction is a tree: registers -> warp shuffles -> shared memory -> (when the
+// reduced axis is split across blocks) a second, ordered pass over per-block partial states.  All
+// shapes of tree are fixed by the problem size alone, so results are run-to-run deterministic.
+//
+// Kernel classes
+//   red_lanes   the reduced axis is the densest axis of the input (|stride| smallest): a warp or a
+//               block walks each lane with coalesced (optionally 128-bit) loads.
+//   red_cols    a KEPT axis is unit-stride: threads own output columns and stride down the reduced
+//               axis; the reduced axis is additionally split over blockIdx.y so that 16384 columns
+//               still fill 148 SMs; partial states are merged in split order by red_finish.
+//   red_generic one thread per output, any strides (correctness net).
+//   red_all_*   whole-view reduction: grid-stride partials + red_finish.
+// var_axis/std_axis use a fused single-pass Welford per thread and Chan's pairwise merge up the tree.
+#include <algorithm>
+#include <cmath>
+#include <cstdlib>
+#include <type_traits>
+#include <vector>
+
+#include "zip_kernels.cuh"  // w_add & friends, Vec128
+#include "zip_plan.h"
+
+namespace ndb {
+
+enum { R_SUM = 0, R_PROD = 1, R_MIN = 2, R_MAX = 3, R_WELFORD = 4 };
+enum { FIN_NONE = 0, FIN_MEAN = 1, FIN_VAR = 2, FIN_STD = 3, FIN_WELFORD_RAW = 4 };
+
+template <typename T>
+struct WelfordState {
+    T n, mean, m2;
+};
+
+template <typename T, int R>
+struct Reducer {
+    using State = T;
+    __device__ __forceinline__ static State init()
+    {
+        if constexpr (R == R_SUM) return T(0);
+        else if constexpr (R == R_PROD) return T(1);
+        else return T(0);  // MIN/MAX seed from the first element, see `seeded`
+    }
+    __device__ __forceinline__ static void add(State &s, T x)
+    {
+        if constexpr (R == R_SUM) s = w_add(s, x);
+        else if constexpr (R == R_PROD) s = w_mul(s, x);
+        else if constexpr (R == R_MIN) s = w_min(s, x);
+        else s = w_max(s, x);
+    }
+    __device__ __forceinline__ static void merge(State &s, const State &o) { add(s, o); }
+    __device__ __forceinline__ static State shfl_down(const State &s, int d) { return __shfl_down_sync(0xffffffffu, s, d); }
+};
+
+template <typename T>
+struct Reducer<T, R_WELFORD> {
+    using State = WelfordState<T>;
+    __device__ __forceinline__ static State init() { return State{T(0), T(0), T(0)}; }
+    // one step of ndarray's loop (impl_numeric.rs:419-421), fused multiply-add included
+    __device__ __forceinline__ static void add(State &s, T x)
+    {
+        s.n += T(1);
+        const T delta = x - s.mean;
+        s.mean = s.mean + delta / s.n;
+        if constexpr (std::is_same<T, float>::value) s.m2 = fmaf(x - s.mean, delta, s.m2);
+        else s.m2 = fma(x - s.mean, delta, s.m2);
+    }
+    // Chan et al. pairwise combination
+    __device__ __forceinline__ static void merge(State &s, const State &o)
+    {
+        if (o.n == T(0)) return;
+        if (s.n == T(0)) {
+            s = o;
+            return;
+        }
+        const T n = s.n + o.n;
+        const T delta = o.mean - s.mean;
+        const T w = o.n / n;
+        s.mean = s.mean + delta * w;
+        s.m2 = s.m2 + o.m2 + delta * delta * (s.n * w);
+        s.n = n;
+    }
+    __device__ __forceinline__ static State shfl_down(const State &s, int d)
+    {
+        State r;
+        r.n = __shfl_down_sync(0xffffffffu, s.n, d);
+        r.mean = __shfl_down_sync(0xffffffffu, s.mean, d);
+        r.m2 = __shfl_down_sync(0xffffffffu, s.m2, d);
+        return r;
+    }
+};
+
+// MIN/MAX have no identity that is safe for every dtype and NaN rule, so states carry "seeded by the
+// first element": every thread that owns at least one element starts from it; threads that own none
+// are skipped in merges via a validity flag folded into the tree.
+template <typename T, int R>
+struct Acc {
+    using Rd = Reducer<T, R>;
+    typename Rd::State s;
+    bool valid;
+    __device__ __forceinline__ void reset()
+    {
+        s = Rd::init();
+        valid = (R != R_MIN && R != R_MAX);
+    }
+    __device__ __forceinline__ void add(T x)
+    {
+        if constexpr (R == R_MIN || R == R_MAX) {
+            if (!valid) {
+                s = x;
+                valid = true;
+                return;
+            }
+        }
+        Rd::add(s, x);
+    }
+    __device__ __forceinline__ void merge(const Acc &o)
+    {
+        if constexpr (R == R_MIN || R == R_MAX) {
+            if (!o.valid) return;
+            if (!valid) {
+                s = o.s;
+                valid = true;
+                return;
+            }
+        }
+        Rd::merge(s, o.s);
+    }
+    __device__ __forceinline__ Acc shfl_down(int d) const
+    {
+        Acc r;
+        r.s = Rd::shfl_down(s, d);
+        r.valid = __shfl_down_sync(0xffffffffu, (int)valid, d) != 0;
+        return r;
+    }
+};
+
+template <typename T, int R>
+__device__ __forceinline__ Acc<T, R> warp_reduce(Acc<T, R> a)
+{
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        Acc<T, R> o = a.shfl_down(d);
+        a.merge(o);
+    }
+    return a;  // lane 0 holds the result; lanes merge in a fixed order
+}
+
+// Block-wide: every warp reduces, warp leaders park in shared memory, warp 0 finishes. Result valid in thread 0.
+template <typename T, int R>
+__device__ __forceinline__ Acc<T, R> block_reduce(Acc<T, R> a, Acc<T, R> *smem /* >= 32 entries */)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int nwarps = (blockDim.x + 31) >> 5;
+    a = warp_reduce(a);
+    if (lane == 0) smem[warp] = a;
+    __syncthreads();
+    if (warp == 0) {
+        Acc<T, R> b;
+        b.reset();
+        if (lane < nwarps) b = smem[lane];
+        b = warp_reduce(b);
+        a = b;
+    }
+    __syncthreads();
+    return a;
+}
+
+template <typename T, int R, int FIN>
+__device__ __forceinline__ T finalize(const Acc<T, R> &a, T nT, T dof)
+{
+    if constexpr (R == R_WELFORD) {
+        T v = a.s.m2 / dof;
+        if constexpr (FIN == FIN_STD) {
+            if constexpr (std::is_same<T, float>::value) v = sqrtf(v);
+            else v = sqrt(v);
+        }
+        return v;
+    } else if constexpr (FIN == FIN_MEAN) {
+        int dummy = 0;
+        return w_div(a.s, nT, &dummy);
+    } else {
+        return a.s;
+    }
+}
+
+// ---- kept-axes geometry ----------------------------------------------------------------------
+struct Kept {
+    int n;  // collapsed kept rank (>= 1)
+    int64_t dim[NDB_MAX_NDIM];
+    int64_t in_stride[NDB_MAX_NDIM];
+    int64_t out_stride[NDB_MAX_NDIM];
+    int64_t out2_stride[NDB_MAX_NDIM];
+};
+
+struct RedArgs {
+    const char *in;
+    char *out;
+    char *out2;  // FIN_WELFORD_RAW: second output (m2); `out` receives the mean
+    Kept k;
+    int64_t n_out;  // product of kept dims
+    int64_t n;      // length of the reduced axis
+    int64_t s;      // its stride, elements
+    double nT;      // n as the element type
+    double dof;     // n - ddof in the element type
+    int splits;     // red_cols: blocks along the reduced axis
+    void *partial;  // [splits][n_out] states
+};
+
+__device__ __forceinline__ void kept_offsets(const Kept &k, int64_t lin, int64_t &in_off, int64_t &out_off,
+                                             int64_t &out2_off)
+{
+    in_off = out_off = out2_off = 0;
+    for (int d = k.n - 1; d >= 0; --d) {
+        const int64_t q = lin / k.dim[d];
+        const int64_t i = lin - q * k.dim[d];
+        lin = q;
+        in_off += i * k.in_stride[d];
+        out_off += i * k.out_stride[d];
+        out2_off += i * k.out2_stride[d];
+    }
+}
+
+template <typename T, int R, int FIN>
+__device__ __forceinline__ void store_result(const RedArgs &a, const Acc<T, R> &acc, int64_t out_off, int64_t out2_off)
+{
+    if constexpr (FIN == FIN_WELFORD_RAW) {
+        reinterpret_cast<T *>(a.out)[out_off] = acc.s.mean;
+        reinterpret_cast<T *>(a.out2)[out2_off] = acc.s.m2;
+    } else {
+        reinterpret_cast<T *>(a.out)[out_off] = finalize<T, R, FIN>(acc, (T)a.nT, (T)a.dof);
+    }
+}
+
+// ---- lanes: reduced axis is the dense one -----------------------------------------------------
+// WARP=true: one warp per output (short lanes); else one block per output.
+template <typename T, int R, int FIN, bool WARP, bool VEC>
+__global__ void __launch_bounds__(256) red_lanes(RedArgs a)
+{
+    using V = Vec128<T>;
+    constexpr int N = V::N;
+    __shared__ Acc<T, R> smem[32];
+    const int lane = threadIdx.x & 31;
+    const int64_t groups = WARP ? (a.n_out + 7) / 8 : a.n_out;
+    for (int64_t g = blockIdx.x; g < groups; g += gridDim.x) {
+        const int64_t o = WARP ? g * 8 + (threadIdx.x >> 5) : g;
+        const bool live = o < a.n_out;
+        int64_t in_off = 0, out_off = 0, out2_off = 0;
+        if (live) kept_offsets(a.k, o, in_off, out_off, out2_off);
+        const T *src = reinterpret_cast<const T *>(a.in) + in_off;
+        const int tid = WARP ? lane : threadIdx.x;
+        const int nt = WARP ? 32 : blockDim.x;
+        Acc<T, R> acc;
+        acc.reset();
+        if (live) {
+            if constexpr (VEC) {
+                // a.s == 1, lanes 16-byte aligned, n % N == 0 (checked on the host)
+                const V *vsrc = reinterpret_cast<const V *>(src);
+                const int64_t nv = a.n / N;
+                int64_t i = tid;
+                for (; i + 3 * (int64_t)nt < nv; i += 4 * (int64_t)nt) {
+                    V v0 = vsrc[i], v1 = vsrc[i + nt], v2 = vsrc[i + 2 * nt], v3 = vsrc[i + 3 * nt];
+#pragma unroll
+                    for (int e = 0; e < N; ++e) acc.add(v0.v[e]);
+#pragma unroll
+                    for (int e = 0; e < N; ++e) acc.add(v1.v[e]);
+#pragma unroll
+                    for (int e = 0; e < N; ++e) acc.add(v2.v[e]);
+#pragma unroll
+                    for (int e = 0; e < N; ++e) acc.add(v3.v[e]);
+                }
+                for (; i < nv; i += nt) {
+                    V v0 = vsrc[i];
+#pragma unroll
+                    for (int e = 0; e < N; ++e) acc.add(v0.v[e]);
+                }
+            } else {
+                int64_t i = tid;
+                for (; i + 3 * (int64_t)nt < a.n; i += 4 * (int64_t)nt) {
+                    const T x0 = src[i * a.s], x1 = src[(i + nt) * a.s], x2 = src[(i + 2 * nt) * a.s],
+                            x3 = src[(i + 3 * nt) * a.s];
+                    acc.add(x0);
+                    acc.add(x1);
+                    acc.add(x2);
+                    acc.add(x3);
+                }
+                for (; i < a.n; i += nt) acc.add(src[i * a.s]);
+            }
+        }
+        if constexpr (WARP) {
+            acc = warp_reduce(acc);
+            if (live && lane == 0) store_result<T, R, FIN>(a, acc, out_off, out2_off);
+        } else {
+            acc = block_reduce(acc, smem);
+            if (threadIdx.x == 0) store_result<T, R, FIN>(a, acc, out_off, out2_off);
+        }
+    }
+}
+
+// ---- cols: a kept axis is unit-stride ------------------------------------------------------------
+// blockDim = (32, 8).  A block owns 32*W consecutive outputs along the last kept axis (in_stride 1) and
+// rows [split*chunk, ...) of the reduced axis; thread (tx, ty) strides rows ty, ty+8, ...
+template <typename T, int R, int FIN, int W>
+__global__ void __launch_bounds__(256) red_cols(RedArgs a)
+{
+    using V = Vec128<T>;
+    static_assert(W == 1 || W == V::N, "W is 1 or one 128-bit vector");
+    __shared__ Acc<T, R> smem[8][32 * W + 1];
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    const int last = a.k.n - 1;
+    const int64_t ncol = a.k.dim[last];
+    const int64_t tiles = (ncol + 32 * W - 1) / (32 * W);
+    const int64_t outer = a.n_out / ncol;
+    const int64_t total = tiles * outer;
+    const int split = blockIdx.y;
+    const int64_t chunk = (a.n + a.splits - 1) / a.splits;
+    const int64_t r0 = (int64_t)split * chunk;
+    const int64_t r1 = r0 + chunk < a.n ? r0 + chunk : a.n;
+    for (int64_t vb = blockIdx.x; vb < total; vb += gridDim.x) {
+        const int64_t o = vb / tiles;
+        const int64_t tile = vb - o * tiles;
+        // offsets of this outer index (all kept axes but the last)
+        int64_t in_off = 0, out_off = 0, out2_off = 0;
+        {
+            int64_t lin = o;
+            for (int d = last - 1; d >= 0; --d) {
+                const int64_t q = lin / a.k.dim[d];
+                const int64_t i = lin - q * a.k.dim[d];
+                lin = q;
+                in_off += i * a.k.in_stride[d];
+                out_off += i * a.k.out_stride[d];
+                out2_off += i * a.k.out2_stride[d];
+            }
+        }
+        const int64_t c0 = tile * (32 * W) + (int64_t)tx * W;
+        Acc<T, R> acc[W];
+#pragma unroll
+        for (int e = 0; e < W; ++e) acc[e].reset();
+        const T *src = reinterpret_cast<const T *>(a.in) + in_off + c0;
+        if (c0 < ncol) {  // ncol % W == 0 when W > 1 (host check), so a vector is all-in or all-out
+            int64_t r = r0 + ty;
+            if constexpr (W > 1) {
+                for (; r + 24 < r1; r += 32) {
+                    V v0 = *reinterpret_cast<const V *>(src + r * a.s);
+                    V v1 = *reinterpret_cast<const V *>(src + (r + 8) * a.s);
+                    V v2 = *reinterpret_cast<const V *>(src + (r + 16) * a.s);
+                    V v3 = *reinterpret_cast<const V *>(src + (r + 24) * a.s);
+#pragma unroll
+                    for (int e = 0; e < W; ++e) {
+                        acc[e].add(v0.v[e]);
+                        acc[e].add(v1.v[e]);
+                        acc[e].add(v2.v[e]);
+                        acc[e].add(v3.v[e]);
+                    }
+                }
+                for (; r < r1; r += 8) {
+                    V v0 = *reinterpret_cast<const V *>(src + r * a.s);
+#pragma unroll
+                    for (int e = 0; e < W; ++e) acc[e].add(v0.v[e]);
+                }
+            } else {
+                for (; r + 24 < r1; r += 32) {
+                    const T x0 = src[r * a.s], x1 = src[(r + 8) * a.s], x2 = src[(r + 16) * a.s],
+                            x3 = src[(r + 24) * a.s];
+                    acc[0].add(x0);
+                    acc[0].add(x1);
+                    acc[0].add(x2);
+                    acc[0].add(x3);
+                }
+                for (; r < r1; r += 8) acc[0].add(src[r * a.s]);
+            }
+        }
+#pragma unroll
+        for (int e = 0; e < W; ++e) smem[ty][tx * W + e] = acc[e];
+        __syncthreads();
+        // 32*W columns, merged over ty in fixed order by the first 32*W threads
+        const int t = ty * 32 + tx;
+        if (t < 32 * W) {
+            Acc<T, R> r = smem[0][t];
+#pragma unroll
+            for (int j = 1; j < 8; ++j) r.merge(smem[j][t]);
+            const int64_t c = tile * (32 * W) + t;
+            if (c < ncol) {
+                if (a.splits == 1) {
+                    store_result<T, R, FIN>(a, r, out_off + c * a.k.out_stride[last], out2_off + c * a.k.out2_stride[last]);
+                } else {
+                    reinterpret_cast<Acc<T, R> *>(a.partial)[(int64_t)split * a.n_out + o * ncol + c] = r;
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// merge per-split partial states in split order, finalize, scatter to the output view
+template <typename T, int R, int FIN>
+__global__ void __launch_bounds__(256) red_finish_cols(RedArgs a)
+{
+    const int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (o >= a.n_out) return;
+    const Acc<T, R> *p = reinterpret_cast<const Acc<T, R> *>(a.partial);
+    Acc<T, R> r = p[o];
+    for (int sidx = 1; sidx < a.splits; ++sidx) r.merge(p[(int64_t)sidx * a.n_out + o]);
+    int64_t in_off, out_off, out2_off;
+    kept_offsets(a.k, o, in_off, out_off, out2_off);
+    store_result<T, R, FIN>(a, r, out_off, out2_off);
+}
+
+// ---- generic: one thread per output ------------------------------------------------------------------
+template <typename T, int R, int FIN>
+__global__ void __launch_bounds__(256) red_generic(RedArgs a)
+{
+    for (int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; o < a.n_out; o += (int64_t)gridDim.x * blockDim.x) {
+        int64_t in_off, out_off, out2_off;
+        kept_offsets(a.k, o, in_off, out_off, out2_off);
+        const T *src = reinterpret_cast<const T *>(a.in) + in_off;
+        Acc<T, R> acc;
+        acc.reset();
+        for (int64_t i = 0; i < a.n; ++i) acc.add(src[i * a.s]);
+        store_result<T, R, FIN>(a, acc, out_off, out2_off);
+    }
+}
+
+// ---- whole-view reduction ---------------------------------------------------------------------------
+struct AllArgs {
+    const char *in;
+    void *partial;  // [gridDim.x] states
+    int ndim;       // collapsed rank
+    int64_t dim[NDB_MAX_NDIM];
+    int64_t stride[NDB_MAX_NDIM];
+    int64_t total;
+    int64_t inner_chunks;  // chunks of 1024 elements per row
+    int64_t n_rows;
+};
+
+// dense unit-stride run, 128-bit loads, 4 vectors in flight per thread
+template <typename T, int R>
+__global__ void __launch_bounds__(256) red_all_flat(AllArgs a)
+{
+    using V = Vec128<T>;
+    constexpr int N = V::N;
+    __shared__ Acc<T, R> smem[32];
+    const T *src = reinterpret_cast<const T *>(a.in);
+    // peel to 16-byte alignment
+    const int64_t mis = (int64_t)(((uintptr_t)src % 16) / sizeof(T));
+    const int64_t head = mis ? ((N - mis) < a.total ? (N - mis) : a.total) : 0;
+    const V *vsrc = reinterpret_cast<const V *>(src + head);
+    const int64_t nv = (a.total - head) / N;
+    Acc<T, R> acc;
+    acc.reset();
+    const int64_t stride = (int64_t)gridDim.x * 256;
+    int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    for (; i + 3 * stride < nv; i += 4 * stride) {
+        V v0 = vsrc[i], v1 = vsrc[i + stride], v2 = vsrc[i + 2 * stride], v3 = vsrc[i + 3 * stride];
+#pragma unroll
+        for (int e = 0; e < N; ++e) acc.add(v0.v[e]);
+#pragma unroll
+        for (int e = 0; e < N; ++e) acc.add(v1.v[e]);
+#pragma unroll
+        for (int e = 0; e < N; ++e) acc.add(v2.v[e]);
+#pragma unroll
+        for (int e = 0; e < N; ++e) acc.add(v3.v[e]);
+    }
+    for (; i < nv; i += stride) {
+        V v0 = vsrc[i];
+#pragma unroll
+        for (int e = 0; e < N; ++e) acc.add(v0.v[e]);
+    }
+    if (blockIdx.x == 0) {  // ragged head and tail
+        const int64_t tail0 = head + nv * N;
+        if (threadIdx.x < head) acc.add(src[threadIdx.x]);
+        const int64_t t = tail0 + threadIdx.x;
+        if (t < a.total) acc.add(src[t]);
+    }
+    acc = block_reduce(acc, smem);
+    if (threadIdx.x == 0) reinterpret_cast<Acc<T, R> *>(a.partial)[blockIdx.x] = acc;
+}
+
+// collapsed N-d view: virtual blocks of (row, 1024-element chunk of the inner axis)
+template <typename T, int R>
+__global__ void __launch_bounds__(256) red_all_rows(AllArgs a)
+{
+    __shared__ Acc<T, R> smem[32];
+    const T *src = reinterpret_cast<const T *>(a.in);
+    const int inner = a.ndim - 1;
+    const int64_t len = a.dim[inner], st = a.stride[inner];
+    const int64_t total_vb = a.n_rows * a.inner_chunks;
+    Acc<T, R> acc;
+    acc.reset();
+    for (int64_t vb = blockIdx.x; vb < total_vb; vb += gridDim.x) {
+        const int64_t row = vb / a.inner_chunks;
+        const int64_t ch = vb - row * a.inner_chunks;
+        int64_t off = 0, lin = row;
+        for (int d = inner - 1; d >= 0; --d) {
+            const int64_t q = lin / a.dim[d];
+            off += (lin - q * a.dim[d]) * a.stride[d];
+            lin = q;
+        }
+        const int64_t i0 = ch * 1024 + threadIdx.x;
+        T x[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int64_t i = i0 + j * 256;
+            if (i < len) x[j] = src[off + i * st];
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int64_t i = i0 + j * 256;
+            if (i < len) acc.add(x[j]);
+        }
+    }
+    acc = block_reduce(acc, smem);
+    if (threadIdx.x == 0) reinterpret_cast<Acc<T, R> *>(a.partial)[blockIdx.x] = acc;
+}
+
+// one block merges the per-block partials in index order and writes the scalar
+template <typename T, int R>
+__global__ void __launch_bounds__(256) red_all_finish(const void *partial, int n, T *out)
+{
+    __shared__ Acc<T, R> smem[32];
+    const Acc<T, R> *p = reinterpret_cast<const Acc<T, R> *>(partial);
+    Acc<T, R> acc;
+    acc.reset();
+    for (int i = threadIdx.x; i < n; i += blockDim.x) acc.merge(p[i]);
+    acc = block_reduce(acc, smem);
+    if (threadIdx.x == 0) *out = acc.s;
+}
+
+// dot product partials: x[i*sx] * y[i*sy], separately rounded product then sum (numeric_util.rs:56)
+template <typename T>
+__global__ void __launch_bounds__(256) dot_partials(const T *x, int64_t sx, const T *y, int64_t sy, int64_t n, void *partial)
+{
+    __shared__ Acc<T, R_SUM> smem[32];
+    Acc<T, R_SUM> acc;
+    acc.reset();
+    const int64_t stride = (int64_t)gridDim.x * 256;
+    int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    for (; i + 3 * stride < n; i += 4 * stride) {
+        const T a0 = x[i * sx], a1 = x[(i + stride) * sx], a2 = x[(i + 2 * stride) * sx], a3 = x[(i + 3 * stride) * sx];
+        const T b0 = y[i * sy], b1 = y[(i + stride) * sy], b2 = y[(i + 2 * stride) * sy], b3 = y[(i + 3 * stride) * sy];
+        acc.add(w_mul(a0, b0));
+        acc.add(w_mul(a1, b1));
+        acc.add(w_mul(a2, b2));
+        acc.add(w_mul(a3, b3));
+    }
+    for (; i < n; i += stride) acc.add(w_mul(x[i * sx], y[i * sy]));
+    acc = block_reduce(acc, smem);
+    if (threadIdx.x == 0) reinterpret_cast<Acc<T, R_SUM> *>(partial)[blockIdx.x] = acc;
+}
+
+// ======================================================================================================
+// host side
+
+// Collapse a read-only view for a whole-view reduction: drop unit axes, make strides positive (order is
+// free for a commutative reduction up to the stated tolerance; exact for integers), sort, merge.
+static void collapse_for_all(const ndb_view *v, AllArgs *a)
+{
+    int n = 0;
+    int64_t d[NDB_MAX_NDIM], s[NDB_MAX_NDIM];
+    int64_t off = 0;
+    for (int i = 0; i < v->ndim; ++i) {
+        if (v->dim[i] == 1) continue;
+        d[n] = v->dim[i];
+        s[n] = v->stride[i];
+        if (s[n] < 0) {
+            off += (d[n] - 1) * s[n];
+            s[n] = -s[n];
+        }
+        ++n;
+    }
+    int order[NDB_MAX_NDIM];
+    for (int i = 0; i < n; ++i) order[i] = i;
+    std::stable_sort(order, order + n, [&](int x, int y) { return s[x] > s[y]; });
+    int m = 0;
+    int64_t rd[NDB_MAX_NDIM], rs[NDB_MAX_NDIM];
+    for (int k = n - 1; k >= 0; --k) {  // innermost outwards
+        const int i = order[k];
+        if (m > 0 && s[i] == rd[m - 1] * rs[m - 1]) rd[m - 1] *= d[i];
+        else {
+            rd[m] = d[i];
+            rs[m] = s[i];
+            ++m;
+        }
+    }
+    if (m == 0) {
+        rd[0] = 1;
+        rs[0] = 1;
+        m = 1;
+    }
+    a->ndim = m;
+    a->total = 1;
+    for (int k = 0; k < m; ++k) {
+        a->dim[k] = rd[m - 1 - k];
+        a->stride[k] = rs[m - 1 - k];
+        a->total *= a->dim[k];
+    }
+    a->in = (const char *)v->ptr + off * (int64_t)dtype_size(v->dtype);
+}
+
+template <typename T, int R>
+static int reduce_all_typed(ndb_ctx *ctx, const ndb_view *v, T *out_dev)
+{
+    AllArgs a;
+    memset(&a, 0, sizeof(a));
+    collapse_for_all(v, &a);
+    const int max_blocks = ctx->sm_count * 8;
+    NDB_TRY(ensure_workspace(ctx, (size_t)max_blocks * sizeof(Acc<T, R>)));
+    a.partial = ctx->workspace;
+    int blocks;
+    if (a.ndim == 1 && a.stride[0] == 1) {
+        const int64_t nv = a.total / Vec128<T>::N;
+        blocks = (int)std::max<int64_t>(1, std::min<int64_t>(max_blocks, (nv + 1023) / 1024));
+        red_all_flat<T, R><<<blocks, 256, 0, ctx->stream>>>(a);
+    } else {
+        const int inner = a.ndim - 1;
+        a.inner_chunks = (a.dim[inner] + 1023) / 1024;
+        a.n_rows = a.total / a.dim[inner];
+        blocks = (int)std::max<int64_t>(1, std::min<int64_t>(max_blocks, a.n_rows * a.inner_chunks));
+        red_all_rows<T, R><<<blocks, 256, 0, ctx->stream>>>(a);
+    }
+    NDB_CHECK_LAUNCH();
+    red_all_finish<T, R><<<1, 256, 0, ctx->stream>>>(a.partial, blocks, out_dev);
+    NDB_CHECK_LAUNCH();
+    return NDB_OK;
+}
+
+template <typename T>
+static int reduce_all_dispatch(ndb_ctx *ctx, int redop, const ndb_view *v, void *out_dev)
+{
+    switch (redop) {
+    case NDB_RED_SUM: return reduce_all_typed<T, R_SUM>(ctx, v, (T *)out_dev);
+    case NDB_RED_PROD: return reduce_all_typed<T, R_PROD>(ctx, v, (T *)out_dev);
+    case NDB_RED_MIN: return reduce_all_typed<T, R_MIN>(ctx, v, (T *)out_dev);
+    case NDB_RED_MAX: return reduce_all_typed<T, R_MAX>(ctx, v, (T *)out_dev);
+    default: break;
+    }
+    set_error("reduce_all: redop %d is not a whole-array reduction", redop);
+    return NDB_ERR_UNSUPPORTED;
+}
+
+static int64_t view_len(const ndb_view *v)
+{
+    int64_t n = 1;
+    for (int i = 0; i < v->ndim; ++i) n *= v->dim[i];
+    return n;
+}
+
+// identity written for empty inputs: sum -> 0, product -> 1 (tests/numeric.rs:57-75)
+static int write_identity(ndb_ctx *ctx, int dtype, int redop, void *out_dev)
+{
+    union { float f; double d; int32_t i; int64_t l; } u;
+    memset(&u, 0, sizeof(u));
+    const bool one = redop == NDB_RED_PROD;
+    switch (dtype) {
+    case NDB_F32: u.f = one ? 1.f : 0.f; break;
+    case NDB_F64: u.d = one ? 1.0 : 0.0; break;
+    case NDB_I32: u.i = one ? 1 : 0; break;
+    case NDB_I64: u.l = one ? 1 : 0; break;
+    }
+    memcpy(ctx->host_scalar, &u, sizeof(u));
+    NDB_CUDA(cudaMemcpyAsync(out_dev, ctx->host_scalar, dtype_size(dtype), cudaMemcpyHostToDevice, ctx->stream));
+    return NDB_OK;
+}
+
+static int reduce_all_dev_impl(ndb_ctx *ctx, int redop, const ndb_view *in, void *out_dev)
+{
+    NDB_TRY(validate_view(in, "reduce_all"));
+    if (view_len(in) == 0) {
+        if (redop == NDB_RED_SUM || redop == NDB_RED_PROD) return write_identity(ctx, in->dtype, redop, out_dev);
+        set_error("reduce_all: min/max of an empty array");
+        return NDB_ERR_EMPTY;
+    }
+    switch (in->dtype) {
+    case NDB_F32: return reduce_all_dispatch<float>(ctx, redop, in, out_dev);
+    case NDB_F64: return reduce_all_dispatch<double>(ctx, redop, in, out_dev);
+    case NDB_I32: return reduce_all_dispatch<int32_t>(ctx, redop, in, out_dev);
+    case NDB_I64: return reduce_all_dispatch<int64_t>(ctx, redop, in, out_dev);
+    }
+    return NDB_ERR_UNSUPPORTED;
+}
+
+// ---- axis reductions ------------------------------------------------------------------------------
+template <typename T, int R, int FIN>
+static int reduce_axis_launch(ndb_ctx *ctx, RedArgs &a, const ZipPlan &z)
+{
+    cudaStream_t st = ctx->stream;
+    const int64_t esz = sizeof(T);
+    const int64_t vecn = Vec128<T>::N;
+    const int last = a.k.n - 1;
+    int64_t min_kept = INT64_MAX;  // smallest non-zero |stride| among kept axes of the input
+    for (int d = 0; d < a.k.n; ++d)
+        if (a.k.dim[d] > 1) min_kept = std::min<int64_t>(min_kept, llabs(a.k.in_stride[d]));
+    const int64_t as = llabs(a.s);
+    const bool lanes = a.n_out == 1 || a.n == 1 || as <= min_kept;
+    if (lanes) {
+        bool vec = a.s == 1 && a.n % vecn == 0 && ((uintptr_t)a.in % 16) == 0 && a.n >= 4 * vecn;
+        for (int d = 0; d < a.k.n && vec; ++d) vec = a.k.dim[d] == 1 || a.k.in_stride[d] % vecn == 0;
+        const bool warp = a.n <= 2048;
+        const int64_t groups = warp ? (a.n_out + 7) / 8 : a.n_out;
+        const unsigned blocks = (unsigned)std::min<int64_t>(groups, (int64_t)1 << 30);
+        if (warp) {
+            if (vec) red_lanes<T, R, FIN, true, true><<<blocks, 256, 0, st>>>(a);
+            else red_lanes<T, R, FIN, true, false><<<blocks, 256, 0, st>>>(a);
+        } else {
+            if (vec) red_lanes<T, R, FIN, false, true><<<blocks, 256, 0, st>>>(a);
+            else red_lanes<T, R, FIN, false, false><<<blocks, 256, 0, st>>>(a);
+        }
+        NDB_CHECK_LAUNCH();
+        return NDB_OK;
+    }
+    if (a.k.in_stride[last] == 1 && a.k.dim[last] >= 32) {
+        const int64_t ncol = a.k.dim[last];
+        bool vec = ncol % vecn == 0 && ((uintptr_t)a.in % 16) == 0 && a.s % vecn == 0;
+        for (int d = 0; d < last && vec; ++d) vec = a.k.in_stride[d] % vecn == 0;
+        const int w = vec ? (int)vecn : 1;
+        const int64_t tiles = (ncol + 32 * w - 1) / (32 * w);
+        const int64_t total = tiles * (a.n_out / ncol);
+        // enough blocks to fill the machine ~4 deep, but every split keeps >= 64 rows
+        int64_t want = ((int64_t)ctx->sm_count * 8 + total - 1) / total;
+        int64_t max_splits = std::max<int64_t>(1, a.n / 64);
+        int splits = (int)std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(want, max_splits), 256));
+        a.splits = splits;
+        if (splits > 1) {
+            NDB_TRY(ensure_workspace(ctx, (size_t)splits * (size_t)a.n_out * sizeof(Acc<T, R>)));
+            a.partial = ctx->workspace;
+        }
+        dim3 grid((unsigned)std::min<int64_t>(total, (int64_t)1 << 30), (unsigned)splits, 1), block(32, 8, 1);
+        if (vec) red_cols<T, R, FIN, Vec128<T>::N><<<grid, block, 0, st>>>(a);
+        else red_cols<T, R, FIN, 1><<<grid, block, 0, st>>>(a);
+        NDB_CHECK_LAUNCH();
+        if (splits > 1) {
+            red_finish_cols<T, R, FIN><<<(unsigned)((a.n_out + 255) / 256), 256, 0, st>>>(a);
+            NDB_CHECK_LAUNCH();
+        }
+        return NDB_OK;
+    }
+    (void)esz;
+    (void)z;
+    const unsigned blocks = (unsigned)std::min<int64_t>((a.n_out + 255) / 256, (int64_t)1 << 30);
+    red_generic<T, R, FIN><<<blocks, 256, 0, st>>>(a);
+    NDB_CHECK_LAUNCH();
+    return NDB_OK;
+}
+
+template <typename T>
+static int reduce_axis_dispatch(ndb_ctx *ctx, int redop, RedArgs &a, const ZipPlan &z)
+{
+    switch (redop) {
+    case NDB_RED_SUM: return reduce_axis_launch<T, R_SUM, FIN_NONE>(ctx, a, z);
+    case NDB_RED_PROD: return reduce_axis_launch<T, R_PROD, FIN_NONE>(ctx, a, z);
+    case NDB_RED_MIN: return reduce_axis_launch<T, R_MIN, FIN_NONE>(ctx, a, z);
+    case NDB_RED_MAX: return reduce_axis_launch<T, R_MAX, FIN_NONE>(ctx, a, z);
+    case NDB_RED_MEAN: return reduce_axis_launch<T, R_SUM, FIN_MEAN>(ctx, a, z);
+    default: break;
+    }
+    if constexpr (std::is_floating_point<T>::value) {
+        switch (redop) {
+        case NDB_RED_VAR: return reduce_axis_launch<T, R_WELFORD, FIN_VAR>(ctx, a, z);
+        case NDB_RED_STD: return reduce_axis_launch<T, R_WELFORD, FIN_STD>(ctx, a, z);
+        case -1: return reduce_axis_launch<T, R_WELFORD, FIN_WELFORD_RAW>(ctx, a, z);
+        default: break;
+        }
+    }
+    set_error("reduce_axis: redop %d unsupported for this element type", redop);
+    return NDB_ERR_UNSUPPORTED;
+}
+
+// Fill `out` with a constant through the Zip engine (empty-axis conventions).
+static int fill_view(ndb_ctx *ctx, const ndb_view *out, double value)
+{
+    union { float f; double d; int32_t i; int64_t l; } u;
+    switch (out->dtype) {
+    case NDB_F32: u.f = (float)value; break;
+    case NDB_F64: u.d = value; break;
+    case NDB_I32: u.i = (int32_t)value; break;
+    default: u.l = (int64_t)value; break;
+    }
+    return ndb_zip(ctx, NDB_OP_FILL, &u, 1, out);
+}
+
+static int reduce_axis_impl(ndb_ctx *ctx, int redop, int axis, const ndb_view *in, const ndb_view *out,
+                            const ndb_view *out2, double ddof)
+{
+    if (!ctx) {
+        set_error("reduce_axis: null context (no CPU fallback exists)");
+        return NDB_ERR_INVALID_ARG;
+    }
+    NDB_TRY(validate_view(in, "reduce_axis input"));
+    NDB_TRY(validate_view(out, "reduce_axis output"));
+    if (axis < 0 || axis >= in->ndim) {
+        set_error("axis %d is out of bounds for array of dimension %d", axis, in->ndim);
+        return NDB_ERR_OUT_OF_BOUNDS;
+    }
+    if (out->dtype != in->dtype || (out2 && out2->dtype != in->dtype)) {
+        set_error("reduce_axis: output dtype differs from input dtype");
+        return NDB_ERR_UNSUPPORTED;
+    }
+    // `in` with the reduced axis removed
+    ndb_view base = *in;
+    for (int i = axis; i + 1 < in->ndim; ++i) {
+        base.dim[i] = in->dim[i + 1];
+        base.stride[i] = in->stride[i + 1];
+    }
+    base.ndim = in->ndim - 1;
+    const int64_t n = in->dim[axis];
+    const bool welford = redop == NDB_RED_VAR || redop == NDB_RED_STD || redop == -1;
+    if (welford && !dtype_is_float(in->dtype)) {
+        set_error("var_axis/std_axis need a float element type");
+        return NDB_ERR_UNSUPPORTED;
+    }
+    double nT = (double)n, dof = 0.0;
+    if (redop == NDB_RED_VAR || redop == NDB_RED_STD) {
+        // assert!(!(ddof < zero || ddof > n)) in the element type; NaN passes (impl_numeric.rs:408-413)
+        if (in->dtype == NDB_F32) {
+            const float d = (float)ddof, nf = (float)n;
+            if (d < 0.f || d > nf) {
+                set_error("`ddof` must not be less than zero or greater than the length of the axis");
+                return NDB_ERR_INVALID_ARG;
+            }
+            dof = (double)(nf - d);
+            nT = (double)nf;
+        } else {
+            if (ddof < 0.0 || ddof > (double)n) {
+                set_error("`ddof` must not be less than zero or greater than the length of the axis");
+                return NDB_ERR_INVALID_ARG;
+            }
+            dof = (double)n - ddof;
+        }
+    }
+    // the plan validates out/base shapes, drops unit axes, flips and merges jointly
+    ndb_view parts[3] = {*out, base, out2 ? *out2 : *out};
+    ZipPlan z;
+    int st = make_zip_plan(out2 ? NDB_OP_ADD : NDB_OP_COPY, out2 ? 3 : 2, parts, &z);
+    if (st == NDB_ERR_INCOMPATIBLE_SHAPE) set_error("reduce_axis: output shape must be the input shape without the axis");
+    NDB_TRY(st);
+    if (z.kernel == NDB_KERNEL_NOOP) return NDB_OK;  // no outputs at all
+    DeviceGuard g(ctx->device);
+    if (n == 0) {
+        // sum -> 0, product -> 1, mean -> None, var/std -> NaN (0/0), min/max -> nothing to fold
+        if (redop == NDB_RED_SUM) return fill_view(ctx, out, 0.0);
+        if (redop == NDB_RED_PROD) return fill_view(ctx, out, 1.0);
+        if (redop == NDB_RED_VAR || redop == NDB_RED_STD) return fill_view(ctx, out, NAN);
+        if (redop == -1) {
+            NDB_TRY(fill_view(ctx, out, 0.0));
+            return fill_view(ctx, out2, 0.0);
+        }
+        set_error("reduction of a zero-length axis has no value (ndarray returns None)");
+        return NDB_ERR_EMPTY;
+    }
+    RedArgs a;
+    memset(&a, 0, sizeof(a));
+    a.out = z.ptr[0];
+    a.in = z.ptr[1];
+    a.out2 = out2 ? z.ptr[2] : nullptr;
+    a.k.n = z.ndim;
+    a.n_out = z.total;
+    for (int d = 0; d < z.ndim; ++d) {
+        a.k.dim[d] = z.dim[d];
+        a.k.out_stride[d] = z.stride[0][d];
+        a.k.in_stride[d] = z.stride[1][d];
+        a.k.out2_stride[d] = out2 ? z.stride[2][d] : 0;
+    }
+    a.n = n;
+    a.s = n > 1 ? in->stride[axis] : 1;
+    a.nT = nT;
+    a.dof = dof;
+    a.splits = 1;
+    // a backwards reduced axis is walked forwards from its low end (legal: commutative up to tolerance)
+    if (a.s < 0) {
+        a.in += (n - 1) * a.s * (int64_t)dtype_size(in->dtype);
+        a.s = -a.s;
+    }
+    switch (in->dtype) {
+    case NDB_F32: return reduce_axis_dispatch<float>(ctx, redop, a, z);
+    case NDB_F64: return reduce_axis_dispatch<double>(ctx, redop, a, z);
+    case NDB_I32: return reduce_axis_dispatch<int32_t>(ctx, redop, a, z);
+    case NDB_I64: return reduce_axis_dispatch<int64_t>(ctx, redop, a, z);
+    }
+    return NDB_ERR_UNSUPPORTED;
+}
+
+// merge Welford shards: out = finalize(merge_s (n_s, mean_s, m2_s)) — Chan's formula in shard order
+template <typename T>
+__global__ void __launch_bounds__(256) welford_merge_kernel(int n_shards, const int64_t *counts, const T *const *means,
+                                                            const T *const *m2s, int64_t n_out, T dof, int want_std, T *out)
+{
+    const int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (o >= n_out) return;
+    using Rd = Reducer<T, R_WELFORD>;
+    typename Rd::State s = Rd::init();
+    for (int k = 0; k < n_shards; ++k) {
+        typename Rd::State t{(T)counts[k], means[k][o], m2s[k][o]};
+        Rd::merge(s, t);
+    }
+    T v = s.m2 / dof;
+    if (want_std) v = std::is_same<T, float>::value ? (T)sqrtf((float)v) : (T)sqrt((double)v);
+    out[o] = v;
+}
+
+}  // namespace ndb
+
+using namespace ndb;
+
+extern "C" {
+
+int ndb_reduce_all_dev(ndb_ctx *ctx, int redop, const ndb_view *in, void *out_dev)
+{
+    if (!ctx || !out_dev) {
+        set_error("reduce_all: null context or output (no CPU fallback exists)");
+        return NDB_ERR_INVALID_ARG;
+    }
+    clear_error();
+    DeviceGuard g(ctx->device);
+    return reduce_all_dev_impl(ctx, redop, in, out_dev);
+}
+
+int ndb_reduce_all(ndb_ctx *ctx, int redop, const ndb_view *in, void *out_host)
+{
+    if (!ctx || !out_host) {
+        set_error("reduce_all: null context or output (no CPU fallback exists)");
+        return NDB_ERR_INVALID_ARG;
+    }
+    clear_error();
+    DeviceGuard g(ctx->device);
+    NDB_TRY(ensure_workspace(ctx, 4096));
+    // the scalar lands at the END of the partials buffer's first page (partials use the front)
+    void *dev_scalar = (char *)ctx->workspace + ctx->workspace_bytes - 64;
+    NDB_TRY(reduce_all_dev_impl(ctx, redop, in, dev_scalar));
+    NDB_CUDA(cudaMemcpyAsync(ctx->host_scalar, dev_scalar, dtype_size(in->dtype), cudaMemcpyDeviceToHost, ctx->stream));
+    NDB_CUDA(cudaStreamSynchronize(ctx->stream));
+    memcpy(out_host, ctx->host_scalar, dtype_size(in->dtype));
+    return NDB_OK;
+}
+
+int ndb_reduce_axis(ndb_ctx *ctx, int redop, int axis, const ndb_view *in, const ndb_view *out, double ddof)
+{
+    clear_error();
+    if (redop < 0 || redop >= NDB_RED__COUNT) {
+        set_error("reduce_axis: unknown redop %d", redop);
+        return NDB_ERR_UNSUPPORTED;
+    }
+    return reduce_axis_impl(ctx, redop, axis, in, out, nullptr, ddof);
+}
+
+int ndb_welford_axis(ndb_ctx *ctx, int axis, const ndb_view *in, const ndb_view *mean_out, const ndb_view *m2_out)
+{
+    clear_error();
+    if (!m2_out) return NDB_ERR_INVALID_ARG;
+    return reduce_axis_impl(ctx, -1, axis, in, mean_out, m2_out, 0.0);
+}
+
+int ndb_welford_merge(ndb_ctx *ctx, int n_shards, const int64_t *counts, const ndb_view *means, const ndb_view *m2s,
+                      double ddof, int want_std, const ndb_view *out)
+{
+    clear_error();
+    if (!ctx || n_shards < 1 || n_shards > 64 || !counts || !means || !m2s || !out) return NDB_ERR_INVALID_ARG;
+    // shards and the output are dense C-order arrays of identical shape (they are library-allocated partials)
+    const int64_t n_out = view_len(out);
+    int64_t total = 0;
+    for (int k = 0; k < n_shards; ++k) {
+        if (view_len(&means[k]) != n_out || view_len(&m2s[k]) != n_out || means[k].dtype != out->dtype) {
+            set_error("welford_merge: shard %d does not match the output", k);
+            return NDB_ERR_INCOMPATIBLE_SHAPE;
+        }
+        if (!is_layout_c(&means[k]) || !is_layout_c(&m2s[k])) {
+            set_error("welford_merge: shards must be standard-layout");
+            return NDB_ERR_INCOMPATIBLE_LAYOUT;
+        }
+        total += counts[k];
+    }
+    if (!is_layout_c(out)) {
+        set_error("welford_merge: output must be standard-layout");
+        return NDB_ERR_INCOMPATIBLE_LAYOUT;
+    }
+    if (!dtype_is_float(out->dtype)) return NDB_ERR_UNSUPPORTED;
+    if (ddof < 0.0 || ddof > (double)total) {
+        set_error("`ddof` must not be less than zero or greater than the length of the axis");
+        return NDB_ERR_INVALID_ARG;
+    }
+    if (n_out == 0) return NDB_OK;
+    DeviceGuard g(ctx->device);
+    // tables of shard pointers + counts go through the workspace tail
+    const size_t tbl = (size_t)n_shards * (sizeof(int64_t) + 2 * sizeof(void *));
+    NDB_TRY(ensure_workspace(ctx, 8192));
+    char *dev_tbl = (char *)ctx->workspace + ctx->workspace_bytes - 4096;
+    std::vector<char> host(tbl);
+    int64_t *hc = (int64_t *)host.data();
+    const void **hm = (const void **)(host.data() + n_shards * sizeof(int64_t));
+    const void **h2 = hm + n_shards;
+    for (int k = 0; k < n_shards; ++k) {
+        hc[k] = counts[k];
+        hm[k] = means[k].ptr;
+        h2[k] = m2s[k].ptr;
+    }
+    NDB_CUDA(cudaMemcpyAsync(dev_tbl, host.data(), tbl, cudaMemcpyHostToDevice, ctx->stream));
+    NDB_CUDA(cudaStreamSynchronize(ctx->stream));  // `host` dies at scope exit
+    const int64_t *dc = (const int64_t *)dev_tbl;
+    const unsigned blocks = (unsigned)((n_out + 255) / 256);
+    if (out->dtype == NDB_F32) {
+        const float dof = (float)total - (float)ddof;
+        welford_merge_kernel<float><<<blocks, 256, 0, ctx->stream>>>(
+            n_shards, dc, (const float *const *)(dev_tbl + n_shards * sizeof(int64_t)),
+            (const float *const *)(dev_tbl + n_shards * (sizeof(int64_t) + sizeof(void *))), n_out, dof, want_std,
+            (float *)out->ptr);
+    } else {
+        const double dof = (double)total - ddof;
+        welford_merge_kernel<double><<<blocks, 256, 0, ctx->stream>>>(
+            n_shards, dc, (const double *const *)(dev_tbl + n_shards * sizeof(int64_t)),
+            (const double *const *)(dev_tbl + n_shards * (sizeof(int64_t) + sizeof(void *))), n_out, dof, want_std,
+            (double *)out->ptr);
+    }
+    NDB_CHECK_LAUNCH();
+    return NDB_OK;
+}
+
+int ndb_dot(ndb_ctx *ctx, const ndb_view *x, const ndb_view *y, void *out_host)
+{
+    clear_error();
+    if (!ctx || !out_host) return NDB_ERR_INVALID_ARG;
+    NDB_TRY(validate_view(x, "dot lhs"));
+    NDB_TRY(validate_view(y, "dot rhs"));
+    if (x->ndim != 1 || y->ndim != 1 || x->dim[0] != y->dim[0] || x->dtype != y->dtype) {
+        set_error("dot: operands must be 1-d, of equal length and element type");
+        return NDB_ERR_INCOMPATIBLE_SHAPE;
+    }
+    DeviceGuard g(ctx->device);
+    const int64_t n = x->dim[0];
+    const int max_blocks = ctx->sm_count * 8;
+    NDB_TRY(ensure_workspace(ctx, (size_t)max_blocks * 32 + 4096));
+    void *dev_scalar = (char *)ctx->workspace + ctx->workspace_bytes - 64;
+    const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>(max_blocks, (n + 1023) / 1024));
+    const int64_t sx = n > 1 ? x->stride[0] : 1, sy = n > 1 ? y->stride[0] : 1;
+#define NDB_DOT(T)                                                                                            \
+    dot_partials<T><<<blocks, 256, 0, ctx->stream>>>((const T *)x->ptr, sx, (const T *)y->ptr, sy, n,         \
+                                                     ctx->workspace);                                         \
+    NDB_CHECK_LAUNCH();                                                                                       \
+    red_all_finish<T, R_SUM><<<1, 256, 0, ctx->stream>>>(ctx->workspace, blocks, (T *)dev_scalar);            \
+    NDB_CHECK_LAUNCH();
+    switch (x->dtype) {
+    case NDB_F32: { NDB_DOT(float) } break;
+    case NDB_F64: { NDB_DOT(double) } break;
+    case NDB_I32: { NDB_DOT(int32_t) } break;
+    case NDB_I64: { NDB_DOT(int64_t) } break;
+    default: return NDB_ERR_UNSUPPORTED;
+    }
+#undef NDB_DOT
+    NDB_CUDA(cudaMemcpyAsync(ctx->host_scalar, dev_scalar, dtype_size(x->dtype), cudaMemcpyDeviceToHost, ctx->stream));
+    NDB_CUDA(cudaStreamSynchronize(ctx->stream));
+    memcpy(out_host, ctx->host_scalar, dtype_size(x->dtype));
+    return NDB_OK;
+}
+
+}  // extern "C"

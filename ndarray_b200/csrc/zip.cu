@@ -1,0 +1,240 @@
+// ndb_zip: plan + launch; ndb_zip_host: the end-to-end form over HOST buffers.
+#include <algorithm>
+#include <cstdlib>
+#include <vector>
+
+#include "zip_kernels.cuh"
+
+using namespace ndb;
+
+namespace ndb {
+
+static int zip_launch_plan(ndb_ctx *ctx, const ZipPlan &z, const void *scalars)
+{
+    if (z.kernel == NDB_KERNEL_NOOP) return NDB_OK;  // Zip over an empty shape does nothing (tests/azip.rs:472)
+    switch (z.dtype) {
+    case NDB_F32: return zip_dispatch_f32(ctx, z, scalars);
+    case NDB_F64: return zip_dispatch_f64(ctx, z, scalars);
+    case NDB_I32: return zip_dispatch_i32(ctx, z, scalars);
+    case NDB_I64: return zip_dispatch_i64(ctx, z, scalars);
+    default: break;
+    }
+    set_error("Zip: unsupported dtype %d", z.dtype);
+    return NDB_ERR_UNSUPPORTED;
+}
+
+static bool op_can_trap(int op, int dtype)
+{
+    if (dtype_is_float(dtype)) return false;
+    return op == NDB_OP_DIV || op == NDB_OP_REM || op == NDB_OP_DIV_S || op == NDB_OP_REM_S || op == NDB_OP_RDIV_S;
+}
+
+// Integer / and % panic in Rust on a zero divisor or MIN / -1.  The kernels raise a device flag;
+// read it back (these ops synchronise, the others stay asynchronous).
+static int check_trap(ndb_ctx *ctx)
+{
+    NDB_CUDA(cudaMemcpyAsync(ctx->host_flag, ctx->dev_flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    NDB_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (*ctx->host_flag) {
+        *ctx->host_flag = 0;
+        NDB_CUDA(cudaMemsetAsync(ctx->dev_flag, 0, sizeof(int), ctx->stream));
+        set_error("attempt to divide by zero (or to divide with overflow)");
+        return NDB_ERR_DIV_BY_ZERO;
+    }
+    return NDB_OK;
+}
+
+}  // namespace ndb
+
+extern "C" {
+
+int ndb_zip(ndb_ctx *ctx, int op, const void *scalars, int n_parts, const ndb_view *parts)
+{
+    if (!ctx) {
+        set_error("ndb_zip: null context (no CPU fallback exists)");
+        return NDB_ERR_INVALID_ARG;
+    }
+    ZipPlan z;
+    NDB_TRY(make_zip_plan(op, n_parts, parts, &z));
+    DeviceGuard g(ctx->device);
+    NDB_TRY(zip_launch_plan(ctx, z, scalars));
+    if (z.kernel != NDB_KERNEL_NOOP && op_can_trap(op, z.dtype)) return check_trap(ctx);
+    return NDB_OK;
+}
+
+}  // extern "C"
+
+// ---------------------------------------------------------------------------------------------
+// Host-buffer path.  Every producer lives in host memory; each one's address span is mirrored in a
+// device staging buffer.  When the outermost axis separates a producer into disjoint slabs, slabs are
+// streamed: H2D of slab c+1, the kernel on slab c and D2H of slab c-1 overlap on three streams, so
+// the call costs about max(bytes in, bytes out) / PCIe bandwidth instead of their sum.
+namespace {
+
+struct Span {
+    int64_t lo, hi;  // element offsets (inclusive) relative to view.ptr; empty if hi < lo
+};
+
+Span view_span(const ndb_view &v, int from_axis = 0)
+{
+    Span s{0, 0};
+    for (int k = from_axis; k < v.ndim; ++k) {
+        if (v.dim[k] == 0) return Span{0, -1};
+        const int64_t e = (v.dim[k] - 1) * v.stride[k];
+        if (e < 0) s.lo += e;
+        else s.hi += e;
+    }
+    return s;
+}
+
+bool slabs_disjoint(const ndb_view &v)
+{
+    if (v.ndim == 0 || v.dim[0] <= 1) return false;
+    const Span inner = view_span(v, 1);
+    return llabs(v.stride[0]) >= (inner.hi - inner.lo + 1);
+}
+
+}  // namespace
+
+extern "C" {
+
+int ndb_zip_host(ndb_ctx *ctx, int op, const void *scalars, int n_parts, const ndb_view *parts)
+{
+    if (!ctx) {
+        set_error("ndb_zip_host: null context (no CPU fallback exists)");
+        return NDB_ERR_INVALID_ARG;
+    }
+    ZipPlan probe;
+    NDB_TRY(make_zip_plan(op, n_parts, parts, &probe));  // validates shapes, arity, aliasing
+    if (probe.kernel == NDB_KERNEL_NOOP) return NDB_OK;
+    DeviceGuard g(ctx->device);
+    const int64_t esz = (int64_t)dtype_size(parts[0].dtype);
+
+    // mirror every producer's span on the device
+    ndb_view dev[NDB_MAX_PARTS];
+    Span span[NDB_MAX_PARTS];
+    for (int p = 0; p < n_parts; ++p) {
+        span[p] = view_span(parts[p]);
+        const size_t bytes = (size_t)((span[p].hi - span[p].lo + 1) * esz);
+        NDB_TRY(ensure_stage(ctx, p, bytes));
+        dev[p] = parts[p];
+        dev[p].ptr = (char *)ctx->stage[p] - span[p].lo * esz;
+    }
+    const bool out_dense = ndb_view_is_contiguous(&parts[0]) != 0;
+    // inputs that alias the output (a += b passes `a` twice) ride on the output's buffer
+    bool alias_out[NDB_MAX_PARTS] = {false};
+    for (int p = 1; p < n_parts; ++p) {
+        if (parts[p].ptr == parts[0].ptr && memcmp(parts[p].dim, parts[0].dim, sizeof(parts[0].dim)) == 0 &&
+            memcmp(parts[p].stride, parts[0].stride, sizeof(parts[0].stride)) == 0) {
+            alias_out[p] = true;
+            dev[p].ptr = dev[0].ptr;
+        }
+    }
+    bool out_is_read = !out_dense;
+    for (int p = 1; p < n_parts; ++p) out_is_read |= alias_out[p];
+
+    // can the outermost axis be streamed?
+    bool stream_out = slabs_disjoint(parts[0]);
+    int64_t n0 = parts[0].ndim > 0 ? parts[0].dim[0] : 1;
+    int64_t total_bytes = probe.total * esz;
+    int chunks = 1;
+    if (stream_out) {
+        chunks = (int)std::min<int64_t>(std::min<int64_t>(n0, 32), std::max<int64_t>(1, total_bytes / (16 << 20)));
+    }
+    cudaStream_t s_in = ctx->copy_in, s_k = ctx->stream, s_out = ctx->copy_out;
+    std::vector<cudaEvent_t> ev_in(chunks), ev_k(chunks);
+    cudaEvent_t ev_start, ev_whole;
+    NDB_CUDA(cudaEventCreateWithFlags(&ev_start, cudaEventDisableTiming));
+    NDB_CUDA(cudaEventCreateWithFlags(&ev_whole, cudaEventDisableTiming));
+    for (int c = 0; c < chunks; ++c) {
+        NDB_CUDA(cudaEventCreateWithFlags(&ev_in[c], cudaEventDisableTiming));
+        NDB_CUDA(cudaEventCreateWithFlags(&ev_k[c], cudaEventDisableTiming));
+    }
+    // copies must not start before earlier work on the compute stream that may still use the staging buffers
+    NDB_CUDA(cudaEventRecord(ev_start, s_k));
+    NDB_CUDA(cudaStreamWaitEvent(s_in, ev_start, 0));
+    NDB_CUDA(cudaStreamWaitEvent(s_out, ev_start, 0));
+
+    // Move one view's elements: a pitched 2-D copy when axis 0 separates it into disjoint slabs (only the
+    // slabs travel, e.g. every other plane of s![..;-2, .., ..]), else its whole address span.
+    auto copy_view = [&](const ndb_view &hv, const ndb_view &dv, cudaMemcpyKind kind, cudaStream_t st) -> int {
+        const Span sp = view_span(hv);
+        if (sp.hi < sp.lo) return NDB_OK;
+        const bool h2d = kind == cudaMemcpyHostToDevice;
+        if (hv.ndim >= 2 && hv.dim[0] > 1) {
+            const Span inner = view_span(hv, 1);
+            const int64_t width = inner.hi - inner.lo + 1;
+            const int64_t s0 = llabs(hv.stride[0]);
+            if (s0 > width && s0 * esz < ((int64_t)1 << 31)) {
+                const int64_t first = (hv.stride[0] < 0 ? (hv.dim[0] - 1) * hv.stride[0] : 0) + inner.lo;
+                char *h = (char *)hv.ptr + first * esz;
+                char *d = (char *)dv.ptr + first * esz;
+                NDB_CUDA(cudaMemcpy2DAsync(h2d ? d : h, (size_t)(s0 * esz), h2d ? h : d, (size_t)(s0 * esz),
+                                           (size_t)(width * esz), (size_t)hv.dim[0], kind, st));
+                return NDB_OK;
+            }
+        }
+        const size_t bytes = (size_t)((sp.hi - sp.lo + 1) * esz);
+        char *h = (char *)hv.ptr + sp.lo * esz;
+        char *d = (char *)dv.ptr + sp.lo * esz;
+        NDB_CUDA(cudaMemcpyAsync(h2d ? d : h, h2d ? h : d, bytes, kind, st));
+        return NDB_OK;
+    };
+
+    // producers whose slabs interleave along axis 0 go over whole, up front
+    bool streamed[NDB_MAX_PARTS] = {false};
+    for (int p = 1; p < n_parts; ++p) {
+        if (alias_out[p]) continue;
+        streamed[p] = chunks > 1 && slabs_disjoint(parts[p]);
+        if (!streamed[p]) NDB_TRY(copy_view(parts[p], dev[p], cudaMemcpyHostToDevice, s_in));
+    }
+    if (chunks == 1 && out_is_read) NDB_TRY(copy_view(parts[0], dev[0], cudaMemcpyHostToDevice, s_in));
+    NDB_CUDA(cudaEventRecord(ev_whole, s_in));
+    NDB_CUDA(cudaStreamWaitEvent(s_k, ev_whole, 0));
+
+    int status = NDB_OK;
+    for (int c = 0; c < chunks && status == NDB_OK; ++c) {
+        const int64_t lo = n0 * c / chunks, hi = n0 * (c + 1) / chunks;
+        ndb_view hv[NDB_MAX_PARTS], dv[NDB_MAX_PARTS];
+        for (int p = 0; p < n_parts; ++p) {
+            hv[p] = parts[p];
+            dv[p] = dev[p];
+            if (chunks > 1) {
+                hv[p].dim[0] = dv[p].dim[0] = hi - lo;
+                hv[p].ptr = (char *)parts[p].ptr + lo * parts[p].stride[0] * esz;
+                dv[p].ptr = (char *)dev[p].ptr + lo * dev[p].stride[0] * esz;
+            }
+        }
+        if (chunks > 1) {
+            for (int p = 1; p < n_parts && status == NDB_OK; ++p)
+                if (streamed[p]) status = copy_view(hv[p], dv[p], cudaMemcpyHostToDevice, s_in);
+            if (status == NDB_OK && out_is_read)
+                status = copy_view(hv[0], dv[0], cudaMemcpyHostToDevice, s_in);
+            if (status != NDB_OK) break;
+            NDB_CUDA(cudaEventRecord(ev_in[c], s_in));
+            NDB_CUDA(cudaStreamWaitEvent(s_k, ev_in[c], 0));
+        }
+        ZipPlan z;
+        status = make_zip_plan(op, n_parts, dv, &z);
+        if (status == NDB_OK) status = zip_launch_plan(ctx, z, scalars);
+        if (status != NDB_OK) break;
+        NDB_CUDA(cudaEventRecord(ev_k[c], s_k));
+        NDB_CUDA(cudaStreamWaitEvent(s_out, ev_k[c], 0));
+        status = copy_view(hv[0], dv[0], cudaMemcpyDeviceToHost, s_out);
+    }
+    cudaError_t e1 = cudaStreamSynchronize(s_in), e2 = cudaStreamSynchronize(s_k), e3 = cudaStreamSynchronize(s_out);
+    cudaEventDestroy(ev_start);
+    cudaEventDestroy(ev_whole);
+    for (int c = 0; c < chunks; ++c) {
+        cudaEventDestroy(ev_in[c]);
+        cudaEventDestroy(ev_k[c]);
+    }
+    if (status != NDB_OK) return status;
+    NDB_CUDA(e1);
+    NDB_CUDA(e2);
+    NDB_CUDA(e3);
+    if (op_can_trap(op, parts[0].dtype)) return check_trap(ctx);
+    return NDB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,536 @@
+// Elementwise Zip kernels for sm_100a.  Three kernel families, picked by the planner (zip_plan.cu):
+//
+//   zip_flat_vec   every producer is one dense run: 128-bit ld/st, UNROLL independent vectors per
+//                  thread per producer in flight (HBM-latency x bandwidth needs ~40 KB in flight per SM).
+//   zip_rows       collapsed N-d views with arbitrary SIGNED strides.  Warps walk the output's
+//                  fastest axis; the outer multi-index is decomposed once per thread-row, not per
+//                  element.  VEC=true is the 128-bit form for aligned unit/zero inner strides
+//                  (covers outer-axis slices such as s![..;-2, .., ..] and row broadcasts).
+//   zip_tile       a producer is dense along ANOTHER axis than the output (x.t()): it is read in
+//                  coalesced runs along its own dense axis into padded shared memory and consumed
+//                  transposed, so both sides move full 32-byte sectors.
+//
+// Arithmetic contract (bit-exact vs ndarray on the CPU): this file is compiled with -fmad=false, so
+// b*c+a rounds twice like Rust; integer +,-,* wrap (done in unsigned); integer / and % raise the
+// device flag where Rust panics.
+#pragma once
+#include <type_traits>
+
+#include "common.h"
+#include "zip_plan.h"
+
+namespace ndb {
+
+template <typename T>
+struct UnsignedOf { using type = T; };
+template <>
+struct UnsignedOf<int32_t> { using type = uint32_t; };
+template <>
+struct UnsignedOf<int64_t> { using type = uint64_t; };
+
+template <typename T>
+struct alignas(16) Vec128 {
+    static constexpr int N = 16 / sizeof(T);
+    T v[N];
+};
+
+template <typename T>
+__device__ __forceinline__ T w_add(T a, T b)
+{
+    using U = typename UnsignedOf<T>::type;
+    return (T)((U)a + (U)b);
+}
+template <typename T>
+__device__ __forceinline__ T w_sub(T a, T b)
+{
+    using U = typename UnsignedOf<T>::type;
+    return (T)((U)a - (U)b);
+}
+template <typename T>
+__device__ __forceinline__ T w_mul(T a, T b)
+{
+    using U = typename UnsignedOf<T>::type;
+    return (T)((U)a * (U)b);
+}
+template <typename T>
+__device__ __forceinline__ T w_neg(T a)
+{
+    if constexpr (std::is_floating_point<T>::value) return -a;
+    else {
+        using U = typename UnsignedOf<T>::type;
+        return (T)((U)0 - (U)a);
+    }
+}
+template <typename T>
+__device__ __forceinline__ T w_div(T a, T b, int *flag)
+{
+    if constexpr (std::is_floating_point<T>::value) return a / b;
+    else {
+        // Rust: "attempt to divide by zero" / "attempt to divide with overflow"
+        if (b == 0 || (b == (T)-1 && a == (T)((typename UnsignedOf<T>::type)1 << (sizeof(T) * 8 - 1)))) {
+            *flag = 1;
+            return 0;
+        }
+        return a / b;
+    }
+}
+template <typename T>
+__device__ __forceinline__ T w_rem(T a, T b, int *flag)
+{
+    if constexpr (std::is_same<T, float>::value) return fmodf(a, b);
+    else if constexpr (std::is_same<T, double>::value) return fmod(a, b);
+    else {
+        if (b == 0 || (b == (T)-1 && a == (T)((typename UnsignedOf<T>::type)1 << (sizeof(T) * 8 - 1)))) {
+            *flag = 1;
+            return 0;
+        }
+        return a % b;
+    }
+}
+template <typename T>
+__device__ __forceinline__ T w_abs(T a)
+{
+    if constexpr (std::is_same<T, float>::value) return fabsf(a);
+    else if constexpr (std::is_same<T, double>::value) return fabs(a);
+    else return a < 0 ? w_neg(a) : a;
+}
+template <typename T>
+__device__ __forceinline__ T w_min(T a, T b)
+{
+    if constexpr (std::is_same<T, float>::value) return fminf(a, b);
+    else if constexpr (std::is_same<T, double>::value) return fmin(a, b);
+    else return b < a ? b : a;
+}
+template <typename T>
+__device__ __forceinline__ T w_max(T a, T b)
+{
+    if constexpr (std::is_same<T, float>::value) return fmaxf(a, b);
+    else if constexpr (std::is_same<T, double>::value) return fmax(a, b);
+    else return b > a ? b : a;
+}
+
+// The op vocabulary (ndb_op).  `x` holds the NIN loaded inputs.
+template <typename T, int OP, int NIN>
+__device__ __forceinline__ T apply_op(const T *x, T s0, T s1, int *flag)
+{
+    if constexpr (OP == NDB_OP_COPY) return x[0];
+    else if constexpr (OP == NDB_OP_FILL) return s0;
+    else if constexpr (OP == NDB_OP_ADD) return w_add(x[0], x[1]);
+    else if constexpr (OP == NDB_OP_SUB) return w_sub(x[0], x[1]);
+    else if constexpr (OP == NDB_OP_MUL) return w_mul(x[0], x[1]);
+    else if constexpr (OP == NDB_OP_DIV) return w_div(x[0], x[1], flag);
+    else if constexpr (OP == NDB_OP_REM) return w_rem(x[0], x[1], flag);
+    else if constexpr (OP == NDB_OP_MUL_ADD) return w_add(w_mul(x[0], x[1]), x[2]);
+    else if constexpr (OP == NDB_OP_ADD_S) return w_add(x[0], s0);
+    else if constexpr (OP == NDB_OP_SUB_S) return w_sub(x[0], s0);
+    else if constexpr (OP == NDB_OP_MUL_S) return w_mul(x[0], s0);
+    else if constexpr (OP == NDB_OP_DIV_S) return w_div(x[0], s0, flag);
+    else if constexpr (OP == NDB_OP_REM_S) return w_rem(x[0], s0, flag);
+    else if constexpr (OP == NDB_OP_RSUB_S) return w_sub(s0, x[0]);
+    else if constexpr (OP == NDB_OP_RDIV_S) return w_div(s0, x[0], flag);
+    else if constexpr (OP == NDB_OP_NEG) return w_neg(x[0]);
+    else if constexpr (OP == NDB_OP_AXPY) return w_add(x[0], w_mul(s0, x[1]));
+    else if constexpr (OP == NDB_OP_ADD_N) {
+        T acc = w_add(x[0], x[1]);
+#pragma unroll
+        for (int i = 2; i < NIN; ++i) acc = w_add(acc, x[i]);
+        return acc;
+    } else if constexpr (OP == NDB_OP_ABS) return w_abs(x[0]);
+    else if constexpr (OP == NDB_OP_SQRT) {
+        if constexpr (std::is_same<T, float>::value) return sqrtf(x[0]);
+        else if constexpr (std::is_same<T, double>::value) return sqrt(x[0]);
+        else return x[0];
+    } else if constexpr (OP == NDB_OP_MIN) return w_min(x[0], x[1]);
+    else if constexpr (OP == NDB_OP_MAX) return w_max(x[0], x[1]);
+    else if constexpr (OP == NDB_OP_SCALE_ADD) return w_add(w_mul(x[0], s0), w_mul(x[1], s1));
+    else return x[0];
+}
+
+// ---------------------------------------------------------------------------------------------
+// flat, 128-bit vectorised
+template <int NP>
+struct FlatArgs {
+    char *ptr[NP];
+    int64_t n;      // elements
+    int64_t n_vec;  // full 16-byte vectors
+};
+
+template <typename T, int OP, int NIN, int UNROLL>
+__global__ void __launch_bounds__(256) zip_flat_vec(FlatArgs<NIN + 1> a, T s0, T s1, int *flag)
+{
+    using V = Vec128<T>;
+    constexpr int N = V::N;
+    constexpr int NI = NIN > 0 ? NIN : 1;
+    const int64_t base = (int64_t)blockIdx.x * (256 * UNROLL) + threadIdx.x;
+    V in[UNROLL][NI];
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) {
+        const int64_t idx = base + (int64_t)u * 256;
+        if (idx < a.n_vec) {
+#pragma unroll
+            for (int p = 0; p < NIN; ++p) in[u][p] = reinterpret_cast<const V *>(a.ptr[p + 1])[idx];
+        }
+    }
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) {
+        const int64_t idx = base + (int64_t)u * 256;
+        if (idx < a.n_vec) {
+            V o;
+#pragma unroll
+            for (int e = 0; e < N; ++e) {
+                T x[NI];
+#pragma unroll
+                for (int p = 0; p < NIN; ++p) x[p] = in[u][p].v[e];
+                o.v[e] = apply_op<T, OP, NIN>(x, s0, s1, flag);
+            }
+            reinterpret_cast<V *>(a.ptr[0])[idx] = o;
+        }
+    }
+    // ragged tail (< N elements), one thread each
+    if (blockIdx.x == 0) {
+        const int64_t i = a.n_vec * N + threadIdx.x;
+        if (i < a.n) {
+            T x[NI];
+#pragma unroll
+            for (int p = 0; p < NIN; ++p) x[p] = reinterpret_cast<const T *>(a.ptr[p + 1])[i];
+            reinterpret_cast<T *>(a.ptr[0])[i] = apply_op<T, OP, NIN>(x, s0, s1, flag);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// collapsed N-d rows
+template <int NP>
+struct RowsArgs {
+    char *ptr[NP];
+    int64_t ostride[NP][NDB_MAX_NDIM - 1];  // outer strides, elements
+    int64_t istride[NP];                    // inner stride, elements (VEC: 0 or 1)
+    int64_t odim[NDB_MAX_NDIM - 1];
+    int n_outer;
+    int64_t n_rows;
+    int64_t inner_len;  // in units (elements, or vectors when VEC)
+    int64_t blocks_inner;
+    int64_t total_blocks;
+};
+
+template <typename T, int OP, int NIN, bool VEC, int ITEMS>
+__global__ void __launch_bounds__(256) zip_rows(RowsArgs<NIN + 1> a, T s0, T s1, int *flag)
+{
+    using V = Vec128<T>;
+    constexpr int N = VEC ? V::N : 1;
+    constexpr int NI = NIN > 0 ? NIN : 1;
+    constexpr int NP = NIN + 1;
+    const int TX = blockDim.x, TY = blockDim.y;
+    for (int64_t vb = blockIdx.x; vb < a.total_blocks; vb += gridDim.x) {
+        const int64_t brow = vb / a.blocks_inner;
+        const int64_t bin = vb - brow * a.blocks_inner;
+        const int64_t row = brow * TY + threadIdx.y;
+        if (row >= a.n_rows) continue;
+        int64_t off[NP];
+#pragma unroll
+        for (int p = 0; p < NP; ++p) off[p] = 0;
+        int64_t r = row;
+        for (int k = a.n_outer - 1; k >= 0; --k) {
+            const int64_t q = r / a.odim[k];
+            const int64_t idx = r - q * a.odim[k];
+            r = q;
+#pragma unroll
+            for (int p = 0; p < NP; ++p) off[p] += idx * a.ostride[p][k];
+        }
+        const int64_t i0 = bin * ((int64_t)TX * ITEMS) + threadIdx.x;
+        if constexpr (VEC) {
+            V in[ITEMS][NI];
+#pragma unroll
+            for (int p = 0; p < NIN; ++p) {
+                const T *base = reinterpret_cast<const T *>(a.ptr[p + 1]) + off[p + 1];
+                if (a.istride[p + 1] == 0) {
+                    const T s = *base;
+#pragma unroll
+                    for (int it = 0; it < ITEMS; ++it)
+#pragma unroll
+                        for (int e = 0; e < N; ++e) in[it][p].v[e] = s;
+                } else {
+#pragma unroll
+                    for (int it = 0; it < ITEMS; ++it) {
+                        const int64_t i = i0 + (int64_t)it * TX;
+                        if (i < a.inner_len) in[it][p] = reinterpret_cast<const V *>(base)[i];
+                    }
+                }
+            }
+            T *obase = reinterpret_cast<T *>(a.ptr[0]) + off[0];
+#pragma unroll
+            for (int it = 0; it < ITEMS; ++it) {
+                const int64_t i = i0 + (int64_t)it * TX;
+                if (i < a.inner_len) {
+                    V o;
+#pragma unroll
+                    for (int e = 0; e < N; ++e) {
+                        T x[NI];
+#pragma unroll
+                        for (int p = 0; p < NIN; ++p) x[p] = in[it][p].v[e];
+                        o.v[e] = apply_op<T, OP, NIN>(x, s0, s1, flag);
+                    }
+                    reinterpret_cast<V *>(obase)[i] = o;
+                }
+            }
+        } else {
+            T in[ITEMS][NI];
+#pragma unroll
+            for (int it = 0; it < ITEMS; ++it) {
+                const int64_t i = i0 + (int64_t)it * TX;
+                if (i < a.inner_len) {
+#pragma unroll
+                    for (int p = 0; p < NIN; ++p)
+                        in[it][p] = reinterpret_cast<const T *>(a.ptr[p + 1])[off[p + 1] + i * a.istride[p + 1]];
+                }
+            }
+            T *obase = reinterpret_cast<T *>(a.ptr[0]) + off[0];
+#pragma unroll
+            for (int it = 0; it < ITEMS; ++it) {
+                const int64_t i = i0 + (int64_t)it * TX;
+                if (i < a.inner_len) obase[i * a.istride[0]] = apply_op<T, OP, NIN>(in[it], s0, s1, flag);
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// shared-memory tile transpose
+template <int NP>
+struct TileArgs {
+    char *ptr[NP];
+    int64_t xs[NP], ys[NP];  // strides along X (output's fastest axis) and Y (staged axis), elements
+    int64_t ostride[NP][NDB_MAX_NDIM - 2];
+    int64_t odim[NDB_MAX_NDIM - 2];
+    int n_outer;
+    int64_t nx, ny, tiles_x, tiles_y, total_tiles;
+    int slot[NP];  // shared-memory slot of a staged producer, -1 = read straight from global
+};
+
+template <typename T>
+struct TileShape {
+    static constexpr int TS = sizeof(T) == 4 ? 64 : 32;  // 256-byte runs either way
+};
+
+template <typename T, int OP, int NIN>
+__global__ void __launch_bounds__(256) zip_tile(TileArgs<NIN + 1> a, T s0, T s1, int *flag)
+{
+    constexpr int TS = TileShape<T>::TS;
+    constexpr int PASS = 256 / TS;  // rows (or columns) covered per pass
+    constexpr int NI = NIN > 0 ? NIN : 1;
+    constexpr int NP = NIN + 1;
+    __shared__ T tile[ZIP_MAX_STAGED][TS][TS + 1];
+    const int lo = threadIdx.x % TS;  // fast lane index
+    const int hi = threadIdx.x / TS;
+    for (int64_t vb = blockIdx.x; vb < a.total_tiles; vb += gridDim.x) {
+        int64_t t = vb;
+        const int64_t tx = t % a.tiles_x;
+        t /= a.tiles_x;
+        const int64_t ty = t % a.tiles_y;
+        t /= a.tiles_y;
+        int64_t off[NP];
+#pragma unroll
+        for (int p = 0; p < NP; ++p) off[p] = 0;
+        for (int k = a.n_outer - 1; k >= 0; --k) {
+            const int64_t q = t / a.odim[k];
+            const int64_t idx = t - q * a.odim[k];
+            t = q;
+#pragma unroll
+            for (int p = 0; p < NP; ++p) off[p] += idx * a.ostride[p][k];
+        }
+        const int64_t x0 = tx * TS, y0 = ty * TS;
+        // stage: lanes run along Y (the staged producer's dense axis)
+#pragma unroll
+        for (int p = 1; p < NP; ++p) {
+            const int sl = a.slot[p];
+            if (sl >= 0) {
+                const T *src = reinterpret_cast<const T *>(a.ptr[p]) + off[p];
+                const int64_t y = y0 + lo;
+#pragma unroll 4
+                for (int ps = 0; ps < TS / PASS; ++ps) {
+                    const int lx = hi + ps * PASS;
+                    const int64_t x = x0 + lx;
+                    if (y < a.ny && x < a.nx) tile[sl][lx][lo] = src[y * a.ys[p] + x * a.xs[p]];
+                }
+            }
+        }
+        __syncthreads();
+        // compute: lanes run along X
+        {
+            const int64_t x = x0 + lo;
+            T *dst = reinterpret_cast<T *>(a.ptr[0]) + off[0];
+#pragma unroll 4
+            for (int ps = 0; ps < TS / PASS; ++ps) {
+                const int ly = hi + ps * PASS;
+                const int64_t y = y0 + ly;
+                if (y < a.ny && x < a.nx) {
+                    T v[NI];
+#pragma unroll
+                    for (int p = 1; p < NP; ++p) {
+                        const int sl = a.slot[p];
+                        if (sl >= 0) v[p - 1] = tile[sl][lo][ly];
+                        else v[p - 1] = (reinterpret_cast<const T *>(a.ptr[p]) + off[p])[y * a.ys[p] + x * a.xs[p]];
+                    }
+                    dst[y * a.ys[0] + x * a.xs[0]] = apply_op<T, OP, NIN>(v, s0, s1, flag);
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host-side launch
+template <typename T, int OP, int NIN>
+int launch_zip(ndb_ctx *ctx, const ZipPlan &z, const void *scalars)
+{
+    constexpr int NP = NIN + 1;
+    T s0 = T(0), s1 = T(0);
+    const int ns = op_scalars(OP);
+    if (ns > 0) {
+        if (!scalars) {
+            set_error("Zip: op %d needs %d scalar(s)", OP, ns);
+            return NDB_ERR_INVALID_ARG;
+        }
+        s0 = reinterpret_cast<const T *>(scalars)[0];
+        if (ns > 1) s1 = reinterpret_cast<const T *>(scalars)[1];
+    }
+    cudaStream_t st = ctx->stream;
+    const int m = z.ndim;
+    if (z.kernel == NDB_KERNEL_FLAT_VEC) {
+        constexpr int UNROLL = NIN <= 3 ? 4 : (NIN <= 5 ? 2 : 1);
+        FlatArgs<NP> a;
+        for (int p = 0; p < NP; ++p) a.ptr[p] = z.ptr[p];
+        a.n = z.total;
+        a.n_vec = z.total / Vec128<T>::N;
+        int64_t blocks = (a.n_vec + 256 * UNROLL - 1) / (256 * UNROLL);
+        if (blocks < 1) blocks = 1;
+        if (blocks > 0x7fffffffLL) {
+            set_error("Zip: %lld elements exceed one launch", (long long)z.total);
+            return NDB_ERR_UNSUPPORTED;
+        }
+        zip_flat_vec<T, OP, NIN, UNROLL><<<(unsigned)blocks, 256, 0, st>>>(a, s0, s1, ctx->dev_flag);
+        NDB_CHECK_LAUNCH();
+        return NDB_OK;
+    }
+    if (z.kernel == NDB_KERNEL_TILE) {
+        constexpr int TS = TileShape<T>::TS;
+        TileArgs<NP> a;
+        memset(&a, 0, sizeof(a));
+        const int X = m - 1, Y = z.tile_axis;
+        int nslot = 0;
+        for (int p = 0; p < NP; ++p) {
+            a.ptr[p] = z.ptr[p];
+            a.xs[p] = z.stride[p][X];
+            a.ys[p] = z.stride[p][Y];
+            a.slot[p] = (z.staged_mask >> p) & 1 ? nslot++ : -1;
+        }
+        int no = 0;
+        for (int k = 0; k < m; ++k) {
+            if (k == X || k == Y) continue;
+            a.odim[no] = z.dim[k];
+            for (int p = 0; p < NP; ++p) a.ostride[p][no] = z.stride[p][k];
+            ++no;
+        }
+        a.n_outer = no;
+        a.nx = z.dim[X];
+        a.ny = z.dim[Y];
+        a.tiles_x = (a.nx + TS - 1) / TS;
+        a.tiles_y = (a.ny + TS - 1) / TS;
+        a.total_tiles = a.tiles_x * a.tiles_y;
+        for (int k = 0; k < no; ++k) a.total_tiles *= a.odim[k];
+        int64_t blocks = a.total_tiles < (int64_t)1 << 30 ? a.total_tiles : (int64_t)1 << 30;
+        zip_tile<T, OP, NIN><<<(unsigned)blocks, 256, 0, st>>>(a, s0, s1, ctx->dev_flag);
+        NDB_CHECK_LAUNCH();
+        return NDB_OK;
+    }
+    // rows (FLAT with unaligned pointers is the 1-d case of ROWS)
+    {
+        const bool vec = z.kernel == NDB_KERNEL_ROWS_VEC;
+        constexpr int ITEMS = NIN <= 3 ? 4 : 2;
+        RowsArgs<NP> a;
+        memset(&a, 0, sizeof(a));
+        const int inner = m - 1;
+        const int64_t unit = vec ? Vec128<T>::N : 1;
+        for (int p = 0; p < NP; ++p) {
+            a.ptr[p] = z.ptr[p];
+            a.istride[p] = z.stride[p][inner];
+            for (int k = 0; k < inner; ++k) a.ostride[p][k] = z.stride[p][k];
+        }
+        a.n_outer = inner;
+        a.n_rows = 1;
+        for (int k = 0; k < inner; ++k) {
+            a.odim[k] = z.dim[k];
+            a.n_rows *= z.dim[k];
+        }
+        a.inner_len = z.dim[inner] / unit;
+        int tx = 256;
+        while (tx > 1 && tx / 2 >= a.inner_len) tx /= 2;  // smallest power of two covering a short row
+        if (tx < 1) tx = 1;
+        const int ty = 256 / tx;
+        a.blocks_inner = (a.inner_len + (int64_t)tx * ITEMS - 1) / ((int64_t)tx * ITEMS);
+        const int64_t brows = (a.n_rows + ty - 1) / ty;
+        a.total_blocks = a.blocks_inner * brows;
+        int64_t blocks = a.total_blocks < (int64_t)1 << 30 ? a.total_blocks : (int64_t)1 << 30;
+        dim3 bd(tx, ty, 1);
+        if (vec) zip_rows<T, OP, NIN, true, ITEMS><<<(unsigned)blocks, bd, 0, st>>>(a, s0, s1, ctx->dev_flag);
+        else zip_rows<T, OP, NIN, false, ITEMS><<<(unsigned)blocks, bd, 0, st>>>(a, s0, s1, ctx->dev_flag);
+        NDB_CHECK_LAUNCH();
+        return NDB_OK;
+    }
+}
+
+template <typename T>
+int zip_dispatch_typed(ndb_ctx *ctx, const ZipPlan &z, const void *scalars)
+{
+    const int nin = z.n_parts - 1;
+    switch (z.op) {
+#define NDB_ZIP_CASE(OP, NIN) \
+    case OP: return launch_zip<T, OP, NIN>(ctx, z, scalars);
+        NDB_ZIP_CASE(NDB_OP_COPY, 1)
+        NDB_ZIP_CASE(NDB_OP_FILL, 0)
+        NDB_ZIP_CASE(NDB_OP_ADD, 2)
+        NDB_ZIP_CASE(NDB_OP_SUB, 2)
+        NDB_ZIP_CASE(NDB_OP_MUL, 2)
+        NDB_ZIP_CASE(NDB_OP_DIV, 2)
+        NDB_ZIP_CASE(NDB_OP_REM, 2)
+        NDB_ZIP_CASE(NDB_OP_MUL_ADD, 3)
+        NDB_ZIP_CASE(NDB_OP_ADD_S, 1)
+        NDB_ZIP_CASE(NDB_OP_SUB_S, 1)
+        NDB_ZIP_CASE(NDB_OP_MUL_S, 1)
+        NDB_ZIP_CASE(NDB_OP_DIV_S, 1)
+        NDB_ZIP_CASE(NDB_OP_REM_S, 1)
+        NDB_ZIP_CASE(NDB_OP_RSUB_S, 1)
+        NDB_ZIP_CASE(NDB_OP_RDIV_S, 1)
+        NDB_ZIP_CASE(NDB_OP_NEG, 1)
+        NDB_ZIP_CASE(NDB_OP_AXPY, 2)
+        NDB_ZIP_CASE(NDB_OP_ABS, 1)
+        NDB_ZIP_CASE(NDB_OP_SQRT, 1)
+        NDB_ZIP_CASE(NDB_OP_MIN, 2)
+        NDB_ZIP_CASE(NDB_OP_MAX, 2)
+        NDB_ZIP_CASE(NDB_OP_SCALE_ADD, 2)
+#undef NDB_ZIP_CASE
+    case NDB_OP_ADD_N:
+        switch (nin) {
+        case 2: return launch_zip<T, NDB_OP_ADD_N, 2>(ctx, z, scalars);
+        case 3: return launch_zip<T, NDB_OP_ADD_N, 3>(ctx, z, scalars);
+        case 4: return launch_zip<T, NDB_OP_ADD_N, 4>(ctx, z, scalars);
+        case 5: return launch_zip<T, NDB_OP_ADD_N, 5>(ctx, z, scalars);
+        case 6: return launch_zip<T, NDB_OP_ADD_N, 6>(ctx, z, scalars);
+        case 7: return launch_zip<T, NDB_OP_ADD_N, 7>(ctx, z, scalars);
+        case 8: return launch_zip<T, NDB_OP_ADD_N, 8>(ctx, z, scalars);
+        default: break;
+        }
+        break;
+    default: break;
+    }
+    set_error("Zip: op %d with %d inputs has no kernel", z.op, nin);
+    return NDB_ERR_UNSUPPORTED;
+}
+
+int zip_dispatch_f32(ndb_ctx *ctx, const ZipPlan &z, const void *scalars);
+int zip_dispatch_f64(ndb_ctx *ctx, const ZipPlan &z, const void *scalars);
+int zip_dispatch_i32(ndb_ctx *ctx, const ZipPlan &z, const void *scalars);
+int zip_dispatch_i64(ndb_ctx *ctx, const ZipPlan &z, const void *scalars);
+
+}  // namespace ndb

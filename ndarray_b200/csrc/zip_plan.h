@@ -1,0 +1,30 @@
+#pragma once
+#include "common.h"
+
+namespace ndb {
+
+constexpr int ZIP_MAX_STAGED = 2;  // producers transposed through shared memory per tile kernel
+
+struct ZipPlan {
+    int kernel;  // ndb_kernel_class
+    int ndim;    // collapsed rank (>= 1 unless NOOP)
+    int n_parts;
+    int dtype;
+    int op;
+    int tile_axis;
+    uint32_t staged_mask;
+    int64_t total;  // number of elements
+    int64_t dim[NDB_MAX_NDIM];
+    int64_t stride[NDB_MAX_PARTS][NDB_MAX_NDIM];
+    int64_t offset[NDB_MAX_PARTS];
+    char *ptr[NDB_MAX_PARTS];  // base pointers with `offset` applied
+};
+
+int make_zip_plan(int op, int n_parts, const ndb_view *parts, ZipPlan *zp);
+
+bool is_layout_c(const ndb_view *v);
+bool is_layout_f(const ndb_view *v);
+uint32_t array_layout(const ndb_view *v);
+int layout_tendency(uint32_t l);
+
+}  // namespace ndb

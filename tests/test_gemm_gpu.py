@@ -1,0 +1,198 @@
+"""GPU parity: general_mat_mul / dot / general_mat_vec_mul and the CBLAS drop-in symbols.
+
+The arithmetic of ndarray's GEMM lives in the un-vendored `matrixmultiply` crate, so — like ndarray's
+own tests — parity is to tolerance against the naive and Kahan references (oracle modes 0 / 1):
+  tests/oper.rs:595-635       relative 1e-7 / abs 1e-12 vs naive, strides {1,2,-1,-2}^2, 9 sizes, f64
+  accuracy.rs:143-223         max|diff| / max|ref| < 1e-5 (f32), 1e-14 (f64; we allow 1e-12*sqrt(k)/k-scaled)
+  tests/oper.rs:321-379       exact equality on integer-valued f32 across C/F operand layouts."""
+import ctypes as C
+import math
+
+import numpy as np
+import pytest
+
+from .test_zip_gpu import Mirror
+
+pytestmark = pytest.mark.gpu
+
+
+def rel_norm(got, ref):
+    return float(np.abs(got.astype(np.float64) - ref.astype(np.float64)).max() / max(np.abs(ref).max(), 1e-300))
+
+
+def nd_slice_np(a, s1, s2):
+    """numpy view equal to ndarray's a.slice(s![..;s1, ..;s2]) (negative step = reversed, then strided)."""
+    r = a[::-1] if s1 < 0 else a
+    r = r[::abs(s1)]
+    r = r[:, ::-1] if s2 < 0 else r
+    return r[:, ::abs(s2)]
+
+
+def range_mat(m, n, dtype):
+    return np.arange(m * n, dtype=dtype).reshape(m, n)
+
+
+def test_gen_mat_mul_reference_sweep(nd, oracle):  # tests/oper.rs:595-635
+    alpha, beta = -2.3, math.pi
+    sizes = [(4, 4, 4), (8, 8, 8), (17, 15, 16), (4, 17, 3), (17, 3, 22), (19, 18, 2), (16, 17, 15), (15, 16, 17), (67, 63, 62)]
+    for s1 in (1, 2, -1, -2):
+        for s2 in (1, 2, -1, -2):
+            for (m, k, n) in sizes:
+                ma, mb, mc = (Mirror(nd, range_mat(*shp, np.float64)) for shp in ((m, k), (k, n), (m, n)))
+                ha, da = ma.view(lambda a: nd_slice_np(a, s1, s2))
+                hb, db = mb.view(lambda a: nd_slice_np(a, s2, s2))
+                hc, dc = mc.view(lambda a: nd_slice_np(a, s1, s2))
+                assert oracle.gemm(alpha, ha, hb, beta, hc) == 0
+                nd.general_mat_mul(alpha, da, db, beta, dc)
+                np.testing.assert_allclose(mc.download(), mc.host, rtol=1e-7, atol=1e-12)
+
+
+def test_gen_mat_mul_i32_exact(nd, oracle):  # tests/oper.rs:653-681
+    for (m, k, n) in [(4, 4, 4), (17, 15, 16), (67, 63, 62)]:
+        a, b, c = range_mat(m, k, np.int32), range_mat(k, n, np.int32), range_mat(m, n, np.int32)
+        want = c.copy()
+        assert oracle.gemm(-1, a, b, 1, want) == 0
+        dc = nd.Array.from_numpy(c)
+        nd.general_mat_mul(-1, nd.Array.from_numpy(a), nd.Array.from_numpy(b), 1, dc)
+        assert np.array_equal(dc.to_numpy(), want)
+
+
+def test_mat_mul_layouts_exact(nd):  # tests/oper.rs:321-399
+    for (m, n, k) in [(8, 8, 8), (10, 17, 9), (64, 64, 64), (130, 70, 40)]:
+        a = range_mat(m, n, np.float32) % 16
+        b = (range_mat(n, k, np.float32) % 8) / np.float32(4.)
+        want = (a.astype(np.float64) @ b.astype(np.float64)).astype(np.float32)
+        for af in (False, True):
+            for bf in (False, True):
+                da = nd.Array.from_numpy(np.asfortranarray(a) if af else a)
+                db = nd.Array.from_numpy(np.asfortranarray(b) if bf else b)
+                c = da.dot(db)
+                assert np.array_equal(c.to_numpy(), want)
+                # dot's output is F-order only when both inputs have unit row stride (impl_linalg.rs:319-327)
+                assert (c.strides == (1, m)) == (af and bf and m > 1 and k > 1) or m == 1 or k == 1
+                # transposed product equals product of transposes
+                ct = db.t().dot(da.t())
+                assert np.array_equal(ct.to_numpy(), want.T)
+
+
+@pytest.mark.parametrize("dtype,tol", [(np.float32, 1e-5), (np.float64, 1e-14)])
+def test_accuracy_random(nd, oracle, dtype, tol):  # accuracy.rs:143-223
+    rng = np.random.default_rng(42)
+    for _ in range(6):
+        m, k, n = int(rng.integers(15, 128)), int(rng.integers(15, 128)), int(rng.integers(15, 512))
+        a = rng.standard_normal((m, k)).astype(dtype)
+        b = rng.standard_normal((k, n)).astype(dtype)
+        ref = np.zeros((m, n), dtype)
+        assert oracle.gemm(1, a, b, 0, ref, mode=1, threads=4) == 0
+        c = nd.Array.from_numpy(a).dot(nd.Array.from_numpy(b)).to_numpy()
+        assert rel_norm(c, ref) < tol * (1 if dtype == np.float32 else 8)
+        # stride-2 operands (accuracy.rs:205-223)
+        a2 = rng.standard_normal((2 * m, 2 * k)).astype(dtype)
+        ma = Mirror(nd, a2)
+        ha, da = ma.view(lambda x: x[::2, ::2])
+        ref2 = np.zeros((m, n), dtype)
+        oracle.gemm(1, ha, b, 0, ref2, mode=1, threads=4)
+        c2 = da.dot(nd.Array.from_numpy(b)).to_numpy()
+        assert rel_norm(c2, ref2) < tol * (1 if dtype == np.float32 else 8)
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_medium_gemm_all_layouts(nd, dtype):
+    """512..1024-sized problems that take the tensor-core path, every C/F combination + alpha/beta, against
+    numpy in float64."""
+    rng = np.random.default_rng(3)
+    tol = 1e-5 if dtype == np.float32 else 1e-12
+    for (m, k, n) in [(512, 512, 512), (768, 1024, 640), (1000, 520, 776), (129, 2048, 257)]:
+        a = rng.standard_normal((m, k)).astype(dtype)
+        b = rng.standard_normal((k, n)).astype(dtype)
+        c0 = rng.standard_normal((m, n)).astype(dtype)
+        for alpha, beta in [(1.0, 0.0), (-2.3, math.pi)]:
+            ref = alpha * (a.astype(np.float64) @ b.astype(np.float64)) + beta * c0.astype(np.float64)
+            for af in (False, True):
+                for bf in (False, True):
+                    for cf in (False, True):
+                        da = nd.Array.from_numpy(np.asfortranarray(a) if af else a)
+                        db = nd.Array.from_numpy(np.asfortranarray(b) if bf else b)
+                        dc = nd.Array.from_numpy(np.asfortranarray(c0) if cf else c0)
+                        nd.general_mat_mul(alpha, da, db, beta, dc)
+                        err = rel_norm(dc.to_numpy(), ref)
+                        assert err < tol * math.sqrt(k) / 8, (m, k, n, alpha, af, bf, cf, err)
+
+
+def test_beta_zero_never_reads_c(nd):
+    a = nd.Array.from_numpy(np.eye(64, dtype=np.float64))
+    b = nd.Array.from_numpy(np.full((64, 64), 2.0))
+    c = nd.Array.from_numpy(np.full((64, 64), np.nan))
+    nd.general_mat_mul(1.0, a, b, 0.0, c)
+    assert np.array_equal(c.to_numpy(), np.full((64, 64), 2.0))
+    big = nd.Array.from_numpy(np.full((512, 512), np.nan))
+    nd.general_mat_mul(1.0, nd.Array.from_numpy(np.eye(512)), nd.Array.from_numpy(np.full((512, 512), 3.0)), 0.0, big)
+    assert np.array_equal(big.to_numpy(), np.full((512, 512), 3.0))
+
+
+def test_zero_sized_and_mismatch(nd):  # tests/oper.rs:464-483
+    for (m, k, n) in [(0, 4, 5), (4, 0, 5), (4, 5, 0)]:
+        a = nd.Array.zeros((m, k), np.float64)
+        b = nd.Array.zeros((k, n), np.float64)
+        c = a.dot(b)
+        assert c.shape == (m, n)
+        assert np.array_equal(c.to_numpy(), np.zeros((m, n)))
+    with pytest.raises(nd.ShapeError, match="not compatible for matrix multiplication"):
+        nd.general_mat_mul(1.0, nd.Array.zeros((3, 4), np.float64), nd.Array.zeros((5, 3), np.float64), 0.0,
+                           nd.Array.zeros((3, 3), np.float64))
+
+
+def test_broadcast_and_reversed_operands(nd):  # tests/oper.rs:427-460
+    rng = np.random.default_rng(1)
+    a = rng.standard_normal((8, 8))
+    x = rng.standard_normal(8)
+    da = nd.Array.from_numpy(a)
+    bx = nd.Array.from_numpy(x).broadcast((8, 8))
+    np.testing.assert_allclose(da.dot(bx).to_numpy(), a @ np.broadcast_to(x, (8, 8)), rtol=1e-12)
+    rev = da.slice(nd.s_[::-1, ::-1])
+    np.testing.assert_allclose(rev.dot(da).to_numpy(), a[::-1, ::-1] @ a, rtol=1e-12)
+
+
+def test_gemv_and_vec_mat(nd):  # tests/oper.rs:686-790
+    rng = np.random.default_rng(2)
+    for (m, k) in [(10, 10), (17, 15), (64, 130), (300, 77)]:
+        a = rng.standard_normal((m, k))
+        x = rng.standard_normal(k)
+        y0 = rng.standard_normal(m)
+        for order in ("C", "F"):
+            da = nd.Array.from_numpy(np.asfortranarray(a) if order == "F" else a)
+            y = nd.Array.from_numpy(y0)
+            nd.general_mat_vec_mul(-2.3, da, nd.Array.from_numpy(x), math.pi, y)
+            np.testing.assert_allclose(y.to_numpy(), -2.3 * (a @ x) + math.pi * y0, rtol=1e-10, atol=1e-12)
+            np.testing.assert_allclose(da.dot(nd.Array.from_numpy(x)).to_numpy(), a @ x, rtol=1e-10, atol=1e-12)
+            v = rng.standard_normal(m)
+            np.testing.assert_allclose(nd.Array.from_numpy(v).dot(da).to_numpy(), v @ a, rtol=1e-10, atol=1e-12)
+
+
+def test_cblas_dropin_symbols(nd):
+    """Call the exported cblas_dgemm / cblas_sgemm / cblas_ddot with HOST pointers, the way ndarray's `blas`
+    feature does (impl_linalg.rs:466-491): row-major C with transposed operands, ld > n padding kept intact."""
+    L = nd.lib()
+    L.cblas_dgemm.restype = None
+    L.cblas_dgemm.argtypes = [C.c_int] * 6 + [C.c_double, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_double, C.c_void_p, C.c_int]
+    L.cblas_sgemm.restype = None
+    L.cblas_sgemm.argtypes = [C.c_int] * 6 + [C.c_float, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_float, C.c_void_p, C.c_int]
+    L.cblas_ddot.restype = C.c_double
+    L.cblas_ddot.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int]
+    rng = np.random.default_rng(8)
+    m, n, k = 33, 21, 47
+    a = rng.standard_normal((m, k))
+    bt = rng.standard_normal((n, k + 3))          # B stored transposed with padding: ldb = k + 3
+    c = rng.standard_normal((m, n + 5))           # ldc = n + 5
+    c0 = c.copy()
+    L.cblas_dgemm(101, 111, 112, m, n, k, -2.3, a.ctypes.data, k, bt.ctypes.data, k + 3, 0.5, c.ctypes.data, n + 5)
+    np.testing.assert_allclose(c[:, :n], -2.3 * a @ bt[:, :k].T + 0.5 * c0[:, :n], rtol=1e-12)
+    assert np.array_equal(c[:, n:], c0[:, n:])    # padding untouched
+    af = np.asfortranarray(a.astype(np.float32))
+    bf = np.asfortranarray(rng.standard_normal((k, n)).astype(np.float32))
+    cf = np.zeros((m, n), np.float32, order="F")
+    L.cblas_sgemm(102, 111, 111, m, n, k, 1.0, af.ctypes.data, m, bf.ctypes.data, k, 0.0, cf.ctypes.data, m)
+    assert rel_norm(cf, af.astype(np.float64) @ bf.astype(np.float64)) < 1e-5
+    x, y = rng.standard_normal(100), rng.standard_normal(100)
+    got = L.cblas_ddot(50, x.ctypes.data, 2, y.ctypes.data, -2)
+    assert abs(got - float(x[:100:2] @ y[:100:2][::-1])) < 1e-12

