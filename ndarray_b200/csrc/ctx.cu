@@ -164,6 +164,13 @@ int ndb_ctx_create(int device, ndb_ctx **out)
     NDB_CUDA(cudaMallocHost((void **)&ctx->host_flag, sizeof(int)));
     NDB_CUDA(cudaMallocHost(&ctx->host_scalar, 64));
     *ctx->host_flag = 0;
+    {
+        // keep freed blocks cached in the pool instead of returning them to the OS at every sync
+        cudaMemPool_t pool;
+        NDB_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
+        uint64_t keep = UINT64_MAX;
+        NDB_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+    }
     int st = ensure_workspace(ctx, size_t(8) << 20);
     if (st != NDB_OK) return st;
     *out = ctx;
@@ -211,7 +218,9 @@ int ndb_alloc(ndb_ctx *ctx, size_t bytes, void **dptr)
     DeviceGuard g(ctx->device);
     *dptr = nullptr;
     if (bytes == 0) bytes = 16;  // a valid, dereferenceable-by-nobody pointer for empty arrays
-    NDB_CUDA(cudaMalloc(dptr, bytes));
+    // Stream-ordered allocation from the device's default pool (kept warm, see ndb_ctx_create): a fresh
+    // output per map_collect / sum_axis costs microseconds, not a cudaMalloc + implicit sync.
+    NDB_CUDA(cudaMallocAsync(dptr, bytes, ctx->stream));
     return NDB_OK;
 }
 
@@ -220,7 +229,7 @@ int ndb_free(ndb_ctx *ctx, void *dptr)
     if (!ctx) return NDB_ERR_INVALID_ARG;
     if (!dptr) return NDB_OK;
     DeviceGuard g(ctx->device);
-    NDB_CUDA(cudaFree(dptr));
+    NDB_CUDA(cudaFreeAsync(dptr, ctx->stream));
     return NDB_OK;
 }
 

@@ -14,6 +14,7 @@
 // b*c+a rounds twice like Rust; integer +,-,* wrap (done in unsigned); integer / and % raise the
 // device flag where Rust panics.
 #pragma once
+#include <cstdlib>
 #include <type_traits>
 
 #include "common.h"
@@ -94,18 +95,18 @@ __device__ __forceinline__ T w_abs(T a)
     else if constexpr (std::is_same<T, double>::value) return fabs(a);
     else return a < 0 ? w_neg(a) : a;
 }
+// min/max: f32::min / f32::max ignore a NaN operand; the sign of a zero result is not pinned by ndarray,
+// so both the kernels and the oracle use the same explicit rule (first operand wins ties).
 template <typename T>
 __device__ __forceinline__ T w_min(T a, T b)
 {
-    if constexpr (std::is_same<T, float>::value) return fminf(a, b);
-    else if constexpr (std::is_same<T, double>::value) return fmin(a, b);
+    if constexpr (std::is_floating_point<T>::value) return (b < a || a != a) ? b : a;
     else return b < a ? b : a;
 }
 template <typename T>
 __device__ __forceinline__ T w_max(T a, T b)
 {
-    if constexpr (std::is_same<T, float>::value) return fmaxf(a, b);
-    else if constexpr (std::is_same<T, double>::value) return fmax(a, b);
+    if constexpr (std::is_floating_point<T>::value) return (b > a || a != a) ? b : a;
     else return b > a ? b : a;
 }
 
@@ -213,22 +214,29 @@ struct RowsArgs {
     int64_t total_blocks;
 };
 
-template <typename T, int OP, int NIN, bool VEC, int ITEMS>
-__global__ void __launch_bounds__(256) zip_rows(RowsArgs<NIN + 1> a, T s0, T s1, int *flag)
+// Element offsets of outer row `row` for every producer.  The common collapsed shapes have one outer
+// axis (no division at all); otherwise 32-bit division when the row count allows it.
+template <int NP>
+__device__ __forceinline__ void row_offsets(const RowsArgs<NP> &a, int64_t row, int64_t (&off)[NP])
 {
-    using V = Vec128<T>;
-    constexpr int N = VEC ? V::N : 1;
-    constexpr int NI = NIN > 0 ? NIN : 1;
-    constexpr int NP = NIN + 1;
-    const int TX = blockDim.x, TY = blockDim.y;
-    for (int64_t vb = blockIdx.x; vb < a.total_blocks; vb += gridDim.x) {
-        const int64_t brow = vb / a.blocks_inner;
-        const int64_t bin = vb - brow * a.blocks_inner;
-        const int64_t row = brow * TY + threadIdx.y;
-        if (row >= a.n_rows) continue;
-        int64_t off[NP];
+    if (a.n_outer == 1) {
 #pragma unroll
-        for (int p = 0; p < NP; ++p) off[p] = 0;
+        for (int p = 0; p < NP; ++p) off[p] = row * a.ostride[p][0];
+        return;
+    }
+#pragma unroll
+    for (int p = 0; p < NP; ++p) off[p] = 0;
+    if (a.n_rows <= 0x7fffffffLL) {
+        unsigned r = (unsigned)row;
+        for (int k = a.n_outer - 1; k >= 0; --k) {
+            const unsigned d = (unsigned)a.odim[k];
+            const unsigned q = r / d;
+            const int64_t idx = (int64_t)(r - q * d);
+            r = q;
+#pragma unroll
+            for (int p = 0; p < NP; ++p) off[p] += idx * a.ostride[p][k];
+        }
+    } else {
         int64_t r = row;
         for (int k = a.n_outer - 1; k >= 0; --k) {
             const int64_t q = r / a.odim[k];
@@ -237,58 +245,90 @@ __global__ void __launch_bounds__(256) zip_rows(RowsArgs<NIN + 1> a, T s0, T s1,
 #pragma unroll
             for (int p = 0; p < NP; ++p) off[p] += idx * a.ostride[p][k];
         }
-        const int64_t i0 = bin * ((int64_t)TX * ITEMS) + threadIdx.x;
-        if constexpr (VEC) {
-            V in[ITEMS][NI];
+    }
+}
+
+// ROWWISE=false: a thread owns ITEMS units of ONE row (long rows).
+// ROWWISE=true : a thread owns one unit in each of ITEMS rows (rows that fit one pass of the block).
+template <typename T, int OP, int NIN, bool VEC, bool ROWWISE, int ITEMS>
+__global__ void __launch_bounds__(256) zip_rows(RowsArgs<NIN + 1> a, T s0, T s1, int *flag)
+{
+    using V = Vec128<T>;
+    using E = typename std::conditional<VEC, V, T>::type;  // the unit moved per access
+    constexpr int N = VEC ? V::N : 1;
+    constexpr int NI = NIN > 0 ? NIN : 1;
+    constexpr int NP = NIN + 1;
+    const int TX = blockDim.x, TY = blockDim.y;
+    for (int64_t vb = blockIdx.x; vb < a.total_blocks; vb += gridDim.x) {
+        int64_t brow, bin;
+        if (a.blocks_inner == 1) {
+            brow = vb;
+            bin = 0;
+        } else if (a.total_blocks <= 0x7fffffffLL) {
+            const unsigned q = (unsigned)vb / (unsigned)a.blocks_inner;
+            brow = q;
+            bin = (int64_t)((unsigned)vb - q * (unsigned)a.blocks_inner);
+        } else {
+            brow = vb / a.blocks_inner;
+            bin = vb - brow * a.blocks_inner;
+        }
+        E in[ITEMS][NI];
+        int64_t ooff[ITEMS];  // element offset of each item's output unit
+        bool live[ITEMS];
+        int64_t off[NP];
+        bool row_ok = true;
+        if constexpr (!ROWWISE) {  // one row for all items: decompose it once
+            const int64_t row0 = brow * TY + threadIdx.y;
+            row_ok = row0 < a.n_rows;
+            if (row_ok) row_offsets<NP>(a, row0, off);
+        }
+#pragma unroll
+        for (int it = 0; it < ITEMS; ++it) {
+            int64_t i;
+            if constexpr (ROWWISE) {
+                const int64_t row = brow * ((int64_t)TY * ITEMS) + (int64_t)it * TY + threadIdx.y;
+                i = bin * TX + threadIdx.x;
+                live[it] = row < a.n_rows && i < a.inner_len;
+                if (live[it]) row_offsets<NP>(a, row, off);
+            } else {
+                i = bin * ((int64_t)TX * ITEMS) + (int64_t)it * TX + threadIdx.x;
+                live[it] = row_ok && i < a.inner_len;
+            }
+            ooff[it] = 0;
+            if (!live[it]) continue;
+            ooff[it] = off[0] + i * N * a.istride[0];
 #pragma unroll
             for (int p = 0; p < NIN; ++p) {
-                const T *base = reinterpret_cast<const T *>(a.ptr[p + 1]) + off[p + 1];
-                if (a.istride[p + 1] == 0) {
-                    const T s = *base;
+                const T *src = reinterpret_cast<const T *>(a.ptr[p + 1]) + off[p + 1];
+                if constexpr (VEC) {
+                    if (a.istride[p + 1] == 0) {
+                        const T sv = *src;
 #pragma unroll
-                    for (int it = 0; it < ITEMS; ++it)
-#pragma unroll
-                        for (int e = 0; e < N; ++e) in[it][p].v[e] = s;
+                        for (int e = 0; e < N; ++e) in[it][p].v[e] = sv;
+                    } else {
+                        in[it][p] = reinterpret_cast<const V *>(src)[i];
+                    }
                 } else {
-#pragma unroll
-                    for (int it = 0; it < ITEMS; ++it) {
-                        const int64_t i = i0 + (int64_t)it * TX;
-                        if (i < a.inner_len) in[it][p] = reinterpret_cast<const V *>(base)[i];
-                    }
+                    in[it][p] = src[i * a.istride[p + 1]];
                 }
             }
-            T *obase = reinterpret_cast<T *>(a.ptr[0]) + off[0];
+        }
 #pragma unroll
-            for (int it = 0; it < ITEMS; ++it) {
-                const int64_t i = i0 + (int64_t)it * TX;
-                if (i < a.inner_len) {
-                    V o;
+        for (int it = 0; it < ITEMS; ++it) {
+            if (!live[it]) continue;
+            T *dst = reinterpret_cast<T *>(a.ptr[0]) + ooff[it];
+            if constexpr (VEC) {
+                V o;
 #pragma unroll
-                    for (int e = 0; e < N; ++e) {
-                        T x[NI];
+                for (int e = 0; e < N; ++e) {
+                    T x[NI];
 #pragma unroll
-                        for (int p = 0; p < NIN; ++p) x[p] = in[it][p].v[e];
-                        o.v[e] = apply_op<T, OP, NIN>(x, s0, s1, flag);
-                    }
-                    reinterpret_cast<V *>(obase)[i] = o;
+                    for (int p = 0; p < NIN; ++p) x[p] = in[it][p].v[e];
+                    o.v[e] = apply_op<T, OP, NIN>(x, s0, s1, flag);
                 }
-            }
-        } else {
-            T in[ITEMS][NI];
-#pragma unroll
-            for (int it = 0; it < ITEMS; ++it) {
-                const int64_t i = i0 + (int64_t)it * TX;
-                if (i < a.inner_len) {
-#pragma unroll
-                    for (int p = 0; p < NIN; ++p)
-                        in[it][p] = reinterpret_cast<const T *>(a.ptr[p + 1])[off[p + 1] + i * a.istride[p + 1]];
-                }
-            }
-            T *obase = reinterpret_cast<T *>(a.ptr[0]) + off[0];
-#pragma unroll
-            for (int it = 0; it < ITEMS; ++it) {
-                const int64_t i = i0 + (int64_t)it * TX;
-                if (i < a.inner_len) obase[i * a.istride[0]] = apply_op<T, OP, NIN>(in[it], s0, s1, flag);
+                *reinterpret_cast<V *>(dst) = o;
+            } else {
+                *dst = apply_op<T, OP, NIN>(in[it], s0, s1, flag);
             }
         }
     }
@@ -304,7 +344,8 @@ struct TileArgs {
     int64_t odim[NDB_MAX_NDIM - 2];
     int n_outer;
     int64_t nx, ny, tiles_x, tiles_y, total_tiles;
-    int slot[NP];  // shared-memory slot of a staged producer, -1 = read straight from global
+    int slot[NP];   // shared-memory slot of a staged producer, -1 = read straight from global
+    int y_fastest;  // block order: 1 = consecutive blocks walk Y tiles first
 };
 
 template <typename T>
@@ -312,6 +353,33 @@ struct TileShape {
     static constexpr int TS = sizeof(T) == 4 ? 64 : 32;  // 256-byte runs either way
 };
 
+template <int NP>
+__device__ __forceinline__ void tile_coords(const TileArgs<NP> &a, int64_t vb, int64_t &tx, int64_t &ty, int64_t (&off)[NP])
+{
+    int64_t t = vb;
+    if (a.y_fastest) {
+        ty = t % a.tiles_y;
+        t /= a.tiles_y;
+        tx = t % a.tiles_x;
+        t /= a.tiles_x;
+    } else {
+        tx = t % a.tiles_x;
+        t /= a.tiles_x;
+        ty = t % a.tiles_y;
+        t /= a.tiles_y;
+    }
+#pragma unroll
+    for (int p = 0; p < NP; ++p) off[p] = 0;
+    for (int k = a.n_outer - 1; k >= 0; --k) {
+        const int64_t q = t / a.odim[k];
+        const int64_t idx = t - q * a.odim[k];
+        t = q;
+#pragma unroll
+        for (int p = 0; p < NP; ++p) off[p] += idx * a.ostride[p][k];
+    }
+}
+
+// scalar form: any signed strides
 template <typename T, int OP, int NIN>
 __global__ void __launch_bounds__(256) zip_tile(TileArgs<NIN + 1> a, T s0, T s1, int *flag)
 {
@@ -323,21 +391,8 @@ __global__ void __launch_bounds__(256) zip_tile(TileArgs<NIN + 1> a, T s0, T s1,
     const int lo = threadIdx.x % TS;  // fast lane index
     const int hi = threadIdx.x / TS;
     for (int64_t vb = blockIdx.x; vb < a.total_tiles; vb += gridDim.x) {
-        int64_t t = vb;
-        const int64_t tx = t % a.tiles_x;
-        t /= a.tiles_x;
-        const int64_t ty = t % a.tiles_y;
-        t /= a.tiles_y;
-        int64_t off[NP];
-#pragma unroll
-        for (int p = 0; p < NP; ++p) off[p] = 0;
-        for (int k = a.n_outer - 1; k >= 0; --k) {
-            const int64_t q = t / a.odim[k];
-            const int64_t idx = t - q * a.odim[k];
-            t = q;
-#pragma unroll
-            for (int p = 0; p < NP; ++p) off[p] += idx * a.ostride[p][k];
-        }
+        int64_t tx, ty, off[NP];
+        tile_coords<NP>(a, vb, tx, ty, off);
         const int64_t x0 = tx * TS, y0 = ty * TS;
         // stage: lanes run along Y (the staged producer's dense axis)
 #pragma unroll
@@ -379,6 +434,95 @@ __global__ void __launch_bounds__(256) zip_tile(TileArgs<NIN + 1> a, T s0, T s1,
     }
 }
 
+// 128-bit form: staged producers have ys == 1, everything else xs == 1, all rows 16-byte aligned and the
+// tile extents multiples of the vector width (checked on the host).  Every thread first issues ALL its
+// global loads (PASSES vectors per producer), then the staged ones go through shared memory.
+template <typename T, int OP, int NIN>
+__global__ void __launch_bounds__(256) zip_tile_vec(TileArgs<NIN + 1> a, T s0, T s1, int *flag)
+{
+    using V = Vec128<T>;
+    constexpr int N = V::N;
+    constexpr int TS = TileShape<T>::TS;
+    constexpr int VPR = TS / N;       // vectors per tile row (16)
+    constexpr int RPP = 256 / VPR;    // tile rows per pass (16)
+    constexpr int PASSES = TS / RPP;  // 4 (f32) / 2 (f64)
+    constexpr int NI = NIN > 0 ? NIN : 1;
+    constexpr int NP = NIN + 1;
+    __shared__ T tile[ZIP_MAX_STAGED][TS][TS + 1];
+    const int vl = threadIdx.x % VPR;
+    const int hi = threadIdx.x / VPR;
+    for (int64_t vb = blockIdx.x; vb < a.total_tiles; vb += gridDim.x) {
+        int64_t tx, ty, off[NP];
+        tile_coords<NP>(a, vb, tx, ty, off);
+        const int64_t x0 = tx * TS, y0 = ty * TS;
+        V ld[NI][PASSES];
+#pragma unroll
+        for (int p = 1; p < NP; ++p) {
+            const T *src = reinterpret_cast<const T *>(a.ptr[p]) + off[p];
+            if (a.slot[p] >= 0) {
+                const int64_t y = y0 + (int64_t)vl * N;  // lanes along Y
+#pragma unroll
+                for (int ps = 0; ps < PASSES; ++ps) {
+                    const int64_t x = x0 + hi + ps * RPP;
+                    if (x < a.nx && y < a.ny) ld[p - 1][ps] = *reinterpret_cast<const V *>(src + y + x * a.xs[p]);
+                }
+            } else {
+                const int64_t x = x0 + (int64_t)vl * N;  // lanes along X
+#pragma unroll
+                for (int ps = 0; ps < PASSES; ++ps) {
+                    const int64_t y = y0 + hi + ps * RPP;
+                    if (x < a.nx && y < a.ny) ld[p - 1][ps] = *reinterpret_cast<const V *>(src + y * a.ys[p] + x);
+                }
+            }
+        }
+#pragma unroll
+        for (int p = 1; p < NP; ++p) {
+            const int sl = a.slot[p];
+            if (sl >= 0) {
+#pragma unroll
+                for (int ps = 0; ps < PASSES; ++ps) {
+                    const int lx = hi + ps * RPP;
+                    if (x0 + lx < a.nx && y0 + (int64_t)vl * N < a.ny) {
+#pragma unroll
+                        for (int e = 0; e < N; ++e) tile[sl][lx][vl * N + e] = ld[p - 1][ps].v[e];
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        {
+            const int64_t x = x0 + (int64_t)vl * N;
+            T *dst = reinterpret_cast<T *>(a.ptr[0]) + off[0];
+#pragma unroll
+            for (int ps = 0; ps < PASSES; ++ps) {
+                const int ly = hi + ps * RPP;
+                const int64_t y = y0 + ly;
+                if (x < a.nx && y < a.ny) {
+                    V o;
+#pragma unroll
+                    for (int e = 0; e < N; ++e) {
+                        T v[NI];
+#pragma unroll
+                        for (int p = 1; p < NP; ++p) {
+                            const int sl = a.slot[p];
+                            v[p - 1] = sl >= 0 ? tile[sl][vl * N + e][ly] : ld[p - 1][ps].v[e];
+                        }
+                        o.v[e] = apply_op<T, OP, NIN>(v, s0, s1, flag);
+                    }
+                    *reinterpret_cast<V *>(dst + y * a.ys[0] + x) = o;
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+
+inline int env_int(const char *name, int dflt)
+{
+    const char *e = getenv(name);
+    return e ? atoi(e) : dflt;
+}
+
 // ---------------------------------------------------------------------------------------------
 // host-side launch
 template <typename T, int OP, int NIN>
@@ -397,12 +541,13 @@ int launch_zip(ndb_ctx *ctx, const ZipPlan &z, const void *scalars)
     }
     cudaStream_t st = ctx->stream;
     const int m = z.ndim;
+    constexpr int64_t VN = Vec128<T>::N;
     if (z.kernel == NDB_KERNEL_FLAT_VEC) {
         constexpr int UNROLL = NIN <= 3 ? 4 : (NIN <= 5 ? 2 : 1);
         FlatArgs<NP> a;
         for (int p = 0; p < NP; ++p) a.ptr[p] = z.ptr[p];
         a.n = z.total;
-        a.n_vec = z.total / Vec128<T>::N;
+        a.n_vec = z.total / VN;
         int64_t blocks = (a.n_vec + 256 * UNROLL - 1) / (256 * UNROLL);
         if (blocks < 1) blocks = 1;
         if (blocks > 0x7fffffffLL) {
@@ -439,8 +584,19 @@ int launch_zip(ndb_ctx *ctx, const ZipPlan &z, const void *scalars)
         a.tiles_y = (a.ny + TS - 1) / TS;
         a.total_tiles = a.tiles_x * a.tiles_y;
         for (int k = 0; k < no; ++k) a.total_tiles *= a.odim[k];
+        a.y_fastest = env_int("NDB_TILE_YFAST", 0);
+        // vector form?
+        bool vec = a.nx % VN == 0 && a.ny % VN == 0;
+        for (int p = 0; p < NP && vec; ++p) {
+            vec = ((uintptr_t)a.ptr[p] % 16) == 0;
+            if (a.slot[p] >= 0) vec = vec && a.ys[p] == 1 && a.xs[p] % VN == 0;
+            else vec = vec && a.xs[p] == 1 && a.ys[p] % VN == 0;
+            for (int k = 0; k < no && vec; ++k) vec = a.ostride[p][k] % VN == 0;
+        }
+        if (env_int("NDB_TILE_SCALAR", 0)) vec = false;
         int64_t blocks = a.total_tiles < (int64_t)1 << 30 ? a.total_tiles : (int64_t)1 << 30;
-        zip_tile<T, OP, NIN><<<(unsigned)blocks, 256, 0, st>>>(a, s0, s1, ctx->dev_flag);
+        if (vec) zip_tile_vec<T, OP, NIN><<<(unsigned)blocks, 256, 0, st>>>(a, s0, s1, ctx->dev_flag);
+        else zip_tile<T, OP, NIN><<<(unsigned)blocks, 256, 0, st>>>(a, s0, s1, ctx->dev_flag);
         NDB_CHECK_LAUNCH();
         return NDB_OK;
     }
@@ -451,7 +607,7 @@ int launch_zip(ndb_ctx *ctx, const ZipPlan &z, const void *scalars)
         RowsArgs<NP> a;
         memset(&a, 0, sizeof(a));
         const int inner = m - 1;
-        const int64_t unit = vec ? Vec128<T>::N : 1;
+        const int64_t unit = vec ? VN : 1;
         for (int p = 0; p < NP; ++p) {
             a.ptr[p] = z.ptr[p];
             a.istride[p] = z.stride[p][inner];
@@ -468,13 +624,23 @@ int launch_zip(ndb_ctx *ctx, const ZipPlan &z, const void *scalars)
         while (tx > 1 && tx / 2 >= a.inner_len) tx /= 2;  // smallest power of two covering a short row
         if (tx < 1) tx = 1;
         const int ty = 256 / tx;
-        a.blocks_inner = (a.inner_len + (int64_t)tx * ITEMS - 1) / ((int64_t)tx * ITEMS);
-        const int64_t brows = (a.n_rows + ty - 1) / ty;
+        const bool rowwise = a.inner_len <= tx && a.n_rows >= (int64_t)ty * 2;
+        int64_t brows;
+        if (rowwise) {
+            a.blocks_inner = 1;
+            brows = (a.n_rows + (int64_t)ty * ITEMS - 1) / ((int64_t)ty * ITEMS);
+        } else {
+            a.blocks_inner = (a.inner_len + (int64_t)tx * ITEMS - 1) / ((int64_t)tx * ITEMS);
+            brows = (a.n_rows + ty - 1) / ty;
+        }
         a.total_blocks = a.blocks_inner * brows;
         int64_t blocks = a.total_blocks < (int64_t)1 << 30 ? a.total_blocks : (int64_t)1 << 30;
         dim3 bd(tx, ty, 1);
-        if (vec) zip_rows<T, OP, NIN, true, ITEMS><<<(unsigned)blocks, bd, 0, st>>>(a, s0, s1, ctx->dev_flag);
-        else zip_rows<T, OP, NIN, false, ITEMS><<<(unsigned)blocks, bd, 0, st>>>(a, s0, s1, ctx->dev_flag);
+        const unsigned gb = (unsigned)blocks;
+        if (vec && rowwise) zip_rows<T, OP, NIN, true, true, ITEMS><<<gb, bd, 0, st>>>(a, s0, s1, ctx->dev_flag);
+        else if (vec) zip_rows<T, OP, NIN, true, false, ITEMS><<<gb, bd, 0, st>>>(a, s0, s1, ctx->dev_flag);
+        else if (rowwise) zip_rows<T, OP, NIN, false, true, ITEMS><<<gb, bd, 0, st>>>(a, s0, s1, ctx->dev_flag);
+        else zip_rows<T, OP, NIN, false, false, ITEMS><<<gb, bd, 0, st>>>(a, s0, s1, ctx->dev_flag);
         NDB_CHECK_LAUNCH();
         return NDB_OK;
     }

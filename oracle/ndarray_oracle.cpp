@@ -309,18 +309,18 @@ static inline T wrem(T a, T b, int *trap)
         return a % b;
     }
 }
+// f32::min / f32::max ignore a NaN operand; the sign of a zero result is unspecified in Rust, so the oracle and
+// the kernels share one explicit rule: the first operand wins ties.
 template <typename T>
 static inline T wmin(T a, T b)
 {
-    if constexpr (std::is_same<T, float>::value) return fminf(a, b);   // f32::min: NaN loses
-    else if constexpr (std::is_same<T, double>::value) return fmin(a, b);
+    if constexpr (std::is_floating_point<T>::value) return (b < a || a != a) ? b : a;
     else return b < a ? b : a;
 }
 template <typename T>
 static inline T wmax(T a, T b)
 {
-    if constexpr (std::is_same<T, float>::value) return fmaxf(a, b);
-    else if constexpr (std::is_same<T, double>::value) return fmax(a, b);
+    if constexpr (std::is_floating_point<T>::value) return (b > a || a != a) ? b : a;
     else return b > a ? b : a;
 }
 
