@@ -201,57 +201,33 @@ __global__ void __launch_bounds__(256) zip_flat_vec(FlatArgs<NIN + 1> a, T s0, T
 
 // ---------------------------------------------------------------------------------------------
 // collapsed N-d rows
+//
+// Geometry: [batch axes...] x [row axis] x [inner axis].  The inner axis is the output's fastest axis; the
+// row axis is the longest remaining axis; whatever is left is the batch, whose multi-index is decomposed
+// once per BLOCK (uniform work), never per thread.  A 256-thread block covers (TY * RI) rows x (TX * CI)
+// units and every thread owns RI x CI = ITEMS units (CI chosen on the host so that short rows do not leave
+// items idle).  Phase 1 computes every address and issues every load of the thread with no branch in
+// between; phase 2 applies the op and stores.
+//   VEC   128-bit units.
+//   PLAIN every producer runs forwards along the row (stride 1).  Otherwise an input may also be constant
+//         along the row (stride 0: one scalar load) or run BACKWARDS (stride -1: the mirrored vector,
+//         lanes reversed in registers) - predicated loads, still no branch, so s![.., ..;-1] views and
+//         row-broadcast operands stay on the vector path.
 template <int NP>
 struct RowsArgs {
     char *ptr[NP];
-    int64_t ostride[NP][NDB_MAX_NDIM - 1];  // outer strides, elements
-    int64_t istride[NP];                    // inner stride, elements (VEC: 0 or 1)
-    int64_t odim[NDB_MAX_NDIM - 1];
-    int n_outer;
+    int64_t bstride[NP][NDB_MAX_NDIM - 2];  // batch-axis strides, elements
+    int64_t bdim[NDB_MAX_NDIM - 2];
+    int n_batch;
+    int64_t rstride[NP];  // row-axis stride, elements
+    int64_t istride[NP];  // inner stride, elements (VEC: 1, 0 or -1)
     int64_t n_rows;
     int64_t inner_len;  // in units (elements, or vectors when VEC)
-    int64_t blocks_inner;
-    int64_t total_blocks;
+    int64_t blocks_inner, blocks_rows, total_blocks;
 };
 
-// Element offsets of outer row `row` for every producer.  The common collapsed shapes have one outer
-// axis (no division at all); otherwise 32-bit division when the row count allows it.
-template <int NP>
-__device__ __forceinline__ void row_offsets(const RowsArgs<NP> &a, int64_t row, int64_t (&off)[NP])
-{
-    if (a.n_outer == 1) {
-#pragma unroll
-        for (int p = 0; p < NP; ++p) off[p] = row * a.ostride[p][0];
-        return;
-    }
-#pragma unroll
-    for (int p = 0; p < NP; ++p) off[p] = 0;
-    if (a.n_rows <= 0x7fffffffLL) {
-        unsigned r = (unsigned)row;
-        for (int k = a.n_outer - 1; k >= 0; --k) {
-            const unsigned d = (unsigned)a.odim[k];
-            const unsigned q = r / d;
-            const int64_t idx = (int64_t)(r - q * d);
-            r = q;
-#pragma unroll
-            for (int p = 0; p < NP; ++p) off[p] += idx * a.ostride[p][k];
-        }
-    } else {
-        int64_t r = row;
-        for (int k = a.n_outer - 1; k >= 0; --k) {
-            const int64_t q = r / a.odim[k];
-            const int64_t idx = r - q * a.odim[k];
-            r = q;
-#pragma unroll
-            for (int p = 0; p < NP; ++p) off[p] += idx * a.ostride[p][k];
-        }
-    }
-}
-
-// ROWWISE=false: a thread owns ITEMS units of ONE row (long rows).
-// ROWWISE=true : a thread owns one unit in each of ITEMS rows (rows that fit one pass of the block).
-template <typename T, int OP, int NIN, bool VEC, bool ROWWISE, int ITEMS>
-__global__ void __launch_bounds__(256) zip_rows(RowsArgs<NIN + 1> a, T s0, T s1, int *flag)
+template <typename T, int OP, int NIN, bool VEC, bool PLAIN, int ITEMS>
+__global__ void __launch_bounds__(256, (NIN <= 3 ? 3 : 1)) zip_rows(RowsArgs<NIN + 1> a, int ci_shift, T s0, T s1, int *flag)
 {
     using V = Vec128<T>;
     using E = typename std::conditional<VEC, V, T>::type;  // the unit moved per access
@@ -259,76 +235,114 @@ __global__ void __launch_bounds__(256) zip_rows(RowsArgs<NIN + 1> a, T s0, T s1,
     constexpr int NI = NIN > 0 ? NIN : 1;
     constexpr int NP = NIN + 1;
     const int TX = blockDim.x, TY = blockDim.y;
+    const int CI = 1 << ci_shift, RI = ITEMS >> ci_shift;
     for (int64_t vb = blockIdx.x; vb < a.total_blocks; vb += gridDim.x) {
-        int64_t brow, bin;
-        if (a.blocks_inner == 1) {
-            brow = vb;
-            bin = 0;
-        } else if (a.total_blocks <= 0x7fffffffLL) {
-            const unsigned q = (unsigned)vb / (unsigned)a.blocks_inner;
-            brow = q;
-            bin = (int64_t)((unsigned)vb - q * (unsigned)a.blocks_inner);
+        // ---- per block (uniform): which batch, which rows, which part of the row
+        int64_t bin = 0, brow = 0;
+        const T *base[NP];
+#pragma unroll
+        for (int p = 0; p < NP; ++p) base[p] = reinterpret_cast<const T *>(a.ptr[p]);
+        if (a.total_blocks <= 0x7fffffffLL) {  // the usual case: 32-bit divisions
+            unsigned t = (unsigned)vb;
+            if (a.blocks_inner > 1) {
+                const unsigned q = t / (unsigned)a.blocks_inner;
+                bin = t - q * (unsigned)a.blocks_inner;
+                t = q;
+            }
+            if (a.n_batch > 0) {
+                const unsigned q = t / (unsigned)a.blocks_rows;
+                brow = t - q * (unsigned)a.blocks_rows;
+                t = q;
+            } else {
+                brow = t;
+            }
+#pragma unroll 1
+            for (int k = a.n_batch - 1; k >= 0; --k) {
+                const unsigned q = t / (unsigned)a.bdim[k];
+                const int64_t idx = (int64_t)(t - q * (unsigned)a.bdim[k]);
+                t = q;
+#pragma unroll
+                for (int p = 0; p < NP; ++p) base[p] += idx * a.bstride[p][k];
+            }
         } else {
-            brow = vb / a.blocks_inner;
-            bin = vb - brow * a.blocks_inner;
+            int64_t t = vb;
+            if (a.blocks_inner > 1) {
+                const int64_t q = t / a.blocks_inner;
+                bin = t - q * a.blocks_inner;
+                t = q;
+            }
+            if (a.n_batch > 0) {
+                const int64_t q = t / a.blocks_rows;
+                brow = t - q * a.blocks_rows;
+                t = q;
+            } else {
+                brow = t;
+            }
+#pragma unroll 1
+            for (int k = a.n_batch - 1; k >= 0; --k) {
+                const int64_t q = t / a.bdim[k];
+                const int64_t idx = t - q * a.bdim[k];
+                t = q;
+#pragma unroll
+                for (int p = 0; p < NP; ++p) base[p] += idx * a.bstride[p][k];
+            }
         }
+        const int64_t row0 = brow * ((int64_t)TY * RI) + threadIdx.y;
+        const int64_t i0 = bin * ((int64_t)TX * CI) + threadIdx.x;
         E in[ITEMS][NI];
-        int64_t ooff[ITEMS];  // element offset of each item's output unit
+        T *dst[ITEMS];
         bool live[ITEMS];
-        int64_t off[NP];
-        bool row_ok = true;
-        if constexpr (!ROWWISE) {  // one row for all items: decompose it once
-            const int64_t row0 = brow * TY + threadIdx.y;
-            row_ok = row0 < a.n_rows;
-            if (row_ok) row_offsets<NP>(a, row0, off);
-        }
+        // ---- phase 1: addresses + loads
 #pragma unroll
         for (int it = 0; it < ITEMS; ++it) {
-            int64_t i;
-            if constexpr (ROWWISE) {
-                const int64_t row = brow * ((int64_t)TY * ITEMS) + (int64_t)it * TY + threadIdx.y;
-                i = bin * TX + threadIdx.x;
-                live[it] = row < a.n_rows && i < a.inner_len;
-                if (live[it]) row_offsets<NP>(a, row, off);
+            const int r_it = it >> ci_shift, c_it = it & (CI - 1);
+            const int64_t row = row0 + (int64_t)r_it * TY;
+            const int64_t i = i0 + (int64_t)c_it * TX;
+            live[it] = row < a.n_rows && i < a.inner_len;
+            if constexpr (PLAIN) {
+                dst[it] = const_cast<T *>(base[0]) + row * a.rstride[0] + i * N;
+#pragma unroll
+                for (int p = 0; p < NIN; ++p) {
+                    const T *src = base[p + 1] + row * a.rstride[p + 1] + i * N;
+                    if (live[it]) in[it][p] = *reinterpret_cast<const E *>(src);
+                }
             } else {
-                i = bin * ((int64_t)TX * ITEMS) + (int64_t)it * TX + threadIdx.x;
-                live[it] = row_ok && i < a.inner_len;
-            }
-            ooff[it] = 0;
-            if (!live[it]) continue;
-            ooff[it] = off[0] + i * N * a.istride[0];
+                dst[it] = const_cast<T *>(base[0]) + row * a.rstride[0] + i * N * a.istride[0];
 #pragma unroll
-            for (int p = 0; p < NIN; ++p) {
-                const T *src = reinterpret_cast<const T *>(a.ptr[p + 1]) + off[p + 1];
-                if constexpr (VEC) {
-                    if (a.istride[p + 1] == 0) {
-                        const T sv = *src;
-#pragma unroll
-                        for (int e = 0; e < N; ++e) in[it][p].v[e] = sv;
+                for (int p = 0; p < NIN; ++p) {
+                    const int64_t is = a.istride[p + 1];
+                    if constexpr (VEC) {
+                        const T *src = base[p + 1] + row * a.rstride[p + 1] + i * N * is - (is < 0 ? (N - 1) : 0);
+                        if (live[it] && is != 0) in[it][p] = *reinterpret_cast<const V *>(src);
+                        if (live[it] && is == 0) in[it][p].v[0] = *src;
                     } else {
-                        in[it][p] = reinterpret_cast<const V *>(src)[i];
+                        if (live[it]) in[it][p] = (base[p + 1] + row * a.rstride[p + 1])[i * is];
                     }
-                } else {
-                    in[it][p] = src[i * a.istride[p + 1]];
                 }
             }
         }
+        // ---- phase 2: op + store
 #pragma unroll
         for (int it = 0; it < ITEMS; ++it) {
             if (!live[it]) continue;
-            T *dst = reinterpret_cast<T *>(a.ptr[0]) + ooff[it];
             if constexpr (VEC) {
                 V o;
 #pragma unroll
                 for (int e = 0; e < N; ++e) {
                     T x[NI];
 #pragma unroll
-                    for (int p = 0; p < NIN; ++p) x[p] = in[it][p].v[e];
+                    for (int p = 0; p < NIN; ++p) {
+                        if constexpr (PLAIN) x[p] = in[it][p].v[e];
+                        else {
+                            const int64_t is = a.istride[p + 1];
+                            x[p] = is > 0 ? in[it][p].v[e] : (is < 0 ? in[it][p].v[N - 1 - e] : in[it][p].v[0]);
+                        }
+                    }
                     o.v[e] = apply_op<T, OP, NIN>(x, s0, s1, flag);
                 }
-                *reinterpret_cast<V *>(dst) = o;
+                *reinterpret_cast<V *>(dst[it]) = o;
             } else {
-                *dst = apply_op<T, OP, NIN>(in[it], s0, s1, flag);
+                *dst[it] = apply_op<T, OP, NIN>(in[it], s0, s1, flag);
             }
         }
     }
@@ -387,7 +401,8 @@ __global__ void __launch_bounds__(256) zip_tile(TileArgs<NIN + 1> a, T s0, T s1,
     constexpr int PASS = 256 / TS;  // rows (or columns) covered per pass
     constexpr int NI = NIN > 0 ? NIN : 1;
     constexpr int NP = NIN + 1;
-    __shared__ T tile[ZIP_MAX_STAGED][TS][TS + 1];
+    extern __shared__ __align__(16) unsigned char tile_raw[];  // one padded TS x (TS+1) tile per staged producer
+    T(*tile)[TS][TS + 1] = reinterpret_cast<T(*)[TS][TS + 1]>(tile_raw);
     const int lo = threadIdx.x % TS;  // fast lane index
     const int hi = threadIdx.x / TS;
     for (int64_t vb = blockIdx.x; vb < a.total_tiles; vb += gridDim.x) {
@@ -438,7 +453,7 @@ __global__ void __launch_bounds__(256) zip_tile(TileArgs<NIN + 1> a, T s0, T s1,
 // tile extents multiples of the vector width (checked on the host).  Every thread first issues ALL its
 // global loads (PASSES vectors per producer), then the staged ones go through shared memory.
 template <typename T, int OP, int NIN>
-__global__ void __launch_bounds__(256) zip_tile_vec(TileArgs<NIN + 1> a, T s0, T s1, int *flag)
+__global__ void __launch_bounds__(256, (NIN <= 2 ? 4 : 2)) zip_tile_vec(TileArgs<NIN + 1> a, T s0, T s1, int *flag)
 {
     using V = Vec128<T>;
     constexpr int N = V::N;
@@ -448,7 +463,8 @@ __global__ void __launch_bounds__(256) zip_tile_vec(TileArgs<NIN + 1> a, T s0, T
     constexpr int PASSES = TS / RPP;  // 4 (f32) / 2 (f64)
     constexpr int NI = NIN > 0 ? NIN : 1;
     constexpr int NP = NIN + 1;
-    __shared__ T tile[ZIP_MAX_STAGED][TS][TS + 1];
+    extern __shared__ __align__(16) unsigned char tile_raw[];  // one padded TS x (TS+1) tile per staged producer
+    T(*tile)[TS][TS + 1] = reinterpret_cast<T(*)[TS][TS + 1]>(tile_raw);
     const int vl = threadIdx.x % VPR;
     const int hi = threadIdx.x / VPR;
     for (int64_t vb = blockIdx.x; vb < a.total_tiles; vb += gridDim.x) {
@@ -595,8 +611,9 @@ int launch_zip(ndb_ctx *ctx, const ZipPlan &z, const void *scalars)
         }
         if (env_int("NDB_TILE_SCALAR", 0)) vec = false;
         int64_t blocks = a.total_tiles < (int64_t)1 << 30 ? a.total_tiles : (int64_t)1 << 30;
-        if (vec) zip_tile_vec<T, OP, NIN><<<(unsigned)blocks, 256, 0, st>>>(a, s0, s1, ctx->dev_flag);
-        else zip_tile<T, OP, NIN><<<(unsigned)blocks, 256, 0, st>>>(a, s0, s1, ctx->dev_flag);
+        const size_t smem = (size_t)nslot * TS * (TS + 1) * sizeof(T);
+        if (vec) zip_tile_vec<T, OP, NIN><<<(unsigned)blocks, 256, smem, st>>>(a, s0, s1, ctx->dev_flag);
+        else zip_tile<T, OP, NIN><<<(unsigned)blocks, 256, smem, st>>>(a, s0, s1, ctx->dev_flag);
         NDB_CHECK_LAUNCH();
         return NDB_OK;
     }
@@ -608,39 +625,47 @@ int launch_zip(ndb_ctx *ctx, const ZipPlan &z, const void *scalars)
         memset(&a, 0, sizeof(a));
         const int inner = m - 1;
         const int64_t unit = vec ? VN : 1;
+        // the longest outer axis becomes the row axis, the others the batch
+        int row_axis = -1;
+        for (int k = 0; k < inner; ++k)
+            if (row_axis < 0 || z.dim[k] > z.dim[row_axis]) row_axis = k;
+        bool plain = true;
         for (int p = 0; p < NP; ++p) {
             a.ptr[p] = z.ptr[p];
             a.istride[p] = z.stride[p][inner];
-            for (int k = 0; k < inner; ++k) a.ostride[p][k] = z.stride[p][k];
+            a.rstride[p] = row_axis >= 0 ? z.stride[p][row_axis] : 0;
+            plain = plain && a.istride[p] == 1;
         }
-        a.n_outer = inner;
-        a.n_rows = 1;
+        a.n_rows = row_axis >= 0 ? z.dim[row_axis] : 1;
+        int nb = 0;
+        int64_t batches = 1;
         for (int k = 0; k < inner; ++k) {
-            a.odim[k] = z.dim[k];
-            a.n_rows *= z.dim[k];
+            if (k == row_axis) continue;
+            a.bdim[nb] = z.dim[k];
+            for (int p = 0; p < NP; ++p) a.bstride[p][nb] = z.stride[p][k];
+            batches *= z.dim[k];
+            ++nb;
         }
+        a.n_batch = nb;
         a.inner_len = z.dim[inner] / unit;
         int tx = 256;
         while (tx > 1 && tx / 2 >= a.inner_len) tx /= 2;  // smallest power of two covering a short row
         if (tx < 1) tx = 1;
-        const int ty = 256 / tx;
-        const bool rowwise = a.inner_len <= tx && a.n_rows >= (int64_t)ty * 2;
-        int64_t brows;
-        if (rowwise) {
-            a.blocks_inner = 1;
-            brows = (a.n_rows + (int64_t)ty * ITEMS - 1) / ((int64_t)ty * ITEMS);
-        } else {
-            a.blocks_inner = (a.inner_len + (int64_t)tx * ITEMS - 1) / ((int64_t)tx * ITEMS);
-            brows = (a.n_rows + ty - 1) / ty;
-        }
-        a.total_blocks = a.blocks_inner * brows;
+        int ty = 256 / tx;
+        while (ty > 1 && ty / 2 >= a.n_rows) ty /= 2;  // few rows: a smaller block beats idle threads
+        // per-thread items: along the row while it is long enough, the rest across rows
+        int ci_shift = 0;
+        while ((1 << ci_shift) < ITEMS && (int64_t)tx * (1 << ci_shift) < a.inner_len) ++ci_shift;
+        const int ci = 1 << ci_shift, ri = ITEMS >> ci_shift;
+        a.blocks_inner = (a.inner_len + (int64_t)tx * ci - 1) / ((int64_t)tx * ci);
+        a.blocks_rows = (a.n_rows + (int64_t)ty * ri - 1) / ((int64_t)ty * ri);
+        a.total_blocks = a.blocks_inner * a.blocks_rows * batches;
         int64_t blocks = a.total_blocks < (int64_t)1 << 30 ? a.total_blocks : (int64_t)1 << 30;
         dim3 bd(tx, ty, 1);
         const unsigned gb = (unsigned)blocks;
-        if (vec && rowwise) zip_rows<T, OP, NIN, true, true, ITEMS><<<gb, bd, 0, st>>>(a, s0, s1, ctx->dev_flag);
-        else if (vec) zip_rows<T, OP, NIN, true, false, ITEMS><<<gb, bd, 0, st>>>(a, s0, s1, ctx->dev_flag);
-        else if (rowwise) zip_rows<T, OP, NIN, false, true, ITEMS><<<gb, bd, 0, st>>>(a, s0, s1, ctx->dev_flag);
-        else zip_rows<T, OP, NIN, false, false, ITEMS><<<gb, bd, 0, st>>>(a, s0, s1, ctx->dev_flag);
+        if (vec && plain) zip_rows<T, OP, NIN, true, true, ITEMS><<<gb, bd, 0, st>>>(a, ci_shift, s0, s1, ctx->dev_flag);
+        else if (vec) zip_rows<T, OP, NIN, true, false, ITEMS><<<gb, bd, 0, st>>>(a, ci_shift, s0, s1, ctx->dev_flag);
+        else zip_rows<T, OP, NIN, false, false, ITEMS><<<gb, bd, 0, st>>>(a, ci_shift, s0, s1, ctx->dev_flag);
         NDB_CHECK_LAUNCH();
         return NDB_OK;
     }

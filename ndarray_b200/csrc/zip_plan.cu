@@ -168,24 +168,28 @@ int make_zip_plan(int op, int n_parts, const ndb_view *parts, ZipPlan *zp)
     // 5. classify
     const int inner = m - 1;
     const int64_t vec = 16 / esz;
-    bool all_unit = true, all_unit_or_bcast = true;
+    bool all_unit = true, all_vec_ok = true;
     for (int p = 0; p < n_parts; ++p) {
         const int64_t s = z.stride[p][inner];
         all_unit &= (s == 1);
-        all_unit_or_bcast &= (s == 1 || (s == 0 && p > 0));
+        // output: forwards only; inputs: forwards, constant along the row, or backwards
+        all_vec_ok &= (s == 1 || (p > 0 && (s == 0 || s == -1)));
     }
     auto aligned = [&](int p) { return ((uintptr_t)z.ptr[p] % 16) == 0; };
+    // a backwards row starts at the LAST element of a 16-byte vector
+    auto aligned_rev = [&](int p) { return ((uintptr_t)(z.ptr[p] + esz) % 16) == 0; };
     if (m == 1 && all_unit) {
         bool al = true;
         for (int p = 0; p < n_parts; ++p) al &= aligned(p);
         z.kernel = al ? NDB_KERNEL_FLAT_VEC : NDB_KERNEL_FLAT;
         return NDB_OK;
     }
-    if (all_unit_or_bcast) {
+    if (all_vec_ok) {
         bool ok = z.dim[inner] % vec == 0;
         for (int p = 0; p < n_parts && ok; ++p) {
-            if (z.stride[p][inner] == 0) continue;  // scalar-per-row producer: loaded once per thread
-            ok &= aligned(p);
+            const int64_t s = z.stride[p][inner];
+            if (s == 0) continue;  // scalar-per-row producer: loaded once per thread
+            ok &= (s == 1) ? aligned(p) : aligned_rev(p);
             for (int k = 0; k < inner && ok; ++k) ok &= (z.stride[p][k] % vec == 0);
         }
         z.kernel = ok ? NDB_KERNEL_ROWS_VEC : NDB_KERNEL_ROWS;

@@ -180,9 +180,13 @@ def test_planner_kernel_classes():
     st, pl = plan(nd.Op.MUL, c3, c3, row)
     assert st == 0 and pl.kernel == 3 and pl.ndim == 2 and list(pl.dim[:2]) == [n * n, n]
     assert list(pl.stride[2][:2]) == [0, 1]
-    # inner-axis reversal: s![.., .., ..;-1] input -> rows (scalar) kernel with stride -1
+    # inner-axis reversal: s![.., .., ..;-1] input stays on the 128-bit path (lanes reversed in registers) when the
+    # mirrored rows are aligned, else the scalar rows kernel
     xr = mk(A + (n - 1) * 4, np.float32, (n, n, n), (n * n, n, -1))
     st, pl = plan(nd.Op.ADD, c3, xr, c3)
+    assert st == 0 and pl.kernel == 3 and pl.stride[1][pl.ndim - 1] == -1
+    xr2 = mk(A + (n - 2) * 4, np.float32, (n, n, n), (n * n, n, -1))
+    st, pl = plan(nd.Op.ADD, c3, xr2, c3)
     assert st == 0 and pl.kernel == 4 and pl.stride[1][pl.ndim - 1] == -1
     # a backwards OUTPUT is flipped for every producer, so it becomes a flat forward run
     o_rev = mk(A + (4096 - 16) * 4 + 12, np.float32, (4096,), (-1,))

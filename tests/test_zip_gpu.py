@@ -111,6 +111,9 @@ VIEW_CASES = {
     "two_transposed": ((70, 65), ident, [((65, 70), lambda a: a.T), ((65, 70), lambda a: a.T)]),
     "neg_outer": ((40, 50), ident, [((80, 50), lambda a: a[::-2]), ((80, 50), lambda a: a[::2])]),
     "neg_inner": ((40, 64), ident, [((40, 128), lambda a: a[:, ::-2]), ((40, 64), lambda a: a[:, ::-1])]),
+    "rev_inner_vec": ((40, 64), ident, [((40, 64), lambda a: a[:, ::-1]), ((40, 64), ident)]),
+    "rev_inner_3d": ((9, 20, 128), ident, [((9, 20, 128), lambda a: a[::-1, :, ::-1]), ((9, 20, 128), lambda a: a[:, :, ::-1])]),
+    "rev_inner_unaligned": ((40, 63), ident, [((40, 63), lambda a: a[:, ::-1]), ((40, 63), ident)]),
     "out_reversed": ((40, 64), lambda a: a[::-1, ::-1], [((40, 64), ident), ((40, 64), lambda a: a[::-1])]),
     "out_strided": ((40, 128), lambda a: a[:, ::2], [((40, 64), ident), ((40, 64), ident)]),
     "out_f_in_c": ((64, 40), lambda a: a.T, [((40, 64), ident), ((40, 64), ident)]),
