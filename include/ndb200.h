@@ -105,6 +105,8 @@ typedef enum {
     NDB_OP_MIN = 20,     /* out = min(in0, in1) */
     NDB_OP_MAX = 21,     /* out = max(in0, in1) */
     NDB_OP_SCALE_ADD = 22, /* out = in0 * s0 + in1 * s1   (gemv/gemm-style alpha/beta combine, two products one sum) */
+    NDB_OP_TF32_HI = 23, /* out = tf32(in0), round to nearest (f32 only; operand packing of the 3xTF32 GEMM) */
+    NDB_OP_TF32_LO = 24, /* out = in0 - tf32(in0)         (f32 only) */
     NDB_OP__COUNT
 } ndb_op;
 

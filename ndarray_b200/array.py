@@ -28,7 +28,7 @@ CODE_DTYPE = {v: k for k, v in DTYPE_CODE.items()}
 
 class Op:
     COPY, FILL, ADD, SUB, MUL, DIV, REM, MUL_ADD, ADD_S, SUB_S, MUL_S, DIV_S, REM_S, RSUB_S, RDIV_S, NEG, AXPY, \
-        ADD_N, ABS, SQRT, MIN, MAX, SCALE_ADD = range(23)
+        ADD_N, ABS, SQRT, MIN, MAX, SCALE_ADD, TF32_HI, TF32_LO = range(25)
 
 
 class Red:

@@ -32,6 +32,8 @@ int op_arity(int op)
     case NDB_OP_RDIV_S:
     case NDB_OP_NEG:
     case NDB_OP_ABS:
+    case NDB_OP_TF32_HI:
+    case NDB_OP_TF32_LO:
     case NDB_OP_SQRT: return 1;
     case NDB_OP_ADD:
     case NDB_OP_SUB:

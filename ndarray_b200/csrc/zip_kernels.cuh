@@ -144,7 +144,16 @@ __device__ __forceinline__ T apply_op(const T *x, T s0, T s1, int *flag)
     } else if constexpr (OP == NDB_OP_MIN) return w_min(x[0], x[1]);
     else if constexpr (OP == NDB_OP_MAX) return w_max(x[0], x[1]);
     else if constexpr (OP == NDB_OP_SCALE_ADD) return w_add(w_mul(x[0], s0), w_mul(x[1], s1));
-    else return x[0];
+    else if constexpr (OP == NDB_OP_TF32_HI || OP == NDB_OP_TF32_LO) {
+        if constexpr (std::is_same<T, float>::value) {
+            uint32_t hi;
+            asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(x[0]));
+            const float h = __uint_as_float(hi);
+            // non-finite values keep their hi part and get a zero lo part (inf - inf would poison the product)
+            if constexpr (OP == NDB_OP_TF32_HI) return h;
+            else return (fabsf(x[0]) <= 3.4028234664e38f) ? x[0] - h : 0.f;
+        } else return x[0];
+    } else return x[0];
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -700,6 +709,8 @@ int zip_dispatch_typed(ndb_ctx *ctx, const ZipPlan &z, const void *scalars)
         NDB_ZIP_CASE(NDB_OP_MIN, 2)
         NDB_ZIP_CASE(NDB_OP_MAX, 2)
         NDB_ZIP_CASE(NDB_OP_SCALE_ADD, 2)
+        NDB_ZIP_CASE(NDB_OP_TF32_HI, 1)
+        NDB_ZIP_CASE(NDB_OP_TF32_LO, 1)
 #undef NDB_ZIP_CASE
     case NDB_OP_ADD_N:
         switch (nin) {

@@ -79,6 +79,10 @@ int make_zip_plan(int op, int n_parts, const ndb_view *parts, ZipPlan *zp)
         set_error("Zip: sqrt needs a float element type");
         return NDB_ERR_UNSUPPORTED;
     }
+    if ((op == NDB_OP_TF32_HI || op == NDB_OP_TF32_LO) && o.dtype != NDB_F32) {
+        set_error("Zip: the tf32 split ops are f32-only");
+        return NDB_ERR_UNSUPPORTED;
+    }
     if (self_overlaps(&o)) {
         set_error("Zip: the output producer overlaps itself (zero or aliasing strides)");
         return NDB_ERR_ALIASING;
