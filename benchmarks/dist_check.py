@@ -1,0 +1,53 @@
+"""torchrun --nproc-per-node N benchmarks/dist_check.py — the multi-GPU protocol of ndarray_b200/parallel.py on
+real GPUs (NCCL): every rank holds the same host data, takes its Axis(0) slab, and the sharded results must equal
+the unsharded numpy results (integers exactly, floats within the north-star tolerance)."""
+import os
+import sys
+from pathlib import Path
+
+import numpy as np
+
+sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
+
+
+def main():
+    import torch
+    import torch.distributed as dist
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    os.environ["NDB_DEVICE"] = str(local)
+    import ndarray_b200 as nd
+    from ndarray_b200 import Array, Zip, parallel as par
+    ctx = nd.Context(local)
+    rng = np.random.default_rng(7)
+    n0 = 1001
+    a = rng.integers(-2 ** 62, 2 ** 62, size=(n0, 300), dtype=np.int64)
+    f = rng.standard_normal((n0, 300))
+    g = rng.uniform(-1, 1, (n0, 300)).astype(np.float32)
+    lo, hi = par.shard_bounds(n0, rank, world)
+    da, df, dg = (Array.from_numpy(x, ctx) for x in (a, f, g))
+    sa, sf, sg = (par.shard_axis0(x, rank, world) for x in (da, df, dg))
+    assert sa.shape[0] == hi - lo
+    # elementwise on the shard: no exchange
+    out = Array.uninit(sg.shape, np.float32, ctx=ctx)
+    Zip.from_(out).and_(sg).and_(sg).for_each("a=b*c")
+    assert np.array_equal(out.to_numpy(), g[lo:hi] * g[lo:hi])
+    with np.errstate(over="ignore"):
+        assert par.global_sum(sa, dist) == a.sum(dtype=np.int64)
+        assert np.array_equal(par.sum_axis0(sa, dist).to_numpy(), a.sum(axis=0, dtype=np.int64))
+    tol = 1e-12 * np.sqrt(n0)
+    assert abs(par.global_sum(sf, dist) - f.sum()) <= tol * 300 * 8
+    assert np.max(np.abs(par.sum_axis0(sf, dist).to_numpy() - f.sum(axis=0))) <= tol * 8
+    assert np.max(np.abs(par.mean_axis0(sf, n0, dist).to_numpy() - f.mean(axis=0))) <= tol
+    assert np.max(np.abs(par.var_axis0(sf, 1.0, dist).to_numpy() - f.var(axis=0, ddof=1))) <= tol * 8
+    assert np.max(np.abs(par.var_axis0(sf, 0.0, dist, want_std=True).to_numpy() - f.std(axis=0))) <= tol * 8
+    ctx.sync()
+    dist.barrier()
+    if rank == 0:
+        print(f"dist_check ok on {world} GPUs")
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,109 @@
+"""Outer-axis sharding across GPUs: one process per GPU, `torch.distributed` (NCCL) for the exchange steps.
+
+ndarray's only parallelism is rayon's recursive `Zip::split` along the outermost axis
+(src/zip/mod.rs:811-815,883-895; src/parallel/par.rs:270-297).  Across GPUs the same partition is made once,
+with `split_at(Axis(0), …)` (src/impl_raw_views.rs:113-135): elementwise Zips then need no communication;
+reductions whose reduced axis is the sharded one finish with one small collective.
+torch is imported lazily and only here (plumbing for the collectives); all arithmetic stays in libndb200.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from ._ffi import View, check, lib
+from .array import Array, Red
+
+
+def shard_bounds(n: int, rank: int, world: int) -> tuple[int, int]:
+    """Rows [lo, hi) of an axis of length n owned by `rank` (balanced, contiguous, in rank order)."""
+    return n * rank // world, n * (rank + 1) // world
+
+
+def shard_axis0(a: Array, rank: int, world: int) -> Array:
+    """This rank's slab of `a` along Axis(0): two split_at calls, zero-copy.  Operands that are broadcast along
+    axis 0 (stride 0) are replicated, not split, exactly as their stride says."""
+    lo, hi = shard_bounds(a.shape[0], rank, world)
+    _, right = a.split_at(0, lo)
+    mine, _ = right.split_at(0, hi - lo)
+    return mine
+
+
+def _torch_view(arr: Array):
+    """A torch tensor aliasing a dense device Array (for NCCL)."""
+    import torch
+    assert arr.is_standard_layout() or arr.ndim == 0
+    n = arr.len()
+    dt = {np.dtype(np.float32): torch.float32, np.dtype(np.float64): torch.float64,
+          np.dtype(np.int32): torch.int32, np.dtype(np.int64): torch.int64}[arr.dtype]
+
+    class _Cai:  # __cuda_array_interface__ shim
+        pass
+
+    obj = _Cai()
+    obj.__cuda_array_interface__ = {"shape": (max(n, 1),), "typestr": arr.dtype.str, "data": (arr.v.ptr, False), "version": 3}
+    t = torch.as_tensor(obj, device=torch.device("cuda", arr.ctx.device))
+    assert t.dtype == dt
+    return t
+
+
+def _on_ctx_stream(arr: Array):
+    import torch
+    return torch.cuda.stream(torch.cuda.ExternalStream(arr.ctx.stream_ptr(), device=torch.device("cuda", arr.ctx.device)))
+
+
+def global_sum(local: Array, dist=None):
+    """sum() over all shards: per-GPU tree reduction, then all-reduce of ONE element on the same stream."""
+    out = Array.zeros((), local.dtype, ctx=local.ctx)
+    check(lib().ndb_reduce_all_dev(local.ctx.handle, Red.SUM, C.byref(local.v), C.c_void_p(out.v.ptr)))
+    if dist is not None and dist.is_initialized() and dist.get_world_size() > 1:
+        with _on_ctx_stream(out):
+            dist.all_reduce(_torch_view(out))
+    return out.to_numpy()[()]
+
+
+def sum_axis0(local: Array, dist=None) -> Array:
+    """sum_axis(Axis(0)) when axis 0 is the sharded axis: local partial vector, then all-reduce(sum)."""
+    part = local.sum_axis(0)
+    if dist is not None and dist.is_initialized() and dist.get_world_size() > 1:
+        with _on_ctx_stream(part):
+            dist.all_reduce(_torch_view(part))
+    return part
+
+
+def mean_axis0(local: Array, n_global: int, dist=None) -> Array:
+    """mean_axis(Axis(0)): divide by the GLOBAL length after the all-reduce (impl_numeric.rs:342-355)."""
+    s = sum_axis0(local, dist)
+    s /= local.dtype.type(n_global)
+    return s
+
+
+def var_axis0(local: Array, ddof: float, dist=None, want_std: bool = False) -> Array:
+    """var_axis(Axis(0), ddof): per-shard Welford state (n, mean, M2), all-gather, Chan merge in rank order."""
+    import torch
+    shape = local.shape[1:]
+    mean, m2 = Array.uninit(shape, local.dtype, ctx=local.ctx), Array.uninit(shape, local.dtype, ctx=local.ctx)
+    check(lib().ndb_welford_axis(local.ctx.handle, 0, C.byref(local.v), C.byref(mean.v), C.byref(m2.v)))
+    world = dist.get_world_size() if dist is not None and dist.is_initialized() else 1
+    counts = [local.shape[0]]
+    means, m2s = [mean], [m2]
+    if world > 1:
+        n_out = max(mean.len(), 1)
+        gm = torch.empty((world, n_out), dtype=_torch_view(mean).dtype, device=_torch_view(mean).device)
+        g2 = torch.empty_like(gm)
+        cnt = torch.tensor([local.shape[0]], dtype=torch.int64, device=gm.device)
+        gc = torch.empty((world,), dtype=torch.int64, device=gm.device)
+        with _on_ctx_stream(mean):
+            dist.all_gather_into_tensor(gm, _torch_view(mean))
+            dist.all_gather_into_tensor(g2, _torch_view(m2))
+            dist.all_gather_into_tensor(gc, cnt)
+        counts = [int(x) for x in gc.tolist()]
+        means = [Array.borrow(gm[r].data_ptr(), shape, local.dtype, ctx=local.ctx, owner=gm) for r in range(world)]
+        m2s = [Array.borrow(g2[r].data_ptr(), shape, local.dtype, ctx=local.ctx, owner=g2) for r in range(world)]
+    out = Array.uninit(shape, local.dtype, ctx=local.ctx)
+    mv = (View * len(means))(*[m.v for m in means])
+    sv = (View * len(m2s))(*[m.v for m in m2s])
+    cv = (C.c_int64 * len(counts))(*counts)
+    check(lib().ndb_welford_merge(local.ctx.handle, len(counts), cv, mv, sv, float(ddof), int(want_std), C.byref(out.v)))
+    return out
