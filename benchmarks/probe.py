@@ -63,6 +63,20 @@ def main():
         print(f"  sum_axis{ax} f32 4096^2 into: {med*1e3:8.1f} us {4096*4096*4/med/1e6:8.1f} GB/s")
         med, best = timeit(ctx, lambda: a.sum_axis(Axis(ax)), 50, 5)
         print(f"  sum_axis{ax} f32 4096^2 alloc: {med*1e3:8.1f} us {4096*4096*4/med/1e6:8.1f} GB/s")
+    import ctypes as C
+    from ndarray_b200._ffi import lib, check
+    n = 16384
+    for dt, ops in ((np.float64, (("sum", 0), ("var", 5), ("min", 2))), (np.int64, (("sum", 0), ("min", 2)))):
+        big = Array.zeros((n, n), dt)
+        o = Array.zeros((n,), dt)
+        for name, red in ops:
+            for ax in (0, 1):
+                fn = lambda: check(lib().ndb_reduce_axis(ctx.handle, red, ax, C.byref(big.v), C.byref(o.v), 1.0))
+                med, best = timeit(ctx, fn, 10, 2)
+                print(f"  {name}_axis{ax} {np.dtype(dt).name} 16384^2 into: {med*1e3:8.1f} us {n*n*8/med/1e6:8.1f} GB/s")
+        del big
+    if os.environ.get("NDB_PROBE_NO_GEMM"):
+        return
     for dt in (np.float64, np.float32):
         for n in (2048, 4096, 8192):
             A, B, Cm = (Array.zeros((n, n), dt) for _ in range(3))

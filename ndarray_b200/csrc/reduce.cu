@@ -117,6 +117,34 @@ struct Acc {
         }
         Rd::add(s, x);
     }
+    // K elements at once.  Welford: two-pass statistics of the batch (exact mean of K values, squared
+    // deviations from it), then ONE Chan merge - one division per K elements instead of one per element, and a
+    // smaller rounding error than K sequential updates.  Other reducers: K sequential adds.
+    template <int K>
+    __device__ __forceinline__ void add_batch(const T (&x)[K])
+    {
+        if constexpr (R == R_WELFORD) {
+            T sum = x[0];
+#pragma unroll
+            for (int i = 1; i < K; ++i) sum += x[i];
+            const T bmean = sum * (T(1) / T(K));
+            T bm2 = T(0);
+#pragma unroll
+            for (int i = 0; i < K; ++i) {
+                const T d = x[i] - bmean;
+                bm2 += d * d;
+            }
+            const T n = s.n + T(K);
+            const T delta = bmean - s.mean;
+            const T w = T(K) / n;
+            s.mean = s.mean + delta * w;
+            s.m2 = s.m2 + bm2 + delta * delta * (s.n * w);
+            s.n = n;
+        } else {
+#pragma unroll
+            for (int i = 0; i < K; ++i) add(x[i]);
+        }
+    }
     __device__ __forceinline__ void merge(const Acc &o)
     {
         if constexpr (R == R_MIN || R == R_MAX) {
@@ -263,29 +291,25 @@ __global__ void __launch_bounds__(256) red_lanes(RedArgs a)
                 int64_t i = tid;
                 for (; i + 3 * (int64_t)nt < nv; i += 4 * (int64_t)nt) {
                     V v0 = vsrc[i], v1 = vsrc[i + nt], v2 = vsrc[i + 2 * nt], v3 = vsrc[i + 3 * nt];
+                    T x[4 * N];
 #pragma unroll
-                    for (int e = 0; e < N; ++e) acc.add(v0.v[e]);
-#pragma unroll
-                    for (int e = 0; e < N; ++e) acc.add(v1.v[e]);
-#pragma unroll
-                    for (int e = 0; e < N; ++e) acc.add(v2.v[e]);
-#pragma unroll
-                    for (int e = 0; e < N; ++e) acc.add(v3.v[e]);
+                    for (int e = 0; e < N; ++e) {
+                        x[e] = v0.v[e];
+                        x[N + e] = v1.v[e];
+                        x[2 * N + e] = v2.v[e];
+                        x[3 * N + e] = v3.v[e];
+                    }
+                    acc.template add_batch<4 * N>(x);
                 }
                 for (; i < nv; i += nt) {
                     V v0 = vsrc[i];
-#pragma unroll
-                    for (int e = 0; e < N; ++e) acc.add(v0.v[e]);
+                    acc.template add_batch<N>(v0.v);
                 }
             } else {
                 int64_t i = tid;
                 for (; i + 3 * (int64_t)nt < a.n; i += 4 * (int64_t)nt) {
-                    const T x0 = src[i * a.s], x1 = src[(i + nt) * a.s], x2 = src[(i + 2 * nt) * a.s],
-                            x3 = src[(i + 3 * nt) * a.s];
-                    acc.add(x0);
-                    acc.add(x1);
-                    acc.add(x2);
-                    acc.add(x3);
+                    const T x[4] = {src[i * a.s], src[(i + nt) * a.s], src[(i + 2 * nt) * a.s], src[(i + 3 * nt) * a.s]};
+                    acc.template add_batch<4>(x);
                 }
                 for (; i < a.n; i += nt) acc.add(src[i * a.s]);
             }
@@ -342,18 +366,18 @@ __global__ void __launch_bounds__(256) red_cols(RedArgs a)
         const T *src = reinterpret_cast<const T *>(a.in) + in_off + c0;
         if (c0 < ncol) {  // ncol % W == 0 when W > 1 (host check), so a vector is all-in or all-out
             int64_t r = r0 + ty;
+            constexpr int U = (R == R_WELFORD) ? 4 : 8;  // rows in flight per thread
             if constexpr (W > 1) {
-                for (; r + 24 < r1; r += 32) {
-                    V v0 = *reinterpret_cast<const V *>(src + r * a.s);
-                    V v1 = *reinterpret_cast<const V *>(src + (r + 8) * a.s);
-                    V v2 = *reinterpret_cast<const V *>(src + (r + 16) * a.s);
-                    V v3 = *reinterpret_cast<const V *>(src + (r + 24) * a.s);
+                for (; r + 8 * (U - 1) < r1; r += 8 * U) {
+                    V v[U];
+#pragma unroll
+                    for (int u = 0; u < U; ++u) v[u] = *reinterpret_cast<const V *>(src + (r + 8 * u) * a.s);
 #pragma unroll
                     for (int e = 0; e < W; ++e) {
-                        acc[e].add(v0.v[e]);
-                        acc[e].add(v1.v[e]);
-                        acc[e].add(v2.v[e]);
-                        acc[e].add(v3.v[e]);
+                        T x[U];
+#pragma unroll
+                        for (int u = 0; u < U; ++u) x[u] = v[u].v[e];
+                        acc[e].template add_batch<U>(x);
                     }
                 }
                 for (; r < r1; r += 8) {
@@ -362,13 +386,11 @@ __global__ void __launch_bounds__(256) red_cols(RedArgs a)
                     for (int e = 0; e < W; ++e) acc[e].add(v0.v[e]);
                 }
             } else {
-                for (; r + 24 < r1; r += 32) {
-                    const T x0 = src[r * a.s], x1 = src[(r + 8) * a.s], x2 = src[(r + 16) * a.s],
-                            x3 = src[(r + 24) * a.s];
-                    acc[0].add(x0);
-                    acc[0].add(x1);
-                    acc[0].add(x2);
-                    acc[0].add(x3);
+                for (; r + 8 * (U - 1) < r1; r += 8 * U) {
+                    T x[U];
+#pragma unroll
+                    for (int u = 0; u < U; ++u) x[u] = src[(r + 8 * u) * a.s];
+                    acc[0].template add_batch<U>(x);
                 }
                 for (; r < r1; r += 8) acc[0].add(src[r * a.s]);
             }
