@@ -18,6 +18,9 @@
 // No CUTLASS: descriptors and PTX are written out below.
 #include <cuda.h>
 
+#include <algorithm>
+#include <cstdlib>
+
 #include "gemm.h"
 #include "zip_plan.h"
 
@@ -46,7 +49,7 @@ struct F32Args {
     int64_t m, n, k;
     int64_t rsc, csc;
     float alpha, beta;
-    int tiles_m, tiles_n;
+    int tiles_m, tiles_n, group_m, chunk_kb;
 };
 
 // ---- PTX helpers -----------------------------------------------------------------------------
@@ -114,6 +117,13 @@ __device__ __forceinline__ constexpr uint32_t make_idesc()
     return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 }
 
+// Accumulation accuracy.  The tensor core adds into its FP32 accumulator with truncation, so one long K
+// chain drifts linearly with K (measured: 9e-9 * K relative, i.e. 6e-5 at K = 8192, back to 1xTF32 quality at
+// K = 32768, benchmarks/gemm_accuracy.py).  The kernel therefore accumulates only chunk_kb k-blocks (8: K = 256)
+// per TMEM accumulator, double-buffers two accumulators, and lets the epilogue warps drain each finished
+// chunk into FP32 registers with round-to-nearest adds while the MMA warp fills the other one.  Error is
+// then ~2e-6 independent of K (fp32 class), for one extra TMEM read per 256 k.
+
 template <int BN>
 __global__ void __launch_bounds__(THREADS, 1)
 gemm_tf32x3(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
@@ -125,14 +135,25 @@ gemm_tf32x3(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t tiles = (raw + 1023u) & ~1023u;  // SWIZZLE_128B needs 1024-byte aligned tiles
     const uint32_t bars = tiles + STAGES * C::STAGE_BYTES;
-    // barrier block: full[STAGES], empty[STAGES], tmem_full, then the TMEM base address
-    const uint32_t full_bar = bars, empty_bar = bars + 8 * STAGES, tmem_full_bar = bars + 16 * STAGES;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem_raw + (bars - raw) + 16 * STAGES + 8);
+    // barrier block: full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2], then the TMEM base address
+    const uint32_t full_bar = bars, empty_bar = bars + 8 * STAGES;
+    const uint32_t tmem_full_bar = bars + 16 * STAGES, tmem_empty_bar = tmem_full_bar + 16;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem_raw + (bars - raw) + 16 * STAGES + 32);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int tile_m = blockIdx.x % p.tiles_m, tile_n = blockIdx.x / p.tiles_m;
+    // rasterise in groups of GROUP tile-rows: the ~148 concurrently resident CTAs then cover a roughly square patch
+    // of C, so each A/B panel slice fetched from DRAM is reused from L2 by many CTAs of the same wave
+    const int GROUP = p.group_m;
+    const int per_group = GROUP * p.tiles_n;
+    const int grp = blockIdx.x / per_group;
+    const int first_m = grp * GROUP;
+    const int gsize = min(GROUP, p.tiles_m - first_m);
+    const int in_grp = blockIdx.x - grp * per_group;
+    const int tile_m = first_m + in_grp % gsize, tile_n = in_grp / gsize;
     const int m0 = tile_m * BM, n0 = tile_n * BN;
     const int num_kb = (int)((p.k + BK - 1) / BK);
+    const int CHUNK_KB = p.chunk_kb;
+    const int num_chunks = (num_kb + CHUNK_KB - 1) / CHUNK_KB;
 
     if (threadIdx.x == 0) {
 #pragma unroll
@@ -140,11 +161,15 @@ gemm_tf32x3(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
             mbar_init(full_bar + 8 * s, 1);
             mbar_init(empty_bar + 8 * s, 1);
         }
-        mbar_init(tmem_full_bar, 1);
+#pragma unroll
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(tmem_full_bar + 8 * b, 1);   // one tcgen05.commit
+            mbar_init(tmem_empty_bar + 8 * b, 4);  // one arrival per epilogue warp
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 1) {  // whole warp: allocate BN TMEM columns, publish the base address through shared memory
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)BN));
+    if (warp == 1) {  // whole warp: allocate two BN-column accumulators, publish the base address through smem
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)(2 * BN)));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
     }
     tc_fence_before();
@@ -169,57 +194,80 @@ gemm_tf32x3(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
     } else if (warp == 1) {
         if (lane == 0) {  // ---- MMA issuer
             constexpr uint32_t idesc = make_idesc<BN>();
-            for (int kb = 0; kb < num_kb; ++kb) {
-                const int s = kb % STAGES;
-                const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
-                mbar_wait(full_bar + 8 * s, ph);
+            for (int ch = 0; ch < num_chunks; ++ch) {
+                const int buf = ch & 1;
+                mbar_wait(tmem_empty_bar + 8 * buf, (((uint32_t)ch >> 1) & 1u) ^ 1u);  // drained by the epilogue
                 tc_fence_after();
-                const uint32_t st = tiles + s * C::STAGE_BYTES;
-                const uint64_t da_hi = make_desc(st), da_lo = make_desc(st + C::A_BYTES);
-                const uint64_t db_hi = make_desc(st + 2 * C::A_BYTES), db_lo = make_desc(st + 2 * C::A_BYTES + C::B_BYTES);
+                const uint32_t acc = tmem_base + (uint32_t)(buf * BN);
+                const int kb_end = min(num_kb, (ch + 1) * CHUNK_KB);
+                for (int kb = ch * CHUNK_KB; kb < kb_end; ++kb) {
+                    const int s = kb % STAGES;
+                    const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
+                    mbar_wait(full_bar + 8 * s, ph);
+                    tc_fence_after();
+                    const uint32_t st = tiles + s * C::STAGE_BYTES;
+                    const uint64_t da_hi = make_desc(st), da_lo = make_desc(st + C::A_BYTES);
+                    const uint64_t db_hi = make_desc(st + 2 * C::A_BYTES), db_lo = make_desc(st + 2 * C::A_BYTES + C::B_BYTES);
+                    const uint32_t first = (kb != ch * CHUNK_KB);
 #pragma unroll
-                for (int k = 0; k < BK / UMMA_K; ++k) {
-                    const uint64_t adv = (uint64_t)(k * UMMA_K * 4 >> 4);  // 32 bytes per slice inside the swizzle row
-                    tc_mma_tf32(tmem_base, da_lo + adv, db_hi + adv, idesc, (kb | k) != 0);
-                    tc_mma_tf32(tmem_base, da_hi + adv, db_lo + adv, idesc, 1u);
-                    tc_mma_tf32(tmem_base, da_hi + adv, db_hi + adv, idesc, 1u);
+                    for (int k = 0; k < BK / UMMA_K; ++k) {
+                        const uint64_t adv = (uint64_t)(k * UMMA_K * 4 >> 4);  // 32 bytes per slice inside the swizzle row
+                        tc_mma_tf32(acc, da_lo + adv, db_hi + adv, idesc, first | (uint32_t)(k != 0));
+                        tc_mma_tf32(acc, da_hi + adv, db_lo + adv, idesc, 1u);
+                        tc_mma_tf32(acc, da_hi + adv, db_hi + adv, idesc, 1u);
+                    }
+                    tc_commit(empty_bar + 8 * s);  // arrives once these MMAs have finished reading the stage
                 }
-                tc_commit(empty_bar + 8 * s);  // arrives once these MMAs have finished reading the stage
+                tc_commit(tmem_full_bar + 8 * buf);  // this chunk's accumulator is complete
             }
-            tc_commit(tmem_full_bar);
         }
     } else {
-        // ---- epilogue: warp w may touch TMEM lanes 32*(w%4) .. +31
+        // ---- epilogue: warp w may touch TMEM lanes 32*(w%4) .. +31; thread = one row of the tile
         const int q = warp & 3;
-        mbar_wait(tmem_full_bar, 0);
-        tc_fence_after();
+        float sum[BN];
+#pragma unroll
+        for (int j = 0; j < BN; ++j) sum[j] = 0.f;
+        for (int ch = 0; ch < num_chunks; ++ch) {
+            const int buf = ch & 1;
+            mbar_wait(tmem_full_bar + 8 * buf, ((uint32_t)ch >> 1) & 1u);
+            tc_fence_after();
+#pragma unroll
+            for (int c0 = 0; c0 < BN; c0 += 32) {
+                uint32_t v[32];
+                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN + c0);
+                asm volatile(
+                    "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                    "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                    "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                    : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+                      "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+                      "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+                      "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                    : "r"(taddr));
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                for (int j = 0; j < 32; ++j) sum[c0 + j] += __uint_as_float(v[j]);
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tmem_empty_bar + 8 * buf) : "memory");
+        }
         const int64_t row = (int64_t)m0 + q * 32 + lane;
         const bool vec_ok = p.csc == 1 && (p.rsc & 3) == 0 && ((uintptr_t)p.c & 15) == 0;
-#pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += 32) {
-            uint32_t v[32];
-            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
-            asm volatile(
-                "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-                "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-                "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-                : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-                  "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
-                  "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
-                  "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-                : "r"(taddr));
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            const int64_t col0 = (int64_t)n0 + c0;
-            if (row < p.m && col0 < p.n) {
+        if (row < p.m) {
+#pragma unroll
+            for (int c0 = 0; c0 < BN; c0 += 32) {
+                const int64_t col0 = (int64_t)n0 + c0;
+                if (col0 >= p.n) break;
                 float *dst = p.c + row * p.rsc + col0 * p.csc;
                 if (vec_ok && col0 + 32 <= p.n) {
 #pragma unroll
                     for (int j = 0; j < 32; j += 4) {
                         float4 o;
-                        o.x = p.alpha * __uint_as_float(v[j]);
-                        o.y = p.alpha * __uint_as_float(v[j + 1]);
-                        o.z = p.alpha * __uint_as_float(v[j + 2]);
-                        o.w = p.alpha * __uint_as_float(v[j + 3]);
+                        o.x = p.alpha * sum[c0 + j];
+                        o.y = p.alpha * sum[c0 + j + 1];
+                        o.z = p.alpha * sum[c0 + j + 2];
+                        o.w = p.alpha * sum[c0 + j + 3];
                         if (p.beta != 0.f) {
                             const float4 old = *reinterpret_cast<const float4 *>(dst + j);
                             o.x += p.beta * old.x;
@@ -233,7 +281,7 @@ gemm_tf32x3(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
 #pragma unroll
                     for (int j = 0; j < 32; ++j) {
                         if (col0 + j < p.n) {
-                            float o = p.alpha * __uint_as_float(v[j]);
+                            float o = p.alpha * sum[c0 + j];
                             if (p.beta != 0.f) o += p.beta * dst[j * p.csc];
                             dst[j * p.csc] = o;
                         }
@@ -241,12 +289,11 @@ gemm_tf32x3(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
                 }
             }
         }
-        tc_fence_before();
     }
     __syncthreads();
     if (warp == 1) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)BN));
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)(2 * BN)));
     }
 }
 
@@ -319,6 +366,8 @@ int launch(ndb_ctx *ctx, const GemmArgs &g, float alpha, float beta, const float
     p.alpha = alpha; p.beta = beta;
     p.tiles_m = (int)((g.m + BM - 1) / BM);
     p.tiles_n = (int)((g.n + BN - 1) / BN);
+    p.group_m = getenv("NDB_GEMM_GROUP_M") ? std::max(1, atoi(getenv("NDB_GEMM_GROUP_M"))) : 12;
+    p.chunk_kb = getenv("NDB_GEMM_CHUNK_KB") ? std::max(1, atoi(getenv("NDB_GEMM_CHUNK_KB"))) : 8;
     static bool attr_done = false;
     if (!attr_done) {
         NDB_CUDA(cudaFuncSetAttribute(gemm_tf32x3<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg<BN>::SMEM_BYTES));
@@ -372,8 +421,8 @@ int gemm_f32_launch(ndb_ctx *ctx, const GemmArgs &g0, float alpha, float beta)
         }
     }
     if (st == NDB_OK) {
-        const bool wide = getenv("NDB_GEMM_F32_BN256") != nullptr && g.n >= 256;  // 128-wide tiles with 3 stages measured faster (248 vs 221 TFLOP/s at 8192^3)
-        st = wide ? launch<256>(ctx, g, alpha, beta, a_hi, a_lo, b_hi, b_lo, kp) : launch<128>(ctx, g, alpha, beta, a_hi, a_lo, b_hi, b_lo, kp);
+        // 128-wide tiles with a 3-stage ring measured faster than 256-wide with 2 stages (248 vs 221 TFLOP/s at 8192^3)
+        st = launch<128>(ctx, g, alpha, beta, a_hi, a_lo, b_hi, b_lo, kp);
     }
     cudaFreeAsync(ws, ctx->stream);
     return st;

@@ -462,7 +462,7 @@ __global__ void __launch_bounds__(256) zip_tile(TileArgs<NIN + 1> a, T s0, T s1,
 // tile extents multiples of the vector width (checked on the host).  Every thread first issues ALL its
 // global loads (PASSES vectors per producer), then the staged ones go through shared memory.
 template <typename T, int OP, int NIN>
-__global__ void __launch_bounds__(256, (NIN <= 2 ? 4 : 2)) zip_tile_vec(TileArgs<NIN + 1> a, T s0, T s1, int *flag)
+__global__ void __launch_bounds__(256, (NIN <= 1 ? 6 : (NIN <= 2 ? 4 : 2))) zip_tile_vec(TileArgs<NIN + 1> a, T s0, T s1, int *flag)
 {
     using V = Vec128<T>;
     constexpr int N = V::N;
