@@ -107,6 +107,13 @@ typedef enum {
     NDB_OP_SCALE_ADD = 22, /* out = in0 * s0 + in1 * s1   (gemv/gemm-style alpha/beta combine, two products one sum) */
     NDB_OP_TF32_HI = 23, /* out = tf32(in0), round to nearest (f32 only; operand packing of the 3xTF32 GEMM) */
     NDB_OP_TF32_LO = 24, /* out = in0 - tf32(in0)         (f32 only) */
+    /* predicates (closures given to Zip::all / Zip::any, src/zip/mod.rs:658-696): out = 1 or 0 in the element type */
+    NDB_OP_EQ = 25,
+    NDB_OP_NE = 26,
+    NDB_OP_LT = 27,
+    NDB_OP_LE = 28,
+    NDB_OP_GT = 29,
+    NDB_OP_GE = 30,
     NDB_OP__COUNT
 } ndb_op;
 
@@ -193,6 +200,11 @@ int ndb_view_broadcast(const ndb_view *v, int ndim, const int64_t *dim, ndb_view
 int ndb_view_permute(const ndb_view *v, const int *perm, ndb_view *out);
 /* invert_axis (src/impl_methods.rs:2676). */
 int ndb_view_invert_axis(ndb_view *v, int axis);
+/* merge_axes (src/dimension/mod.rs:739-763, src/impl_methods.rs:2724): fold axis `take` into axis `into` if the
+ * memory layout allows; returns 1 if merged (view updated), 0 if not possible (view unchanged), <0 on bad axes. */
+int ndb_view_merge_axes(ndb_view *v, int take, int into);
+/* collapse_axis (src/impl_methods.rs:1075): keep only `index` along `axis`; the axis stays with length 1. */
+int ndb_view_collapse_axis(ndb_view *v, int axis, int64_t index);
 /* split_at (src/impl_raw_views.rs:113-135): the sharding primitive. */
 int ndb_view_split_at(const ndb_view *v, int axis, int64_t index, ndb_view *left, ndb_view *right);
 /* Layout bitset of src/layout/mod.rs:9-16 as computed by array_layout (src/zip/mod.rs:54-77):
@@ -213,6 +225,14 @@ int ndb_view_min_stride_axis(const ndb_view *v);
 int ndb_zip(ndb_ctx *ctx, int op, const void *scalars, int n_parts, const ndb_view *parts);
 /* The plan ndb_zip would execute; pure host code (no device needed). */
 int ndb_zip_plan(int op, int n_parts, const ndb_view *parts, ndb_zip_plan_t *plan);
+/* Zip::all / Zip::any (src/zip/mod.rs:658-696): does the predicate `op` (NDB_OP_EQ..GE, or any op whose result is
+ * compared with zero) hold for every / some element tuple?  `inputs` are the producers (none is written); an empty
+ * shape gives all = 1 (vacuously true, tests/azip.rs:472-478) and any = 0.  Synchronises. */
+int ndb_zip_all(ndb_ctx *ctx, int op, const void *scalars, int n_inputs, const ndb_view *inputs, int *result);
+int ndb_zip_any(ndb_ctx *ctx, int op, const void *scalars, int n_inputs, const ndb_view *inputs, int *result);
+/* Zip::fold / par_fold with an additive accumulator (src/zip/mod.rs:622, parallel/impl_par_methods.rs:173):
+ * sum over all element tuples of op(inputs...), result (element type) to host. */
+int ndb_zip_fold_sum(ndb_ctx *ctx, int op, const void *scalars, int n_inputs, const ndb_view *inputs, void *out_host);
 /* Zip::map_collect's output-order rule (src/zip/mod.rs:278-281,764-789): returns 1 if the fresh
  * output must be F-order, 0 for C-order, given the INPUT producers only. */
 int ndb_zip_prefer_f(int n_inputs, const ndb_view *inputs);
@@ -233,6 +253,8 @@ int ndb_reduce_axis(ndb_ctx *ctx, int redop, int axis, const ndb_view *in, const
 int ndb_welford_axis(ndb_ctx *ctx, int axis, const ndb_view *in, const ndb_view *mean_out, const ndb_view *m2_out);
 int ndb_welford_merge(ndb_ctx *ctx, int n_shards, const int64_t *counts, const ndb_view *means, const ndb_view *m2s,
                       double ddof, int want_std, const ndb_view *out);
+/* ArrayRef::var / std over every element (src/numeric/impl_numeric.rs:180-249), result to host (floats only). */
+int ndb_var(ndb_ctx *ctx, const ndb_view *in, double ddof, int want_std, void *out_host);
 /* 1-D dot product (src/linalg/impl_linalg.rs:74-133, numeric_util.rs:56), result to host. */
 int ndb_dot(ndb_ctx *ctx, const ndb_view *x, const ndb_view *y, void *out_host);
 
@@ -257,6 +279,10 @@ void cblas_sgemm(int layout, int transa, int transb, int m, int n, int k, float 
                  const float *b, int ldb, float beta, float *c, int ldc);
 void cblas_dgemm(int layout, int transa, int transb, int m, int n, int k, double alpha, const double *a, int lda,
                  const double *b, int ldb, double beta, double *c, int ldc);
+void cblas_sgemv(int layout, int trans, int m, int n, float alpha, const float *a, int lda, const float *x, int incx,
+                 float beta, float *y, int incy);
+void cblas_dgemv(int layout, int trans, int m, int n, double alpha, const double *a, int lda, const double *x, int incx,
+                 double beta, double *y, int incy);
 float cblas_sdot(int n, const float *x, int incx, const float *y, int incy);
 double cblas_ddot(int n, const double *x, int incx, const double *y, int incy);
 

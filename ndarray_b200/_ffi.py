@@ -94,6 +94,8 @@ def lib():
         "ndb_view_permute": (i32, [PV, C.POINTER(i32), PV]),
         "ndb_view_invert_axis": (i32, [PV, i32]),
         "ndb_view_split_at": (i32, [PV, i32, i64, PV, PV]),
+        "ndb_view_merge_axes": (i32, [PV, i32, i32]),
+        "ndb_view_collapse_axis": (i32, [PV, i32, i64]),
         "ndb_view_layout": (C.c_uint32, [PV]),
         "ndb_view_is_contiguous": (i32, [PV]),
         "ndb_view_min_stride_axis": (i32, [PV]),
@@ -101,6 +103,10 @@ def lib():
         "ndb_zip_plan": (i32, [i32, i32, PV, C.POINTER(ZipPlan)]),
         "ndb_zip_prefer_f": (i32, [i32, PV]),
         "ndb_zip_host": (i32, [vp, i32, vp, i32, PV]),
+        "ndb_zip_all": (i32, [vp, i32, vp, i32, PV, C.POINTER(i32)]),
+        "ndb_zip_any": (i32, [vp, i32, vp, i32, PV, C.POINTER(i32)]),
+        "ndb_zip_fold_sum": (i32, [vp, i32, vp, i32, PV, vp]),
+        "ndb_var": (i32, [vp, PV, dbl, i32, vp]),
         "ndb_reduce_all": (i32, [vp, i32, PV, vp]),
         "ndb_reduce_all_dev": (i32, [vp, i32, PV, vp]),
         "ndb_reduce_axis": (i32, [vp, i32, i32, PV, PV, dbl]),

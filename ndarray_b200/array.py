@@ -28,7 +28,7 @@ CODE_DTYPE = {v: k for k, v in DTYPE_CODE.items()}
 
 class Op:
     COPY, FILL, ADD, SUB, MUL, DIV, REM, MUL_ADD, ADD_S, SUB_S, MUL_S, DIV_S, REM_S, RSUB_S, RDIV_S, NEG, AXPY, \
-        ADD_N, ABS, SQRT, MIN, MAX, SCALE_ADD, TF32_HI, TF32_LO = range(25)
+        ADD_N, ABS, SQRT, MIN, MAX, SCALE_ADD, TF32_HI, TF32_LO, EQ, NE, LT, LE, GT, GE = range(31)
 
 
 class Red:
@@ -425,6 +425,17 @@ class Array:
         check(st)
         return self._derive(out)
 
+    def merge_axes(self, take: int, into: int) -> bool:
+        """merge_axes (src/impl_methods.rs:2724): in place; True if the layout allowed it."""
+        r = lib().ndb_view_merge_axes(C.byref(self.v), int(take), int(into))
+        if r < 0:
+            raise _ffi.NdbError(-r, lib().ndb_last_error().decode())
+        return bool(r)
+
+    def collapse_axis(self, axis: int, index: int) -> None:
+        """collapse_axis (src/impl_methods.rs:1075): in place; the axis keeps length 1."""
+        check(lib().ndb_view_collapse_axis(C.byref(self.v), int(axis), int(index)))
+
     def split_at(self, axis: int, index: int):
         l, r = View(), View()
         check(lib().ndb_view_split_at(C.byref(self.v), int(axis), int(index), C.byref(l), C.byref(r)))
@@ -537,6 +548,17 @@ class Array:
             return s / self.dtype.type(n)
         q = abs(int(s)) // n  # Rust integer division truncates toward zero
         return self.dtype.type(-q if int(s) < 0 else q)
+
+    def var(self, ddof):
+        """ArrayRef::var (src/numeric/impl_numeric.rs:180): Welford over every element / (n - ddof)."""
+        out = np.zeros((), dtype=self.dtype)
+        check(lib().ndb_var(self.ctx.handle, C.byref(self.v), float(ddof), 0, C.c_void_p(out.ctypes.data)))
+        return out[()]
+
+    def std(self, ddof):
+        out = np.zeros((), dtype=self.dtype)
+        check(lib().ndb_var(self.ctx.handle, C.byref(self.v), float(ddof), 1, C.c_void_p(out.ctypes.data)))
+        return out[()]
 
     def _reduce_axis(self, redop, axis, ddof=0.0) -> "Array":
         axis = int(axis)
@@ -709,6 +731,34 @@ class Zip:
 
     par_map_assign_into = map_assign_into
 
+    def _pred(self, fn, op: int, scalars=()) -> bool:
+        n = len(self.parts)
+        views = (View * n)(*[p.v for p in self.parts])
+        sc = np.asarray(scalars, dtype=self.parts[0].dtype) if len(scalars) else None
+        res = C.c_int()
+        check(fn(self._ctx().handle, op, C.c_void_p(sc.ctypes.data) if sc is not None else None, n, views, C.byref(res)))
+        return bool(res.value)
+
+    def all(self, op: int, scalars=()) -> bool:
+        """Zip::all (src/zip/mod.rs:658) with a predicate op (Op.EQ .. Op.GE) over ALL producers (none is written)."""
+        return self._pred(lib().ndb_zip_all, op, scalars)
+
+    def any(self, op: int, scalars=()) -> bool:
+        """Zip::any (src/zip/mod.rs:685)."""
+        return self._pred(lib().ndb_zip_any, op, scalars)
+
+    def fold_sum(self, op: int, scalars=()):
+        """Zip::fold(0, |acc, ...| acc + op(...)) / par_fold (src/zip/mod.rs:622, impl_par_methods.rs:173)."""
+        n = len(self.parts)
+        views = (View * n)(*[p.v for p in self.parts])
+        sc = np.asarray(scalars, dtype=self.parts[0].dtype) if len(scalars) else None
+        out = np.zeros((), dtype=self.parts[0].dtype)
+        check(lib().ndb_zip_fold_sum(self._ctx().handle, op, C.c_void_p(sc.ctypes.data) if sc is not None else None, n, views,
+                                     C.c_void_p(out.ctypes.data)))
+        return out[()]
+
+    par_fold_sum = fold_sum
+
     def plan(self, op: int = Op.ADD_N):
         """The kernel class the planner picks for (first producer written, rest read)."""
         n = len(self.parts)
@@ -716,3 +766,14 @@ class Zip:
         pl = _ffi.ZipPlan()
         check(lib().ndb_zip_plan(op, n, views, C.byref(pl)))
         return pl
+
+
+def azip(closure, *producers, scalars=()):
+    """`azip!((a in &mut a, &b in &b, ...) closure)` (src/zip/zipmacro.rs:98): sugar for Zip::from(a).and(b)....for_each."""
+    z = Zip.from_(producers[0])
+    for p in producers[1:]:
+        z = z.and_(p)
+    z.for_each(closure, scalars)
+
+
+par_azip = azip  # src/parallel/zipmacro.rs:53

@@ -43,6 +43,12 @@ int op_arity(int op)
     case NDB_OP_AXPY:
     case NDB_OP_MIN:
     case NDB_OP_MAX:
+    case NDB_OP_EQ:
+    case NDB_OP_NE:
+    case NDB_OP_LT:
+    case NDB_OP_LE:
+    case NDB_OP_GT:
+    case NDB_OP_GE:
     case NDB_OP_SCALE_ADD: return 2;
     case NDB_OP_MUL_ADD: return 3;
     case NDB_OP_ADD_N: return -1;

@@ -99,6 +99,78 @@ __global__ void __launch_bounds__(256) gemm_any(GemmArgs g, T alpha, T beta)
     }
 }
 
+// ---- matrix-vector: y <- alpha * A x + beta * y (general_mat_vec_mul, impl_linalg.rs:657-743) ------------------
+// HBM-bound (A is read once).  Two forms, chosen by which axis of A is denser:
+//   gemv_rows: a warp per row, lanes stride along k (coalesced when A is row-major), shuffle reduction;
+//   gemv_cols: a thread per row, all threads walk k together (coalesced when A is column-major).
+struct GemvArgs {
+    const char *a, *x;
+    char *y;
+    int64_t m, k, rsa, csa, sx, sy;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(256) gemv_rows(GemvArgs g, T alpha, T beta)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (row >= g.m) return;
+    const T *A = reinterpret_cast<const T *>(g.a) + row * g.rsa;
+    const T *x = reinterpret_cast<const T *>(g.x);
+    T acc0 = T(0), acc1 = T(0), acc2 = T(0), acc3 = T(0);
+    int64_t k = lane;
+    for (; k + 96 < g.k; k += 128) {
+        const T a0 = A[k * g.csa], a1 = A[(k + 32) * g.csa], a2 = A[(k + 64) * g.csa], a3 = A[(k + 96) * g.csa];
+        acc0 = mul_add(a0, x[k * g.sx], acc0);
+        acc1 = mul_add(a1, x[(k + 32) * g.sx], acc1);
+        acc2 = mul_add(a2, x[(k + 64) * g.sx], acc2);
+        acc3 = mul_add(a3, x[(k + 96) * g.sx], acc3);
+    }
+    for (; k < g.k; k += 32) acc0 = mul_add(A[k * g.csa], x[k * g.sx], acc0);
+    T acc = w_add(w_add(acc0, acc1), w_add(acc2, acc3));
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) acc = w_add(acc, __shfl_down_sync(0xffffffffu, acc, d));
+    if (lane == 0) {
+        T *dst = reinterpret_cast<T *>(g.y) + row * g.sy;
+        *dst = beta == T(0) ? w_mul(alpha, acc) : w_add(w_mul(alpha, acc), w_mul(beta, *dst));
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) gemv_cols(GemvArgs g, T alpha, T beta)
+{
+    const int64_t row = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (row >= g.m) return;
+    const T *A = reinterpret_cast<const T *>(g.a) + row * g.rsa;
+    const T *x = reinterpret_cast<const T *>(g.x);
+    T acc0 = T(0), acc1 = T(0), acc2 = T(0), acc3 = T(0);
+    int64_t k = 0;
+    for (; k + 3 < g.k; k += 4) {
+        const T a0 = A[k * g.csa], a1 = A[(k + 1) * g.csa], a2 = A[(k + 2) * g.csa], a3 = A[(k + 3) * g.csa];
+        acc0 = mul_add(a0, x[k * g.sx], acc0);
+        acc1 = mul_add(a1, x[(k + 1) * g.sx], acc1);
+        acc2 = mul_add(a2, x[(k + 2) * g.sx], acc2);
+        acc3 = mul_add(a3, x[(k + 3) * g.sx], acc3);
+    }
+    for (; k < g.k; ++k) acc0 = mul_add(A[k * g.csa], x[k * g.sx], acc0);
+    const T acc = w_add(w_add(acc0, acc1), w_add(acc2, acc3));
+    T *dst = reinterpret_cast<T *>(g.y) + row * g.sy;
+    *dst = beta == T(0) ? w_mul(alpha, acc) : w_add(w_mul(alpha, acc), w_mul(beta, *dst));
+}
+
+template <typename T>
+static int gemv_launch(ndb_ctx *ctx, const GemvArgs &g, T alpha, T beta)
+{
+    if (g.m == 0) return NDB_OK;
+    if (llabs(g.csa) <= llabs(g.rsa) || g.m < 2048) {
+        gemv_rows<T><<<(unsigned)((g.m + 7) / 8), 256, 0, ctx->stream>>>(g, alpha, beta);
+    } else {
+        gemv_cols<T><<<(unsigned)((g.m + 255) / 256), 256, 0, ctx->stream>>>(g, alpha, beta);
+    }
+    NDB_CHECK_LAUNCH();
+    return NDB_OK;
+}
+
 // C <- beta * C  (k == 0, or alpha == 0)
 template <typename T>
 __global__ void __launch_bounds__(256) scale_c(GemmArgs g, T beta)
@@ -283,6 +355,46 @@ static void cblas_gemm_impl(int dtype, int layout, int transa, int transb, int m
 }
 
 template <typename T>
+static void cblas_gemv_impl(int dtype, int layout, int trans, int m, int n, T alpha, const T *a, int lda, const T *x, int incx,
+                            T beta, T *y, int incy)
+{
+    ndb_ctx *ctx = blas_ctx();
+    if (!ctx) abort();
+    std::lock_guard<std::mutex> lk(g_blas_mu);
+    DeviceGuard guard(ctx->device);
+    const bool t = trans != NdbCblasNoTrans;
+    const int64_t ylen = t ? n : m, xlen = t ? m : n;
+    if (ylen <= 0) return;
+    // op(A): ylen x xlen
+    const BlasMat A = blas_operand(layout, trans, ylen, xlen, lda);
+    const int64_t ax = llabs((int64_t)incx), ay = llabs((int64_t)incy);
+    const size_t sxb = xlen > 0 ? ((size_t)(xlen - 1) * ax + 1) * sizeof(T) : 16;
+    const size_t syb = ((size_t)(ylen - 1) * ay + 1) * sizeof(T);
+    bool ok = ensure_stage(ctx, 0, std::max<size_t>(16, A.span * sizeof(T))) == NDB_OK && ensure_stage(ctx, 1, sxb) == NDB_OK &&
+              ensure_stage(ctx, 2, syb) == NDB_OK;
+    if (ok && A.span) ok = cudaMemcpyAsync(ctx->stage[0], a, A.span * sizeof(T), cudaMemcpyHostToDevice, ctx->stream) == cudaSuccess;
+    if (ok && xlen > 0) ok = cudaMemcpyAsync(ctx->stage[1], x, sxb, cudaMemcpyHostToDevice, ctx->stream) == cudaSuccess;
+    if (ok && (beta != T(0) || ay != 1)) ok = cudaMemcpyAsync(ctx->stage[2], y, syb, cudaMemcpyHostToDevice, ctx->stream) == cudaSuccess;
+    ndb_view va, vx, vy;
+    memset(&va, 0, sizeof(va));
+    memset(&vx, 0, sizeof(vx));
+    memset(&vy, 0, sizeof(vy));
+    va.ptr = ctx->stage[0]; va.ndim = 2; va.dtype = dtype; va.dim[0] = ylen; va.dim[1] = xlen; va.stride[0] = A.rs; va.stride[1] = A.cs;
+    vx.ndim = vy.ndim = 1; vx.dtype = vy.dtype = dtype;
+    vx.dim[0] = xlen; vx.stride[0] = incx;
+    vy.dim[0] = ylen; vy.stride[0] = incy;
+    vx.ptr = (char *)ctx->stage[1] + (incx < 0 && xlen > 0 ? (int64_t)(xlen - 1) * ax * (int64_t)sizeof(T) : 0);
+    vy.ptr = (char *)ctx->stage[2] + (incy < 0 ? (int64_t)(ylen - 1) * ay * (int64_t)sizeof(T) : 0);
+    if (ok) ok = ndb_gemv(ctx, &alpha, &va, &vx, &beta, &vy) == NDB_OK;
+    if (ok) ok = cudaMemcpyAsync(y, ctx->stage[2], syb, cudaMemcpyDeviceToHost, ctx->stream) == cudaSuccess;
+    if (ok) ok = cudaStreamSynchronize(ctx->stream) == cudaSuccess;
+    if (!ok) {
+        fprintf(stderr, "libndb200: cblas gemv failed: %s\n", ndb_last_error());
+        abort();
+    }
+}
+
+template <typename T>
 static T cblas_dot_impl(int dtype, int n, const T *x, int incx, const T *y, int incy)
 {
     ndb_ctx *ctx = blas_ctx();
@@ -328,10 +440,15 @@ int ndb_gemm(ndb_ctx *ctx, const void *alpha, const ndb_view *a, const ndb_view 
     return gemm_impl(ctx, alpha, a, b, beta, c);
 }
 
-// general_mat_vec_mul (impl_linalg.rs:657-743): y <- alpha*A*x + beta*y, as the n == 1 case.
+// general_mat_vec_mul (impl_linalg.rs:657-743): y <- alpha*A*x + beta*y
 int ndb_gemv(ndb_ctx *ctx, const void *alpha, const ndb_view *a, const ndb_view *x, const void *beta, const ndb_view *y)
 {
     clear_error();
+    if (!ctx) {
+        set_error("gemv: null context (no CPU fallback exists)");
+        return NDB_ERR_INVALID_ARG;
+    }
+    if (!alpha || !beta) return NDB_ERR_INVALID_ARG;
     NDB_TRY(validate_view(a, "gemv matrix"));
     NDB_TRY(validate_view(x, "gemv x"));
     NDB_TRY(validate_view(y, "gemv y"));
@@ -341,14 +458,32 @@ int ndb_gemv(ndb_ctx *ctx, const void *alpha, const ndb_view *a, const ndb_view 
                   (long long)(x->ndim == 1 ? x->dim[0] : -1), (long long)(y->ndim == 1 ? y->dim[0] : -1));
         return NDB_ERR_INCOMPATIBLE_SHAPE;
     }
-    ndb_view xb = *x, yc = *y;
-    xb.ndim = 2;
-    xb.dim[1] = 1;
-    xb.stride[1] = 1;
-    yc.ndim = 2;
-    yc.dim[1] = 1;
-    yc.stride[1] = 1;
-    return gemm_impl(ctx, alpha, a, &xb, beta, &yc);
+    if (a->dtype != x->dtype || a->dtype != y->dtype) {
+        set_error("general_mat_vec_mul: mixed element types");
+        return NDB_ERR_UNSUPPORTED;
+    }
+    if (y->dim[0] > 1 && y->stride[0] == 0) {
+        set_error("general_mat_vec_mul: output has a zero stride");
+        return NDB_ERR_ALIASING;
+    }
+    GemvArgs g;
+    g.a = (const char *)a->ptr;
+    g.x = (const char *)x->ptr;
+    g.y = (char *)y->ptr;
+    g.m = a->dim[0];
+    g.k = a->dim[1];
+    g.rsa = a->stride[0];
+    g.csa = a->stride[1];
+    g.sx = x->stride[0];
+    g.sy = y->stride[0];
+    DeviceGuard guard(ctx->device);
+    switch (a->dtype) {
+    case NDB_F32: return gemv_launch<float>(ctx, g, *(const float *)alpha, *(const float *)beta);
+    case NDB_F64: return gemv_launch<double>(ctx, g, *(const double *)alpha, *(const double *)beta);
+    case NDB_I32: return gemv_launch<int32_t>(ctx, g, *(const int32_t *)alpha, *(const int32_t *)beta);
+    case NDB_I64: return gemv_launch<int64_t>(ctx, g, *(const int64_t *)alpha, *(const int64_t *)beta);
+    }
+    return NDB_ERR_UNSUPPORTED;
 }
 
 void cblas_sgemm(int layout, int transa, int transb, int m, int n, int k, float alpha, const float *a, int lda,
@@ -361,6 +496,18 @@ void cblas_dgemm(int layout, int transa, int transb, int m, int n, int k, double
                  const double *b, int ldb, double beta, double *c, int ldc)
 {
     cblas_gemm_impl<double>(NDB_F64, layout, transa, transb, m, n, k, alpha, a, lda, b, ldb, beta, c, ldc);
+}
+
+void cblas_sgemv(int layout, int trans, int m, int n, float alpha, const float *a, int lda, const float *x, int incx,
+                 float beta, float *y, int incy)
+{
+    cblas_gemv_impl<float>(NDB_F32, layout, trans, m, n, alpha, a, lda, x, incx, beta, y, incy);
+}
+
+void cblas_dgemv(int layout, int trans, int m, int n, double alpha, const double *a, int lda, const double *x, int incx,
+                 double beta, double *y, int incy)
+{
+    cblas_gemv_impl<double>(NDB_F64, layout, trans, m, n, alpha, a, lda, x, incx, beta, y, incy);
 }
 
 float cblas_sdot(int n, const float *x, int incx, const float *y, int incy)

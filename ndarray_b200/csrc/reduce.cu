@@ -540,7 +540,7 @@ __global__ void __launch_bounds__(256) red_all_rows(AllArgs a)
 
 // one block merges the per-block partials in index order and writes the scalar
 template <typename T, int R>
-__global__ void __launch_bounds__(256) red_all_finish(const void *partial, int n, T *out)
+__global__ void __launch_bounds__(256) red_all_finish(const void *partial, int n, T *out, T dof, int want_std)
 {
     __shared__ Acc<T, R> smem[32];
     const Acc<T, R> *p = reinterpret_cast<const Acc<T, R> *>(partial);
@@ -548,7 +548,15 @@ __global__ void __launch_bounds__(256) red_all_finish(const void *partial, int n
     acc.reset();
     for (int i = threadIdx.x; i < n; i += blockDim.x) acc.merge(p[i]);
     acc = block_reduce(acc, smem);
-    if (threadIdx.x == 0) *out = acc.s;
+    if (threadIdx.x == 0) {
+        if constexpr (R == R_WELFORD) {
+            T v = acc.s.m2 / dof;
+            if (want_std) v = std::is_same<T, float>::value ? (T)sqrtf((float)v) : (T)sqrt((double)v);
+            *out = v;
+        } else {
+            *out = acc.s;
+        }
+    }
 }
 
 // dot product partials: x[i*sx] * y[i*sy], separately rounded product then sum (numeric_util.rs:56)
@@ -623,7 +631,7 @@ static void collapse_for_all(const ndb_view *v, AllArgs *a)
 }
 
 template <typename T, int R>
-static int reduce_all_typed(ndb_ctx *ctx, const ndb_view *v, T *out_dev)
+static int reduce_all_typed(ndb_ctx *ctx, const ndb_view *v, T *out_dev, T dof = T(1), int want_std = 0)
 {
     AllArgs a;
     memset(&a, 0, sizeof(a));
@@ -644,7 +652,7 @@ static int reduce_all_typed(ndb_ctx *ctx, const ndb_view *v, T *out_dev)
         red_all_rows<T, R><<<blocks, 256, 0, ctx->stream>>>(a);
     }
     NDB_CHECK_LAUNCH();
-    red_all_finish<T, R><<<1, 256, 0, ctx->stream>>>(a.partial, blocks, out_dev);
+    red_all_finish<T, R><<<1, 256, 0, ctx->stream>>>(a.partial, blocks, out_dev, dof, want_std);
     NDB_CHECK_LAUNCH();
     return NDB_OK;
 }
@@ -957,6 +965,44 @@ int ndb_reduce_all(ndb_ctx *ctx, int redop, const ndb_view *in, void *out_host)
     return NDB_OK;
 }
 
+// ArrayRef::var / std (src/numeric/impl_numeric.rs:180-249): Welford over every element, M2 / (n - ddof).
+int ndb_var(ndb_ctx *ctx, const ndb_view *in, double ddof, int want_std, void *out_host)
+{
+    clear_error();
+    if (!ctx || !out_host) {
+        set_error("var: null context or output (no CPU fallback exists)");
+        return NDB_ERR_INVALID_ARG;
+    }
+    NDB_TRY(validate_view(in, "var"));
+    if (!dtype_is_float(in->dtype)) {
+        set_error("var/std need a float element type");
+        return NDB_ERR_UNSUPPORTED;
+    }
+    const int64_t n = view_len(in);
+    // assert!(!(ddof < zero || ddof > n)) in the element type; NaN passes (impl_numeric.rs:185-190)
+    const bool f32 = in->dtype == NDB_F32;
+    const double nn = f32 ? (double)(float)n : (double)n, dd = f32 ? (double)(float)ddof : ddof;
+    if (dd < 0.0 || dd > nn) {
+        set_error("`ddof` must not be less than zero or greater than the length of the axis");
+        return NDB_ERR_INVALID_ARG;
+    }
+    DeviceGuard g(ctx->device);
+    if (n == 0) {  // 0 / (0 - ddof): NaN for ddof == 0 (tests/numeric.rs:175-188)
+        const double v = 0.0 / (nn - dd);
+        if (f32) *(float *)out_host = (float)v;
+        else *(double *)out_host = v;
+        return NDB_OK;
+    }
+    NDB_TRY(ensure_workspace(ctx, 4096));
+    void *dev_scalar = (char *)ctx->workspace + ctx->workspace_bytes - 64;
+    if (f32) NDB_TRY((reduce_all_typed<float, R_WELFORD>(ctx, in, (float *)dev_scalar, (float)n - (float)ddof, want_std)));
+    else NDB_TRY((reduce_all_typed<double, R_WELFORD>(ctx, in, (double *)dev_scalar, (double)n - ddof, want_std)));
+    NDB_CUDA(cudaMemcpyAsync(ctx->host_scalar, dev_scalar, dtype_size(in->dtype), cudaMemcpyDeviceToHost, ctx->stream));
+    NDB_CUDA(cudaStreamSynchronize(ctx->stream));
+    memcpy(out_host, ctx->host_scalar, dtype_size(in->dtype));
+    return NDB_OK;
+}
+
 int ndb_reduce_axis(ndb_ctx *ctx, int redop, int axis, const ndb_view *in, const ndb_view *out, double ddof)
 {
     clear_error();
@@ -1059,7 +1105,7 @@ int ndb_dot(ndb_ctx *ctx, const ndb_view *x, const ndb_view *y, void *out_host)
     dot_partials<T><<<blocks, 256, 0, ctx->stream>>>((const T *)x->ptr, sx, (const T *)y->ptr, sy, n,         \
                                                      ctx->workspace);                                         \
     NDB_CHECK_LAUNCH();                                                                                       \
-    red_all_finish<T, R_SUM><<<1, 256, 0, ctx->stream>>>(ctx->workspace, blocks, (T *)dev_scalar);            \
+    red_all_finish<T, R_SUM><<<1, 256, 0, ctx->stream>>>(ctx->workspace, blocks, (T *)dev_scalar, T(1), 0);   \
     NDB_CHECK_LAUNCH();
     switch (x->dtype) {
     case NDB_F32: { NDB_DOT(float) } break;

@@ -174,6 +174,54 @@ int ndb_view_invert_axis(ndb_view *v, int axis)
     return NDB_OK;
 }
 
+// reference: src/dimension/mod.rs:739-763 (merge_axes)
+int ndb_view_merge_axes(ndb_view *v, int take, int into)
+{
+    if (validate_view(v, "merge_axes") != NDB_OK) return -1;
+    if (take < 0 || take >= v->ndim || into < 0 || into >= v->ndim) {
+        set_error("merge_axes: axis out of bounds");
+        return -NDB_ERR_OUT_OF_BOUNDS;
+    }
+    const int64_t into_len = v->dim[into], into_stride = v->stride[into];
+    const int64_t take_len = v->dim[take], take_stride = v->stride[take];
+    const int64_t merged = into_len * take_len;
+    if (take_len <= 1) {
+        v->dim[into] = merged;
+        v->dim[take] = merged == 0 ? 0 : 1;
+        return 1;
+    }
+    if (into_len <= 1) {
+        v->stride[into] = take_stride;
+        v->dim[into] = merged;
+        v->dim[take] = merged == 0 ? 0 : 1;
+        return 1;
+    }
+    if (take_stride == into_len * into_stride) {
+        v->dim[into] = merged;
+        v->dim[take] = 1;
+        return 1;
+    }
+    return 0;
+}
+
+// reference: src/impl_methods.rs:1075-1081 (collapse_axis) -> dimension::do_collapse_axis (mod.rs:372-386)
+int ndb_view_collapse_axis(ndb_view *v, int axis, int64_t index)
+{
+    NDB_TRY(validate_view(v, "collapse_axis"));
+    if (axis < 0 || axis >= v->ndim) {
+        set_error("collapse_axis: axis %d out of bounds", axis);
+        return NDB_ERR_OUT_OF_BOUNDS;
+    }
+    if (index < 0 || index >= v->dim[axis]) {
+        set_error("collapse_axis: Index %lld must be less than axis length %lld for array with shape", (long long)index,
+                  (long long)v->dim[axis]);
+        return NDB_ERR_OUT_OF_BOUNDS;
+    }
+    move_ptr(v, index * v->stride[axis]);
+    v->dim[axis] = 1;
+    return NDB_OK;
+}
+
 // reference: src/impl_raw_views.rs:113-135 (split_at): the right part starts `index` steps along `axis`,
 // unless that would point past the allocation (index == len), in which case the pointer is left alone.
 int ndb_view_split_at(const ndb_view *v, int axis, int64_t index, ndb_view *left, ndb_view *right)

@@ -65,6 +65,112 @@ int ndb_zip(ndb_ctx *ctx, int op, const void *scalars, int n_parts, const ndb_vi
 }  // extern "C"
 
 // ---------------------------------------------------------------------------------------------
+// Zip::all / any / fold (src/zip/mod.rs:622-696).  The closure's result is materialised into a dense scratch
+// array by the Zip engine and reduced by the reduction engine (MIN for all, MAX for any, SUM for fold).
+extern "C" int ndb_reduce_all(ndb_ctx *ctx, int redop, const ndb_view *in, void *out_host);
+
+namespace ndb {
+
+static int zip_then_reduce(ndb_ctx *ctx, int op, const void *scalars, int n_inputs, const ndb_view *inputs, int redop,
+                           void *out_host, bool *empty)
+{
+    clear_error();
+    *empty = false;
+    if (!ctx) {
+        set_error("Zip: null context (no CPU fallback exists)");
+        return NDB_ERR_INVALID_ARG;
+    }
+    if (n_inputs < 1 || n_inputs > NDB_MAX_PARTS - 1 || !inputs) {
+        set_error("Zip: between 1 and %d input producers are supported", NDB_MAX_PARTS - 1);
+        return NDB_ERR_UNSUPPORTED;
+    }
+    NDB_TRY(validate_view(&inputs[0], "Zip producer"));
+    ndb_view parts[NDB_MAX_PARTS];
+    ndb_view &out = parts[0];
+    memset(&out, 0, sizeof(out));
+    out.ndim = inputs[0].ndim;
+    out.dtype = inputs[0].dtype;
+    int64_t total = 1;
+    for (int i = out.ndim - 1; i >= 0; --i) {
+        out.dim[i] = inputs[0].dim[i];
+        out.stride[i] = total;
+        total *= out.dim[i];
+    }
+    for (int p = 0; p < n_inputs; ++p) parts[p + 1] = inputs[p];
+    if (total == 0) {
+        // still validate shapes / arity like a real traversal would
+        ZipPlan z;
+        out.ptr = inputs[0].ptr;
+        NDB_TRY(make_zip_plan(op, n_inputs + 1, parts, &z));
+        *empty = true;
+        return NDB_OK;
+    }
+    DeviceGuard g(ctx->device);
+    void *tmp = nullptr;
+    NDB_CUDA(cudaMallocAsync(&tmp, (size_t)total * dtype_size(out.dtype), ctx->stream));
+    out.ptr = tmp;
+    int st = ndb_zip(ctx, op, scalars, n_inputs + 1, parts);
+    if (st == NDB_OK) st = ndb_reduce_all(ctx, redop, &out, out_host);
+    cudaFreeAsync(tmp, ctx->stream);
+    return st;
+}
+
+static bool nonzero(int dtype, const void *v)
+{
+    switch (dtype) {
+    case NDB_F32: return *(const float *)v != 0.f;
+    case NDB_F64: return *(const double *)v != 0.0;
+    case NDB_I32: return *(const int32_t *)v != 0;
+    default: return *(const int64_t *)v != 0;
+    }
+}
+
+static bool is_predicate(int op) { return op >= NDB_OP_EQ && op <= NDB_OP_GE; }
+
+}  // namespace ndb
+
+extern "C" {
+
+int ndb_zip_all(ndb_ctx *ctx, int op, const void *scalars, int n_inputs, const ndb_view *inputs, int *result)
+{
+    if (!result) return NDB_ERR_INVALID_ARG;
+    if (!is_predicate(op)) {
+        set_error("Zip::all takes a predicate op (NDB_OP_EQ..NDB_OP_GE)");
+        return NDB_ERR_UNSUPPORTED;
+    }
+    unsigned char v[8] = {0};
+    bool empty = false;
+    NDB_TRY(zip_then_reduce(ctx, op, scalars, n_inputs, inputs, NDB_RED_MIN, v, &empty));
+    *result = empty ? 1 : (nonzero(inputs[0].dtype, v) ? 1 : 0);  // vacuously true on an empty shape
+    return NDB_OK;
+}
+
+int ndb_zip_any(ndb_ctx *ctx, int op, const void *scalars, int n_inputs, const ndb_view *inputs, int *result)
+{
+    if (!result) return NDB_ERR_INVALID_ARG;
+    if (!is_predicate(op)) {
+        set_error("Zip::any takes a predicate op (NDB_OP_EQ..NDB_OP_GE)");
+        return NDB_ERR_UNSUPPORTED;
+    }
+    unsigned char v[8] = {0};
+    bool empty = false;
+    NDB_TRY(zip_then_reduce(ctx, op, scalars, n_inputs, inputs, NDB_RED_MAX, v, &empty));
+    *result = empty ? 0 : (nonzero(inputs[0].dtype, v) ? 1 : 0);
+    return NDB_OK;
+}
+
+int ndb_zip_fold_sum(ndb_ctx *ctx, int op, const void *scalars, int n_inputs, const ndb_view *inputs, void *out_host)
+{
+    if (!out_host) return NDB_ERR_INVALID_ARG;
+    bool empty = false;
+    NDB_TRY(zip_then_reduce(ctx, op, scalars, n_inputs, inputs, NDB_RED_SUM, out_host, &empty));
+    if (empty) memset(out_host, 0, dtype_size(inputs[0].dtype));
+    return NDB_OK;
+}
+
+}  // extern "C"
+
+// ---------------------------------------------------------------------------------------------
 // Host-buffer path.  Every producer lives in host memory; each one's address span is mirrored in a
 // device staging buffer.  When the outermost axis separates a producer into disjoint slabs, slabs are
 // streamed: H2D of slab c+1, the kernel on slab c and D2H of slab c-1 overlap on three streams, so

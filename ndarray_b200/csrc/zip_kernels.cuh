@@ -144,6 +144,12 @@ __device__ __forceinline__ T apply_op(const T *x, T s0, T s1, int *flag)
     } else if constexpr (OP == NDB_OP_MIN) return w_min(x[0], x[1]);
     else if constexpr (OP == NDB_OP_MAX) return w_max(x[0], x[1]);
     else if constexpr (OP == NDB_OP_SCALE_ADD) return w_add(w_mul(x[0], s0), w_mul(x[1], s1));
+    else if constexpr (OP == NDB_OP_EQ) return x[0] == x[1] ? T(1) : T(0);
+    else if constexpr (OP == NDB_OP_NE) return x[0] != x[1] ? T(1) : T(0);
+    else if constexpr (OP == NDB_OP_LT) return x[0] < x[1] ? T(1) : T(0);
+    else if constexpr (OP == NDB_OP_LE) return x[0] <= x[1] ? T(1) : T(0);
+    else if constexpr (OP == NDB_OP_GT) return x[0] > x[1] ? T(1) : T(0);
+    else if constexpr (OP == NDB_OP_GE) return x[0] >= x[1] ? T(1) : T(0);
     else if constexpr (OP == NDB_OP_TF32_HI || OP == NDB_OP_TF32_LO) {
         if constexpr (std::is_same<T, float>::value) {
             uint32_t hi;
@@ -711,6 +717,12 @@ int zip_dispatch_typed(ndb_ctx *ctx, const ZipPlan &z, const void *scalars)
         NDB_ZIP_CASE(NDB_OP_SCALE_ADD, 2)
         NDB_ZIP_CASE(NDB_OP_TF32_HI, 1)
         NDB_ZIP_CASE(NDB_OP_TF32_LO, 1)
+        NDB_ZIP_CASE(NDB_OP_EQ, 2)
+        NDB_ZIP_CASE(NDB_OP_NE, 2)
+        NDB_ZIP_CASE(NDB_OP_LT, 2)
+        NDB_ZIP_CASE(NDB_OP_LE, 2)
+        NDB_ZIP_CASE(NDB_OP_GT, 2)
+        NDB_ZIP_CASE(NDB_OP_GE, 2)
 #undef NDB_ZIP_CASE
     case NDB_OP_ADD_N:
         switch (nin) {

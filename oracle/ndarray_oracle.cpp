@@ -45,7 +45,8 @@ enum { F32 = 0, F64 = 1, I32 = 2, I64 = 3 };
 // op / redop numbering is shared with include/ndb200.h on purpose (the tests pass the same integers)
 enum {
     OP_COPY, OP_FILL, OP_ADD, OP_SUB, OP_MUL, OP_DIV, OP_REM, OP_MUL_ADD, OP_ADD_S, OP_SUB_S, OP_MUL_S, OP_DIV_S,
-    OP_REM_S, OP_RSUB_S, OP_RDIV_S, OP_NEG, OP_AXPY, OP_ADD_N, OP_ABS, OP_SQRT, OP_MIN, OP_MAX, OP_SCALE_ADD
+    OP_REM_S, OP_RSUB_S, OP_RDIV_S, OP_NEG, OP_AXPY, OP_ADD_N, OP_ABS, OP_SQRT, OP_MIN, OP_MAX, OP_SCALE_ADD,
+    OP_TF32_HI, OP_TF32_LO, OP_EQ, OP_NE, OP_LT, OP_LE, OP_GT, OP_GE
 };
 enum { RED_SUM, RED_PROD, RED_MIN, RED_MAX, RED_MEAN, RED_VAR, RED_STD };
 
@@ -360,6 +361,12 @@ static inline T apply(int op, int nin, const T *x, T s0, T s1, int *trap)
     case OP_MIN: return wmin(x[0], x[1]);
     case OP_MAX: return wmax(x[0], x[1]);
     case OP_SCALE_ADD: return wadd(wmul(x[0], s0), wmul(x[1], s1));
+    case OP_EQ: return x[0] == x[1] ? (T)1 : (T)0;
+    case OP_NE: return x[0] != x[1] ? (T)1 : (T)0;
+    case OP_LT: return x[0] < x[1] ? (T)1 : (T)0;
+    case OP_LE: return x[0] <= x[1] ? (T)1 : (T)0;
+    case OP_GT: return x[0] > x[1] ? (T)1 : (T)0;
+    case OP_GE: return x[0] >= x[1] ? (T)1 : (T)0;
     default: return x[0];
     }
 }

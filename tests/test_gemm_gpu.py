@@ -196,3 +196,38 @@ def test_cblas_dropin_symbols(nd):
     x, y = rng.standard_normal(100), rng.standard_normal(100)
     got = L.cblas_ddot(50, x.ctypes.data, 2, y.ctypes.data, -2)
     assert abs(got - float(x[:100:2] @ y[:100:2][::-1])) < 1e-12
+
+
+def test_cblas_gemv_dropin(nd):  # impl_linalg.rs:705-728
+    L = nd.lib()
+    L.cblas_dgemv.restype = None
+    L.cblas_dgemv.argtypes = [C.c_int] * 4 + [C.c_double, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_double, C.c_void_p, C.c_int]
+    L.cblas_sgemv.restype = None
+    L.cblas_sgemv.argtypes = [C.c_int] * 4 + [C.c_float, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_float, C.c_void_p, C.c_int]
+    rng = np.random.default_rng(4)
+    m, n = 37, 53
+    a = rng.standard_normal((m, n + 2))            # row-major, lda = n + 2
+    x, y = rng.standard_normal(2 * n), rng.standard_normal(m)
+    y0 = y.copy()
+    L.cblas_dgemv(101, 111, m, n, -2.3, a.ctypes.data, n + 2, x.ctypes.data, 2, 0.5, y.ctypes.data, 1)
+    np.testing.assert_allclose(y, -2.3 * a[:, :n] @ x[::2] + 0.5 * y0, rtol=1e-12)
+    xt, yt = rng.standard_normal(m), rng.standard_normal(2 * n)
+    yt0 = yt.copy()
+    L.cblas_dgemv(101, 112, m, n, 1.0, a.ctypes.data, n + 2, xt.ctypes.data, 1, 1.0, yt.ctypes.data, -2)   # y += A^T x, y reversed
+    np.testing.assert_allclose(yt[::2][::-1], a[:, :n].T @ xt + yt0[::2][::-1], rtol=1e-12)
+    assert np.array_equal(yt[1::2], yt0[1::2])      # gaps untouched
+    af = np.asfortranarray(rng.standard_normal((m, n)).astype(np.float32))
+    xs, ys = rng.standard_normal(n).astype(np.float32), np.zeros(m, np.float32)
+    L.cblas_sgemv(102, 111, m, n, 1.0, af.ctypes.data, m, xs.ctypes.data, 1, 0.0, ys.ctypes.data, 1)
+    np.testing.assert_allclose(ys, af.astype(np.float64) @ xs.astype(np.float64), rtol=2e-5, atol=1e-5)
+
+
+def test_large_gemv_both_layouts(nd):
+    rng = np.random.default_rng(5)
+    for dtype, tol in ((np.float32, 2e-5), (np.float64, 1e-12)):
+        a = rng.standard_normal((5000, 3000)).astype(dtype)
+        x = rng.standard_normal(3000).astype(dtype)
+        ref = a.astype(np.float64) @ x.astype(np.float64)
+        for arr in (a, np.asfortranarray(a)):
+            y = nd.Array.from_numpy(arr).dot(nd.Array.from_numpy(x)).to_numpy()
+            assert np.abs(y - ref).max() / np.abs(ref).max() < tol * math.sqrt(3000) / 8

@@ -219,3 +219,60 @@ def test_prefer_f_matches_oracle():
     for ins in cases:
         views = (View * len(ins))(*[mk(orc.view(x).ptr, x.dtype, x.shape, [s // x.itemsize for s in x.strides]) for x in ins])
         assert bool(nd.lib().ndb_zip_prefer_f(len(ins), views)) == orc.zip_prefer_f(ins)
+
+
+def test_merge_axes_golden():  # tests/array.rs:780-868
+    L = nd.lib()
+
+    def sliced(shape, strides, specs):
+        v = mk(1 << 20, np.int32, shape, strides)
+        for ax, sp in enumerate(specs):
+            if sp is not None:
+                s, e, st = sp
+                assert L.ndb_view_slice_axis(C.byref(v), ax, s, 0 if e is None else e, 0 if e is None else 1, st) == 0
+        return v
+
+    def check(shape, strides, specs, take, into, expect):
+        v = sliced(shape, strides, specs)
+        before = ([v.dim[i] for i in range(4)], [v.stride[i] for i in range(4)])
+        merged_len = v.dim[take] * v.dim[into]
+        r = L.ndb_view_merge_axes(C.byref(v), take, into)
+        assert bool(r) == expect, (specs, take, into)
+        if expect:
+            assert v.dim[take] == (0 if merged_len == 0 else 1) and v.dim[into] == merged_len
+        else:
+            assert ([v.dim[i] for i in range(4)], [v.stride[i] for i in range(4)]) == before
+
+    shp = (3, 4, 5, 4)
+    cs = c_strides(shp)
+    full = [None] * 4
+    merged_full = {(0, 1), (1, 2), (2, 3)}
+    for t in range(4):
+        for i in range(4):
+            check(shp, cs, full, t, i, (t, i) in merged_full)
+    last2 = [None, None, None, (0, None, 2)]
+    for (t, i, e) in [(0, 1, True), (1, 0, False), (1, 2, True), (2, 1, False), (2, 3, True), (3, 2, False)]:
+        check(shp, cs, last2, t, i, e)
+    last3 = [None, None, None, (0, 3, 1)]
+    for (t, i, e) in [(0, 1, True), (1, 0, False), (1, 2, True), (2, 1, False), (2, 3, False)]:
+        check(shp, cs, last3, t, i, e)
+    ax2 = [None, None, (0, None, 2), None]
+    for (t, i, e) in [(0, 1, True), (1, 0, False), (1, 2, False), (2, 3, False)]:
+        check(shp, cs, ax2, t, i, e)
+    ax1 = [None, (0, None, 2), None, None]
+    for (t, i, e) in [(0, 1, True), (1, 0, False), (1, 2, False), (2, 3, True), (3, 2, False)]:
+        check(shp, cs, ax1, t, i, e)
+    shp = (3, 1, 5, 1)
+    fs = f_strides(shp)
+    for (t, i) in [(0, 1), (0, 3), (1, 0), (1, 1), (1, 2), (1, 3), (2, 1), (2, 3), (3, 0), (3, 1), (3, 2), (3, 3)]:
+        check(shp, fs, ax2, t, i, True)
+    shp = (3, 0, 5, 1)
+    for (t, i) in [(0, 1), (1, 1), (2, 1), (3, 1), (1, 0), (1, 2), (1, 3)]:
+        check(shp, [0, 0, 0, 0], ax2, t, i, True)
+
+
+def test_collapse_axis():
+    v = mk(1000, np.float64, (3, 4), (4, 1))
+    assert nd.lib().ndb_view_collapse_axis(C.byref(v), 0, 2) == 0
+    assert (v.ptr, v.dim[0], v.dim[1]) == (1000 + 2 * 4 * 8, 1, 4)
+    assert nd.lib().ndb_view_collapse_axis(C.byref(v), 1, 4) == _ffi.ERR_OOB

@@ -225,3 +225,27 @@ def test_config3_full_size(nd):
     v0, v1 = f.var_axis(Axis(0), 1.0).to_numpy(), f.var_axis(Axis(1), 1.0).to_numpy()
     assert np.max(np.abs(v0[:64] - hf[:, :64].var(axis=0, ddof=1))) <= tol
     assert np.max(np.abs(v1[:64] - hf[:64].var(axis=1, ddof=1))) <= tol
+
+
+def test_var_std_whole_array(nd, oracle):  # tests/numeric.rs:149-233
+    from ndarray_b200 import Array
+    a = Array.from_numpy(np.array([1., -4.32, 1.14, 0.32]))
+    assert abs(a.var(0.) - 5.049875) < 1e-8
+    assert abs(a.std(0.) - 2.24719) < 1e-5
+    t = Array.from_numpy(np.array([1., 2., 3.]))
+    for bad in (-1., 4.):
+        with pytest.raises(nd.NdbError, match="ddof"):
+            t.var(bad)
+        with pytest.raises(nd.NdbError, match="ddof"):
+            t.std(bad)
+    assert math.isnan(Array.zeros((2, 3), np.float64).var(float("nan")))
+    assert math.isnan(Array.zeros(0, np.float64).var(0.0)) and math.isnan(Array.zeros(0, np.float64).std(0.0))
+    rng = np.random.default_rng(12)
+    for dtype, tol in ((np.float32, 1e-5), (np.float64, 1e-12)):
+        h = (rng.standard_normal((300, 257)) * 2 + 5).astype(dtype)
+        for fn in (lambda x: x, lambda x: x.T, lambda x: x[::-1, ::2]):
+            m = Mirror(nd, h)
+            hv, dv = m.view(fn)
+            want = float(hv.astype(np.float64).var(ddof=1))
+            assert abs(dv.var(1.0) - want) <= tol * math.sqrt(hv.size) * want
+            assert abs(dv.std(1.0) - math.sqrt(want)) <= tol * math.sqrt(hv.size) * math.sqrt(want)

@@ -300,3 +300,29 @@ def test_config2_full_size_properties(nd):
     Zip.from_(out).and_(x).and_broadcast(row).for_each("a=b*c")
     for i in (0, 300, 511):
         assert np.array_equal(out.index_axis(0, i).to_numpy(), xh[i] * rowh[None, :])
+
+
+def test_zip_all_any_fold(nd):  # tests/azip.rs:460-478
+    from ndarray_b200 import Array, Zip, Op
+    a = Array.zeros(62, np.float32)
+    b = Array.ones(62, np.float32)
+    ch = np.ones(62, np.float32)
+    ch[5] = 0.0
+    c = Array.from_numpy(ch)
+    one = Array.from_elem((), 1.0, np.float32).broadcast(62)
+    s_ab = Zip.from_(a).and_(b).map_collect(Op.ADD)
+    s_ac = Zip.from_(a).and_(c).map_collect(Op.ADD)
+    assert Zip.from_(s_ab).and_(one).all(Op.EQ)            # all(|x, y| x + y == 1.0)
+    assert not Zip.from_(a).and_(b).all(Op.EQ)              # all(|x, y| x == y)
+    assert not Zip.from_(s_ac).and_(one).all(Op.EQ)
+    assert Zip.from_(s_ac).and_(one).any(Op.NE) and not Zip.from_(s_ab).and_(one).any(Op.NE)
+    e0, e1 = Array.zeros(0, np.float32), Array.ones(0, np.float32)
+    assert Zip.from_(e0).and_(e1).all(Op.EQ) and Zip.from_(e0).and_(e1).all(Op.NE)   # vacuously true
+    assert not Zip.from_(e0).and_(e1).any(Op.EQ)
+    x = np.arange(1000, dtype=np.int64)
+    y = (x * 3 - 7).astype(np.int64)
+    assert Zip.from_(Array.from_numpy(x)).and_(Array.from_numpy(y)).fold_sum(Op.MUL) == int((x * y).sum())
+    with pytest.raises(nd.NdbError):
+        Zip.from_(a).and_(b).all(Op.ADD)
+    with pytest.raises(nd.ShapeError):
+        Zip([a, Array.zeros(61, np.float32)]).all(Op.EQ)
