@@ -15,7 +15,11 @@
 //
 // Reference semantics: src/linalg/impl_linalg.rs:633-643 (general_mat_mul), :512-546 (dgemm call with
 // arbitrary strides).  Layouts outside the fast path's rules fall back to gemm.cu's generic kernel.
+#include <cstdlib>
+
 #include "gemm.h"
+
+extern "C" int ndb_zip(ndb_ctx *ctx, int op, const void *scalars, int n_parts, const ndb_view *parts);
 
 namespace ndb {
 
@@ -220,30 +224,33 @@ Operand classify(const char *ptr, int64_t rows, int64_t cols, int64_t rs, int64_
 
 bool gemm_f64_eligible(const GemmArgs &g)
 {
+    if (getenv("NDB_GEMM_F64_GENERIC")) return false;
     if (g.m < 64 || g.n < 64 || g.k < 16) return false;  // small problems: the generic kernel launches less
     if (g.m > INT32_MAX / 2 || g.n > INT32_MAX / 2) return false;
+    return true;
+}
+
+namespace {
+
+ndb_view dview2(const void *ptr, int64_t d0, int64_t d1, int64_t s0, int64_t s1)
+{
+    ndb_view v;
+    memset(&v, 0, sizeof(v));
+    v.ptr = const_cast<void *>(ptr);
+    v.ndim = 2;
+    v.dtype = NDB_F64;
+    v.dim[0] = d0;
+    v.dim[1] = d1;
+    v.stride[0] = s0;
+    v.stride[1] = s1;
+    return v;
+}
+
+int launch_dense(ndb_ctx *ctx, const GemmArgs &g, double alpha, double beta)
+{
     const Operand a = classify(g.a, g.m, g.k, g.rsa, g.csa);
     const Operand b = classify(g.b, g.k, g.n, g.rsb, g.csb);
     const Operand c = classify(g.c, g.m, g.n, g.rsc, g.csc);
-    return a.ok && b.ok && c.ok;
-}
-
-int gemm_f64_launch(ndb_ctx *ctx, const GemmArgs &g0, double alpha, double beta)
-{
-    GemmArgs g = g0;
-    Operand c = classify(g.c, g.m, g.n, g.rsc, g.csc);
-    if (!c.unit_inner) {
-        // column-major C: compute C^T = B^T A^T (swap operands and their roles)
-        GemmArgs t = g;
-        t.a = g.b; t.rsa = g.csb; t.csa = g.rsb;
-        t.b = g.a; t.rsb = g.csa; t.csb = g.rsa;
-        t.rsc = g.csc; t.csc = g.rsc;
-        t.m = g.n; t.n = g.m;
-        g = t;
-        c = classify(g.c, g.m, g.n, g.rsc, g.csc);
-    }
-    const Operand a = classify(g.a, g.m, g.k, g.rsa, g.csa);
-    const Operand b = classify(g.b, g.k, g.n, g.rsb, g.csb);
     if (!a.ok || !b.ok || !c.ok || !c.unit_inner) {
         set_error("gemm_f64: operand layout outside the tensor-core path");
         return NDB_ERR_INCOMPATIBLE_LAYOUT;
@@ -272,6 +279,63 @@ int gemm_f64_launch(ndb_ctx *ctx, const GemmArgs &g0, double alpha, double beta)
     else gemm_f64_dmma<false, false><<<blocks, THREADS, SMEM_BYTES, ctx->stream>>>(p);
     NDB_CHECK_LAUNCH();
     return NDB_OK;
+}
+
+}  // namespace
+
+// Any signed strides are accepted (like matrixmultiply::dgemm, impl_linalg.rs:531-546): an operand that is not a
+// dense, aligned C- or F-order matrix (stride-2 views, reversed axes, broadcasts, odd leading dimensions) is first
+// packed into a dense row-major scratch array by the Zip engine; a C outside those rules is computed in scratch
+// (pre-loaded with C when beta != 0) and scattered back.
+int gemm_f64_launch(ndb_ctx *ctx, const GemmArgs &g0, double alpha, double beta)
+{
+    GemmArgs g = g0;
+    if (llabs(g.rsc) < llabs(g.csc)) {
+        // column-major C: compute C^T = B^T A^T (swap operands and their roles)
+        GemmArgs t = g;
+        t.a = g.b; t.rsa = g.csb; t.csa = g.rsb;
+        t.b = g.a; t.rsb = g.csa; t.csb = g.rsa;
+        t.rsc = g.csc; t.csc = g.rsc;
+        t.m = g.n; t.n = g.m;
+        g = t;
+    }
+    const bool a_ok = classify(g.a, g.m, g.k, g.rsa, g.csa).ok;
+    const bool b_ok = classify(g.b, g.k, g.n, g.rsb, g.csb).ok;
+    const Operand c_cls = classify(g.c, g.m, g.n, g.rsc, g.csc);
+    const bool c_ok = c_cls.ok && c_cls.unit_inner;
+    const int64_t kp = (g.k + 1) & ~(int64_t)1, np = (g.n + 1) & ~(int64_t)1;
+    const size_t need = (a_ok ? 0 : (size_t)g.m * kp) + (b_ok ? 0 : (size_t)g.k * np) + (c_ok ? 0 : (size_t)g.m * np);
+    double *ws = nullptr;
+    if (need) NDB_CUDA(cudaMallocAsync((void **)&ws, need * sizeof(double), ctx->stream));
+    double *cur = ws;
+    int st = NDB_OK;
+    GemmArgs d = g;
+    if (!a_ok) {
+        ndb_view parts[2] = {dview2(cur, g.m, g.k, kp, 1), dview2(g.a, g.m, g.k, g.rsa, g.csa)};
+        st = ndb_zip(ctx, NDB_OP_COPY, nullptr, 2, parts);
+        d.a = (const char *)cur; d.rsa = kp; d.csa = 1;
+        cur += (size_t)g.m * kp;
+    }
+    if (st == NDB_OK && !b_ok) {
+        ndb_view parts[2] = {dview2(cur, g.k, g.n, np, 1), dview2(g.b, g.k, g.n, g.rsb, g.csb)};
+        st = ndb_zip(ctx, NDB_OP_COPY, nullptr, 2, parts);
+        d.b = (const char *)cur; d.rsb = np; d.csb = 1;
+        cur += (size_t)g.k * np;
+    }
+    if (st == NDB_OK && !c_ok) {
+        if (beta != 0.0) {
+            ndb_view parts[2] = {dview2(cur, g.m, g.n, np, 1), dview2(g.c, g.m, g.n, g.rsc, g.csc)};
+            st = ndb_zip(ctx, NDB_OP_COPY, nullptr, 2, parts);
+        }
+        d.c = (char *)cur; d.rsc = np; d.csc = 1;
+    }
+    if (st == NDB_OK) st = launch_dense(ctx, d, alpha, beta);
+    if (st == NDB_OK && !c_ok) {
+        ndb_view parts[2] = {dview2(g.c, g.m, g.n, g.rsc, g.csc), dview2(d.c, g.m, g.n, np, 1)};
+        st = ndb_zip(ctx, NDB_OP_COPY, nullptr, 2, parts);
+    }
+    if (ws) cudaFreeAsync(ws, ctx->stream);
+    return st;
 }
 
 }  // namespace ndb

@@ -231,3 +231,34 @@ def test_large_gemv_both_layouts(nd):
         for arr in (a, np.asfortranarray(a)):
             y = nd.Array.from_numpy(arr).dot(nd.Array.from_numpy(x)).to_numpy()
             assert np.abs(y - ref).max() / np.abs(ref).max() < tol * math.sqrt(3000) / 8
+
+
+@pytest.mark.parametrize("dtype,tol", [(np.float32, 1e-5), (np.float64, 1e-13)])
+def test_strided_operands_take_the_tensor_path(nd, oracle, dtype, tol):
+    """Stride-2 / reversed / broadcast operands and a strided, reversed C at a size the tensor-core kernels accept
+    (they pack such operands through the Zip engine): values vs numpy float64, and untouched gaps in C."""
+    rng = np.random.default_rng(17)
+    m, k, n = 200, 136, 264
+    alpha, beta = -2.3, math.pi
+    for (sa, sb, sc) in [((2, -1), (-2, 2), (-1, 2)), ((-2, 2), (1, -1), (2, -2)), ((1, 1), (2, 1), (1, -1))]:
+        ma = Mirror(nd, rng.standard_normal((m * abs(sa[0]), k * abs(sa[1]))).astype(dtype))
+        mb = Mirror(nd, rng.standard_normal((k * abs(sb[0]), n * abs(sb[1]))).astype(dtype))
+        mc = Mirror(nd, rng.standard_normal((m * abs(sc[0]), n * abs(sc[1]))).astype(dtype))
+        c0 = mc.host.copy()
+        ha, da = ma.view(lambda x: nd_slice_np(x, *sa))
+        hb, db = mb.view(lambda x: nd_slice_np(x, *sb))
+        hc, dc = mc.view(lambda x: nd_slice_np(x, *sc))
+        want = alpha * (ha.astype(np.float64) @ hb.astype(np.float64)) + beta * hc.astype(np.float64)
+        nd.general_mat_mul(alpha, da, db, beta, dc)
+        got_full = mc.download()
+        got = nd_slice_np(got_full, *sc)
+        assert rel_norm(got, want) < tol * math.sqrt(k), (sa, sb, sc)
+        mask = np.ones_like(c0, dtype=bool)
+        nd_slice_np(mask, *sc)[...] = False
+        assert np.array_equal(got_full[mask], c0[mask]), "elements outside the C view were modified"
+    # broadcast B (a row repeated): tests/oper.rs:427-445
+    a = rng.standard_normal((m, k)).astype(dtype)
+    row = rng.standard_normal(n).astype(dtype)
+    bb = nd.Array.from_numpy(row).broadcast((k, n))
+    c = nd.Array.from_numpy(a).dot(bb).to_numpy()
+    assert rel_norm(c, a.astype(np.float64) @ np.broadcast_to(row.astype(np.float64), (k, n))) < tol * math.sqrt(k)
