@@ -114,8 +114,23 @@ typedef enum {
     NDB_OP_LE = 28,
     NDB_OP_GT = 29,
     NDB_OP_GE = 30,
+    /* float maps of src/numeric/impl_float_maths.rs:80-160 (mapv with a libm function; floats only).  The function
+     * is a RUN-TIME selector so one kernel serves all of them: s0 = (ndb_math_fn) as the element type, s1 = parameter
+     * (powi exponent, powf exponent, log base, abs_sub / hypot other operand).  Exactly-rounded functions (floor,
+     * ceil, round, trunc, fract, signum, recip, pow2, is_nan, is_infinite) are bit-exact; transcendental ones are
+     * CUDA libm (<= 2 ulp) and compared to the CPU within a tolerance. */
+    NDB_OP_MATH = 31,
+    NDB_OP_CLAMP = 32, /* out = clamp(in0, s0, s1)  (impl_float_maths.rs clamp; NaN stays NaN) */
     NDB_OP__COUNT
 } ndb_op;
+
+typedef enum {
+    NDB_FN_FLOOR = 0, NDB_FN_CEIL, NDB_FN_ROUND, NDB_FN_TRUNC, NDB_FN_FRACT, NDB_FN_SIGNUM, NDB_FN_RECIP, NDB_FN_EXP,
+    NDB_FN_EXP2, NDB_FN_EXP_M1, NDB_FN_LN, NDB_FN_LOG2, NDB_FN_LOG10, NDB_FN_LN_1P, NDB_FN_CBRT, NDB_FN_SIN, NDB_FN_COS,
+    NDB_FN_TAN, NDB_FN_ASIN, NDB_FN_ACOS, NDB_FN_ATAN, NDB_FN_SINH, NDB_FN_COSH, NDB_FN_TANH, NDB_FN_ASINH, NDB_FN_ACOSH,
+    NDB_FN_ATANH, NDB_FN_TO_DEGREES, NDB_FN_TO_RADIANS, NDB_FN_POW2, NDB_FN_POWI, NDB_FN_POWF, NDB_FN_LOG, NDB_FN_ABS_SUB,
+    NDB_FN_HYPOT, NDB_FN_IS_NAN, NDB_FN_IS_INFINITE, NDB_FN__COUNT
+} ndb_math_fn;
 
 /* ---- axis-reduction vocabulary -------------------------------------------
  * sum_axis / product_axis / mean_axis / var_axis / std_axis

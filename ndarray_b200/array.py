@@ -28,7 +28,13 @@ CODE_DTYPE = {v: k for k, v in DTYPE_CODE.items()}
 
 class Op:
     COPY, FILL, ADD, SUB, MUL, DIV, REM, MUL_ADD, ADD_S, SUB_S, MUL_S, DIV_S, REM_S, RSUB_S, RDIV_S, NEG, AXPY, \
-        ADD_N, ABS, SQRT, MIN, MAX, SCALE_ADD, TF32_HI, TF32_LO, EQ, NE, LT, LE, GT, GE = range(31)
+        ADD_N, ABS, SQRT, MIN, MAX, SCALE_ADD, TF32_HI, TF32_LO, EQ, NE, LT, LE, GT, GE, MATH, CLAMP = range(33)
+
+
+MATH_FNS = ["floor", "ceil", "round", "trunc", "fract", "signum", "recip", "exp", "exp2", "exp_m1", "ln", "log2", "log10",
+            "ln_1p", "cbrt", "sin", "cos", "tan", "asin", "acos", "atan", "sinh", "cosh", "tanh", "asinh", "acosh", "atanh",
+            "to_degrees", "to_radians", "pow2", "powi", "powf", "log", "abs_sub", "hypot", "is_nan", "is_infinite"]
+MATH_FN = {name: i for i, name in enumerate(MATH_FNS)}
 
 
 class Red:
@@ -486,6 +492,31 @@ class Array:
     def mapv_inplace(self, op: int, scalars=()) -> None:
         _zip_call(self.ctx, op, self, [self], scalars)
 
+    # -- float maths maps (src/numeric/impl_float_maths.rs:80-160): `a.exp()`, `a.powi(3)`, `a.clamp(lo, hi)`, ...
+    def map_math(self, fn: str, param=0.0) -> "Array":
+        return self.mapv(Op.MATH, [MATH_FN[fn], param])
+
+    def abs(self) -> "Array":
+        return self.mapv(Op.ABS)
+
+    def sqrt(self) -> "Array":
+        return self.mapv(Op.SQRT)
+
+    def clamp(self, lo, hi) -> "Array":
+        return self.mapv(Op.CLAMP, [lo, hi])
+
+    def is_all_nan(self) -> bool:
+        return self.len() == 0 or self.map_math("is_nan")._reduce_all(Red.MIN) != 0
+
+    def is_any_nan(self) -> bool:
+        return self.len() > 0 and self.map_math("is_nan")._reduce_all(Red.MAX) != 0
+
+    def is_all_infinite(self) -> bool:
+        return self.len() == 0 or self.map_math("is_infinite")._reduce_all(Red.MIN) != 0
+
+    def is_any_infinite(self) -> bool:
+        return self.len() > 0 and self.map_math("is_infinite")._reduce_all(Red.MAX) != 0
+
     def _binary(self, other, op, op_s, rop_s=None, reflected=False):
         if isinstance(other, Array):
             lhs, rhs = (other, self) if reflected else (self, other)
@@ -777,3 +808,14 @@ def azip(closure, *producers, scalars=()):
 
 
 par_azip = azip  # src/parallel/zipmacro.rs:53
+
+
+def _install_math_methods():
+    unary = [f for f in MATH_FNS if f not in ("powi", "powf", "log", "abs_sub", "hypot")]
+    for name in unary:
+        setattr(Array, name, (lambda n: lambda self: self.map_math(n))(name))
+    for name in ("powi", "powf", "log", "abs_sub", "hypot"):
+        setattr(Array, name, (lambda n: lambda self, p: self.map_math(n, p))(name))
+
+
+_install_math_methods()

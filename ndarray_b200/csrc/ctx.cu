@@ -34,6 +34,8 @@ int op_arity(int op)
     case NDB_OP_ABS:
     case NDB_OP_TF32_HI:
     case NDB_OP_TF32_LO:
+    case NDB_OP_MATH:
+    case NDB_OP_CLAMP:
     case NDB_OP_SQRT: return 1;
     case NDB_OP_ADD:
     case NDB_OP_SUB:
@@ -68,6 +70,8 @@ int op_scalars(int op)
     case NDB_OP_RSUB_S:
     case NDB_OP_RDIV_S:
     case NDB_OP_AXPY: return 1;
+    case NDB_OP_MATH:
+    case NDB_OP_CLAMP:
     case NDB_OP_SCALE_ADD: return 2;
     default: return 0;
     }

@@ -110,6 +110,68 @@ __device__ __forceinline__ T w_max(T a, T b)
     else return b > a ? b : a;
 }
 
+// The float maps of src/numeric/impl_float_maths.rs, selected at run time (uniform across the launch).
+template <typename T>
+__device__ __forceinline__ T math_fn(int fn, T x, T p)
+{
+    if constexpr (std::is_floating_point<T>::value) {
+        constexpr bool F = std::is_same<T, float>::value;
+        switch (fn) {
+        case NDB_FN_FLOOR: return F ? (T)floorf((float)x) : (T)floor((double)x);
+        case NDB_FN_CEIL: return F ? (T)ceilf((float)x) : (T)ceil((double)x);
+        case NDB_FN_ROUND: return F ? (T)roundf((float)x) : (T)round((double)x);  // half away from zero, like Rust
+        case NDB_FN_TRUNC: return F ? (T)truncf((float)x) : (T)trunc((double)x);
+        case NDB_FN_FRACT: return x - (F ? (T)truncf((float)x) : (T)trunc((double)x));
+        case NDB_FN_SIGNUM: return x != x ? x : (T)copysign(1.0, (double)x);     // +-0 -> +-1, NaN -> NaN
+        case NDB_FN_RECIP: return T(1) / x;
+        case NDB_FN_EXP: return F ? (T)expf((float)x) : (T)exp((double)x);
+        case NDB_FN_EXP2: return F ? (T)exp2f((float)x) : (T)exp2((double)x);
+        case NDB_FN_EXP_M1: return F ? (T)expm1f((float)x) : (T)expm1((double)x);
+        case NDB_FN_LN: return F ? (T)logf((float)x) : (T)log((double)x);
+        case NDB_FN_LOG2: return F ? (T)log2f((float)x) : (T)log2((double)x);
+        case NDB_FN_LOG10: return F ? (T)log10f((float)x) : (T)log10((double)x);
+        case NDB_FN_LN_1P: return F ? (T)log1pf((float)x) : (T)log1p((double)x);
+        case NDB_FN_CBRT: return F ? (T)cbrtf((float)x) : (T)cbrt((double)x);
+        case NDB_FN_SIN: return F ? (T)sinf((float)x) : (T)sin((double)x);
+        case NDB_FN_COS: return F ? (T)cosf((float)x) : (T)cos((double)x);
+        case NDB_FN_TAN: return F ? (T)tanf((float)x) : (T)tan((double)x);
+        case NDB_FN_ASIN: return F ? (T)asinf((float)x) : (T)asin((double)x);
+        case NDB_FN_ACOS: return F ? (T)acosf((float)x) : (T)acos((double)x);
+        case NDB_FN_ATAN: return F ? (T)atanf((float)x) : (T)atan((double)x);
+        case NDB_FN_SINH: return F ? (T)sinhf((float)x) : (T)sinh((double)x);
+        case NDB_FN_COSH: return F ? (T)coshf((float)x) : (T)cosh((double)x);
+        case NDB_FN_TANH: return F ? (T)tanhf((float)x) : (T)tanh((double)x);
+        case NDB_FN_ASINH: return F ? (T)asinhf((float)x) : (T)asinh((double)x);
+        case NDB_FN_ACOSH: return F ? (T)acoshf((float)x) : (T)acosh((double)x);
+        case NDB_FN_ATANH: return F ? (T)atanhf((float)x) : (T)atanh((double)x);
+        case NDB_FN_TO_DEGREES: return x * (F ? (T)57.2957795130823208767981548141051703f : (T)(180.0 / 3.14159265358979323846264338327950288));
+        case NDB_FN_TO_RADIANS: return x * (F ? (T)(3.14159265358979323846264338327950288f / 180.0f) : (T)(3.14159265358979323846264338327950288 / 180.0));
+        case NDB_FN_POW2: return x * x;
+        case NDB_FN_POWI: {  // compiler-rt's __powisf2 / __powidf2, which is what Rust's powi lowers to
+            int b = (int)p;
+            const bool recip = b < 0;
+            T a = x, r = T(1);
+            for (;;) {
+                if (b & 1) r *= a;
+                b /= 2;
+                if (b == 0) break;
+                a *= a;
+            }
+            return recip ? T(1) / r : r;
+        }
+        case NDB_FN_POWF: return F ? (T)powf((float)x, (float)p) : (T)pow((double)x, (double)p);
+        case NDB_FN_LOG: return F ? (T)(logf((float)x) / logf((float)p)) : (T)(log((double)x) / log((double)p));
+        case NDB_FN_ABS_SUB: return F ? (T)fdimf((float)x, (float)p) : (T)fdim((double)x, (double)p);
+        case NDB_FN_HYPOT: return F ? (T)hypotf((float)x, (float)p) : (T)hypot((double)x, (double)p);
+        case NDB_FN_IS_NAN: return x != x ? T(1) : T(0);
+        case NDB_FN_IS_INFINITE: return (x == x && (x - x) != (x - x)) ? T(1) : T(0);
+        default: return x;
+        }
+    } else {
+        return x;
+    }
+}
+
 // The op vocabulary (ndb_op).  `x` holds the NIN loaded inputs.
 template <typename T, int OP, int NIN>
 __device__ __forceinline__ T apply_op(const T *x, T s0, T s1, int *flag)
@@ -150,6 +212,8 @@ __device__ __forceinline__ T apply_op(const T *x, T s0, T s1, int *flag)
     else if constexpr (OP == NDB_OP_LE) return x[0] <= x[1] ? T(1) : T(0);
     else if constexpr (OP == NDB_OP_GT) return x[0] > x[1] ? T(1) : T(0);
     else if constexpr (OP == NDB_OP_GE) return x[0] >= x[1] ? T(1) : T(0);
+    else if constexpr (OP == NDB_OP_MATH) return math_fn<T>((int)s0, x[0], s1);
+    else if constexpr (OP == NDB_OP_CLAMP) return x[0] != x[0] ? x[0] : (x[0] < s0 ? s0 : (x[0] > s1 ? s1 : x[0]));
     else if constexpr (OP == NDB_OP_TF32_HI || OP == NDB_OP_TF32_LO) {
         if constexpr (std::is_same<T, float>::value) {
             uint32_t hi;
@@ -723,6 +787,8 @@ int zip_dispatch_typed(ndb_ctx *ctx, const ZipPlan &z, const void *scalars)
         NDB_ZIP_CASE(NDB_OP_LE, 2)
         NDB_ZIP_CASE(NDB_OP_GT, 2)
         NDB_ZIP_CASE(NDB_OP_GE, 2)
+        NDB_ZIP_CASE(NDB_OP_MATH, 1)
+        NDB_ZIP_CASE(NDB_OP_CLAMP, 1)
 #undef NDB_ZIP_CASE
     case NDB_OP_ADD_N:
         switch (nin) {

@@ -75,8 +75,8 @@ int make_zip_plan(int op, int n_parts, const ndb_view *parts, ZipPlan *zp)
             return NDB_ERR_INCOMPATIBLE_SHAPE;
         }
     }
-    if ((op == NDB_OP_SQRT) && !dtype_is_float(o.dtype)) {
-        set_error("Zip: sqrt needs a float element type");
+    if ((op == NDB_OP_SQRT || op == NDB_OP_MATH) && !dtype_is_float(o.dtype)) {
+        set_error("Zip: sqrt and the float maths maps need a float element type");
         return NDB_ERR_UNSUPPORTED;
     }
     if ((op == NDB_OP_TF32_HI || op == NDB_OP_TF32_LO) && o.dtype != NDB_F32) {

@@ -15,6 +15,7 @@
 // Build: g++ -O2 -ffp-contract=off -fopenmp -shared -fPIC (see oracle/Makefile).  -ffp-contract=off
 // matters: Rust never fuses a*b+c.
 #include <math.h>
+#include <cmath>
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
@@ -46,7 +47,12 @@ enum { F32 = 0, F64 = 1, I32 = 2, I64 = 3 };
 enum {
     OP_COPY, OP_FILL, OP_ADD, OP_SUB, OP_MUL, OP_DIV, OP_REM, OP_MUL_ADD, OP_ADD_S, OP_SUB_S, OP_MUL_S, OP_DIV_S,
     OP_REM_S, OP_RSUB_S, OP_RDIV_S, OP_NEG, OP_AXPY, OP_ADD_N, OP_ABS, OP_SQRT, OP_MIN, OP_MAX, OP_SCALE_ADD,
-    OP_TF32_HI, OP_TF32_LO, OP_EQ, OP_NE, OP_LT, OP_LE, OP_GT, OP_GE
+    OP_TF32_HI, OP_TF32_LO, OP_EQ, OP_NE, OP_LT, OP_LE, OP_GT, OP_GE, OP_MATH, OP_CLAMP
+};
+enum {
+    FN_FLOOR, FN_CEIL, FN_ROUND, FN_TRUNC, FN_FRACT, FN_SIGNUM, FN_RECIP, FN_EXP, FN_EXP2, FN_EXP_M1, FN_LN, FN_LOG2, FN_LOG10,
+    FN_LN_1P, FN_CBRT, FN_SIN, FN_COS, FN_TAN, FN_ASIN, FN_ACOS, FN_ATAN, FN_SINH, FN_COSH, FN_TANH, FN_ASINH, FN_ACOSH, FN_ATANH,
+    FN_TO_DEGREES, FN_TO_RADIANS, FN_POW2, FN_POWI, FN_POWF, FN_LOG, FN_ABS_SUB, FN_HYPOT, FN_IS_NAN, FN_IS_INFINITE
 };
 enum { RED_SUM, RED_PROD, RED_MIN, RED_MAX, RED_MEAN, RED_VAR, RED_STD };
 
@@ -325,6 +331,69 @@ static inline T wmax(T a, T b)
     else return b > a ? b : a;
 }
 
+// the float maps of src/numeric/impl_float_maths.rs:80-160 (each is `mapv(A::f)` on num_traits::Float, i.e. libm)
+template <typename T>
+static inline T math_fn(int fn, T x, T p)
+{
+    if constexpr (std::is_floating_point<T>::value) {
+        switch (fn) {
+        case FN_FLOOR: return std::floor(x);
+        case FN_CEIL: return std::ceil(x);
+        case FN_ROUND: return std::round(x);
+        case FN_TRUNC: return std::trunc(x);
+        case FN_FRACT: return x - std::trunc(x);
+        case FN_SIGNUM: return x != x ? x : (T)copysign(1.0, (double)x);
+        case FN_RECIP: return (T)1 / x;
+        case FN_EXP: return std::exp(x);
+        case FN_EXP2: return std::exp2(x);
+        case FN_EXP_M1: return std::expm1(x);
+        case FN_LN: return std::log(x);
+        case FN_LOG2: return std::log2(x);
+        case FN_LOG10: return std::log10(x);
+        case FN_LN_1P: return std::log1p(x);
+        case FN_CBRT: return std::cbrt(x);
+        case FN_SIN: return std::sin(x);
+        case FN_COS: return std::cos(x);
+        case FN_TAN: return std::tan(x);
+        case FN_ASIN: return std::asin(x);
+        case FN_ACOS: return std::acos(x);
+        case FN_ATAN: return std::atan(x);
+        case FN_SINH: return std::sinh(x);
+        case FN_COSH: return std::cosh(x);
+        case FN_TANH: return std::tanh(x);
+        case FN_ASINH: return std::asinh(x);
+        case FN_ACOSH: return std::acosh(x);
+        case FN_ATANH: return std::atanh(x);
+        case FN_TO_DEGREES:
+            return std::is_same<T, float>::value ? (T)((float)x * 57.2957795130823208767981548141051703f)
+                                                 : (T)((double)x * (180.0 / 3.14159265358979323846264338327950288));
+        case FN_TO_RADIANS:
+            return std::is_same<T, float>::value ? (T)((float)x * (3.14159265358979323846264338327950288f / 180.0f))
+                                                 : (T)((double)x * (3.14159265358979323846264338327950288 / 180.0));
+        case FN_POW2: return x * x;
+        case FN_POWI: {  // f32::powi -> llvm.powi -> compiler-rt __powisf2 / __powidf2
+            int b = (int)p;
+            const bool recip = b < 0;
+            T a = x, r = (T)1;
+            for (;;) {
+                if (b & 1) r *= a;
+                b /= 2;
+                if (b == 0) break;
+                a *= a;
+            }
+            return recip ? (T)1 / r : r;
+        }
+        case FN_POWF: return std::pow(x, p);
+        case FN_LOG: return std::log(x) / std::log(p);
+        case FN_ABS_SUB: return std::fdim(x, p);
+        case FN_HYPOT: return std::hypot(x, p);
+        case FN_IS_NAN: return x != x ? (T)1 : (T)0;
+        case FN_IS_INFINITE: return std::isinf(x) ? (T)1 : (T)0;
+        }
+    }
+    return x;
+}
+
 template <typename T>
 static inline T apply(int op, int nin, const T *x, T s0, T s1, int *trap)
 {
@@ -367,6 +436,8 @@ static inline T apply(int op, int nin, const T *x, T s0, T s1, int *trap)
     case OP_LE: return x[0] <= x[1] ? (T)1 : (T)0;
     case OP_GT: return x[0] > x[1] ? (T)1 : (T)0;
     case OP_GE: return x[0] >= x[1] ? (T)1 : (T)0;
+    case OP_MATH: return math_fn<T>((int)s0, x[0], s1);
+    case OP_CLAMP: return x[0] != x[0] ? x[0] : (x[0] < s0 ? s0 : (x[0] > s1 ? s1 : x[0]));
     default: return x[0];
     }
 }
@@ -380,7 +451,7 @@ static void zip_serial(int op, const void *scalars, int n_parts, const orc_view 
     T s0 = 0, s1 = 0;
     if (scalars) {
         s0 = ((const T *)scalars)[0];
-        if (op == OP_SCALE_ADD) s1 = ((const T *)scalars)[1];
+        if (op == OP_SCALE_ADD || op == OP_MATH || op == OP_CLAMP) s1 = ((const T *)scalars)[1];
     }
     const orc_view &o = parts[0];
     const int nd = o.ndim;

@@ -326,3 +326,43 @@ def test_zip_all_any_fold(nd):  # tests/azip.rs:460-478
         Zip.from_(a).and_(b).all(Op.ADD)
     with pytest.raises(nd.ShapeError):
         Zip([a, Array.zeros(61, np.float32)]).all(Op.EQ)
+
+
+EXACT_FNS = ["floor", "ceil", "round", "trunc", "fract", "signum", "recip", "pow2", "powi", "is_nan", "is_infinite"]
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_float_maths_maps(nd, oracle, dtype):
+    """impl_float_maths.rs:80-160: exactly-rounded maps bit-exact, libm maps within a few ulp of the CPU libm."""
+    from ndarray_b200.array import MATH_FN, MATH_FNS
+    rng = np.random.default_rng(21)
+    base = rng.uniform(-3, 3, 5000).astype(dtype)
+    base[:8] = [0.0, -0.0, 0.5, -0.5, 1.5, 2.5, -2.5, 1.0]
+    special = np.concatenate([base, np.array([np.inf, -np.inf, np.nan], dtype)])
+    ulp = np.finfo(dtype).eps
+    domain = {"ln": np.abs(base) + 1e-3, "log2": np.abs(base) + 1e-3, "log10": np.abs(base) + 1e-3, "ln_1p": np.abs(base),
+              "asin": base / 3.01, "acos": base / 3.01, "acosh": np.abs(base) + 1.0, "atanh": base / 3.01,
+              "log": np.abs(base) + 1e-3, "powf": np.abs(base) + 1e-3, "cbrt": base}
+    param = {"powi": 3, "powf": 1.7, "log": 2.5, "abs_sub": 0.25, "hypot": 1.25}
+    for name in MATH_FNS:
+        x = special if name in EXACT_FNS else domain.get(name, base).astype(dtype)
+        want = np.zeros_like(x)
+        with np.errstate(all="ignore"):
+            assert oracle.zip_(31, want, [x], [MATH_FN[name], param.get(name, 0.0)]) == 0
+        dx = nd.Array.from_numpy(x)
+        got = (getattr(dx, name)(param[name]) if name in param else getattr(dx, name)()).to_numpy()
+        if name in EXACT_FNS:
+            assert_bit_equal(got, want, name)
+        else:
+            scale = np.maximum(np.abs(want), np.finfo(dtype).tiny)
+            rel = np.abs(got.astype(np.float64) - want.astype(np.float64)) / scale
+            assert np.nanmax(rel) <= 8 * ulp, (name, float(np.nanmax(rel)))
+    c = nd.Array.from_numpy(special).clamp(-1.0, 2.0).to_numpy()
+    wantc = np.zeros_like(special)
+    assert oracle.zip_(32, wantc, [special], [-1.0, 2.0]) == 0
+    assert_bit_equal(c, wantc, "clamp")
+    assert np.array_equal(np.isnan(wantc), np.isnan(special))
+    nanarr = nd.Array.from_numpy(np.array([np.nan, 1.0], dtype))
+    assert nanarr.is_any_nan() and not nanarr.is_all_nan() and not nanarr.is_any_infinite()
+    with pytest.raises(nd.NdbError):
+        nd.Array.from_numpy(np.arange(4, dtype=np.int32)).map_math("exp")
