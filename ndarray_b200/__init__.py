@@ -5,8 +5,8 @@ Importing this package does not need a GPU; creating a Context / Array does, and
 without one — there is no CPU fallback.
 """
 from ._ffi import NdbError, ShapeError, KERNEL_NAMES, lib  # noqa: F401
-from .array import (Array, Axis, Context, NewAxis, Op, Red, Slice, Zip, azip, default_context, par_azip, s_)  # noqa: F401
+from .array import (Array, Axis, Context, NewAxis, Op, Red, Slice, Zip, azip, default_context, indices, par_azip, s_)  # noqa: F401
 from .linalg import dot, general_mat_mul, general_mat_vec_mul  # noqa: F401
 
-__all__ = ["Array", "Axis", "Context", "NewAxis", "Op", "Red", "Slice", "Zip", "default_context", "s_", "azip", "par_azip", "dot",
+__all__ = ["Array", "Axis", "Context", "NewAxis", "Op", "Red", "Slice", "Zip", "default_context", "s_", "azip", "par_azip", "indices", "dot",
            "general_mat_mul", "general_mat_vec_mul", "NdbError", "ShapeError", "KERNEL_NAMES", "lib"]

@@ -634,6 +634,41 @@ class Array:
             _zip_call(self.ctx, Op.MIN if fold == "min" else Op.MAX, out, [ini, out])
         return out
 
+    def diff(self, n: int, axis) -> "Array":
+        """diff (src/numeric/impl_numeric.rs:495-532): n-th forward difference along `axis`, one Zip per order."""
+        axis = int(axis)
+        if n == 0:
+            return self.to_owned()
+        if not 0 <= axis < self.ndim:
+            raise _ffi.NdbError(_ffi.ERR_OOB, f"The array has only ndim {self.ndim}, but `axis` Axis({axis}) is given.")
+        if not n < self.shape[axis]:
+            raise _ffi.NdbError(_ffi.ERR_INVALID, f"The array must have length at least `n+1`=={n + 1} in the direction of "
+                                f"`axis`. It has length {self.shape[axis]}")
+        inp = self
+        for _ in range(n):
+            head = inp.slice_axis(axis, Slice(0, -1, 1))
+            tail = inp.slice_axis(axis, Slice(1, None, 1))
+            out = Array._alloc(head.shape, self.dtype, "C", self.ctx)
+            _zip_call(self.ctx, Op.SUB, out, [tail, head])
+            inp = out
+        return inp
+
+    def accumulate_axis_inplace(self, axis, op: int) -> None:
+        """accumulate_axis_inplace (src/impl_methods.rs:3243): a[i] = op(a[i-1], a[i]) along `axis`, in axis order —
+        one Zip over the two adjacent subviews per step, the same sequence of elementwise passes ndarray performs."""
+        axis = int(axis)
+        if not 0 <= axis < self.ndim:
+            raise _ffi.NdbError(_ffi.ERR_OOB, f"axis {axis} is out of bounds for array of dimension {self.ndim}")
+        for i in range(1, self.shape[axis]):
+            prev, cur = self.index_axis(axis, i - 1), self.index_axis(axis, i)
+            _zip_call(self.ctx, op, cur, [prev, cur])
+
+    def cumprod(self, axis) -> "Array":
+        """cumprod (src/numeric/impl_numeric.rs:125)."""
+        out = self.to_owned("C")
+        out.accumulate_axis_inplace(axis, Op.MUL)
+        return out
+
     def dot(self, rhs: "Array"):
         """Dot::dot (src/linalg/impl_linalg.rs:160-386): 1-d·1-d -> scalar, 2-d·2-d -> matrix, 2-d·1-d, 1-d·2-d."""
         from .linalg import dot as _dot
@@ -790,6 +825,15 @@ class Zip:
 
     par_fold_sum = fold_sum
 
+    @staticmethod
+    def indexed(p: "Array") -> "Zip":
+        """Zip::indexed (src/zip/mod.rs:237): the index along each axis rides along as extra producers (broadcast
+        aranges — the Indices producer of src/indexes.rs as stride-0/1 views), after `p`: parts = [p, i0, i1, ...]."""
+        z = Zip([p])
+        for ix in indices(p.shape, p.dtype, p.ctx):
+            z = z.and_(ix)
+        return z
+
     def plan(self, op: int = Op.ADD_N):
         """The kernel class the planner picks for (first producer written, rest read)."""
         n = len(self.parts)
@@ -797,6 +841,21 @@ class Zip:
         pl = _ffi.ZipPlan()
         check(lib().ndb_zip_plan(op, n, views, C.byref(pl)))
         return pl
+
+
+def indices(shape, dtype=np.int64, ctx=None) -> list:
+    """One producer per axis holding that axis' index, broadcast to `shape` (ndarray::indices, src/indexes.rs)."""
+    shape = _as_shape(shape)
+    out = []
+    for k, d in enumerate(shape):
+        ar = Array.from_numpy(np.arange(d, dtype=dtype), ctx)
+        v = View()
+        v.ptr, v.ndim, v.dtype = ar.v.ptr, len(shape), ar.v.dtype
+        for i, di in enumerate(shape):
+            v.dim[i] = di
+            v.stride[i] = 1 if (i == k and di > 1) else 0
+        out.append(ar._derive(v))
+    return out
 
 
 def azip(closure, *producers, scalars=()):

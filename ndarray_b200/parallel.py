@@ -98,6 +98,7 @@ def var_axis0(local: Array, ddof: float, dist=None, want_std: bool = False) -> A
             dist.all_gather_into_tensor(gm, _torch_view(mean))
             dist.all_gather_into_tensor(g2, _torch_view(m2))
             dist.all_gather_into_tensor(gc, cnt)
+        local.ctx.sync()  # the gathers ran on the context stream; the host reads the counts next
         counts = [int(x) for x in gc.tolist()]
         means = [Array.borrow(gm[r].data_ptr(), shape, local.dtype, ctx=local.ctx, owner=gm) for r in range(world)]
         m2s = [Array.borrow(g2[r].data_ptr(), shape, local.dtype, ctx=local.ctx, owner=g2) for r in range(world)]

@@ -249,3 +249,40 @@ def test_var_std_whole_array(nd, oracle):  # tests/numeric.rs:149-233
             want = float(hv.astype(np.float64).var(ddof=1))
             assert abs(dv.var(1.0) - want) <= tol * math.sqrt(hv.size) * want
             assert abs(dv.std(1.0) - math.sqrt(want)) <= tol * math.sqrt(hv.size) * math.sqrt(want)
+
+
+def test_diff_cumprod_indexed_golden(nd):
+    from ndarray_b200 import Array, Axis, Zip, Op
+    d = Array.from_numpy(np.array([1.0, 2.0, 4.0, 7.0]))                     # tests/numeric.rs:412-477
+    assert d.diff(1, Axis(0)).to_numpy().tolist() == [1.0, 2.0, 3.0]
+    assert d.diff(2, Axis(0)).to_numpy().tolist() == d.diff(1, Axis(0)).diff(1, Axis(0)).to_numpy().tolist()
+    assert d.diff(3, Axis(0)).to_numpy().tolist() == d.diff(1, Axis(0)).diff(1, Axis(0)).diff(1, Axis(0)).to_numpy().tolist() == [0.0]
+    d2 = Array.from_numpy(np.array([[1.0, 2.0, 4.0, 7.0], [1.0, 3.0, 6.0, 6.0], [1.5, 3.5, 5.5, 5.5]]))
+    assert d2.diff(1, Axis(0)).to_numpy().tolist() == [[0.0, 1.0, 2.0, -1.0], [0.5, 0.5, -0.5, -0.5]]
+    assert d2.diff(1, Axis(1)).to_numpy().tolist() == [[1.0, 2.0, 3.0], [2.0, 3.0, 0.0], [2.0, 2.0, 0.0]]
+    with pytest.raises(nd.NdbError):
+        d.diff(10, Axis(0))
+    with pytest.raises(nd.NdbError):
+        Array.from_numpy(np.array([1, 2, 4, 7])).diff(1, Axis(2))
+    a = Array.from_numpy(np.array([1, 2, 3, 4]))                             # tests/numeric.rs:78-137
+    assert a.cumprod(Axis(0)).to_numpy().tolist() == [1, 2, 6, 24]
+    a2 = Array.from_numpy(np.array([[1, 2], [3, 4]]))
+    assert a2.cumprod(Axis(0)).to_numpy().tolist() == [[1, 2], [3, 8]]
+    assert a2.cumprod(Axis(1)).to_numpy().tolist() == [[1, 2], [3, 12]]
+    a3 = Array.from_numpy(np.array([[[1, 2], [3, 4]], [[5, 6], [7, 8]]]))
+    assert a3.cumprod(Axis(0)).to_numpy().tolist() == [[[1, 2], [3, 4]], [[5, 12], [21, 32]]]
+    assert a3.cumprod(Axis(1)).to_numpy().tolist() == [[[1, 2], [3, 8]], [[5, 6], [35, 48]]]
+    assert a3.cumprod(Axis(2)).to_numpy().tolist() == [[[1, 2], [3, 12]], [[5, 30], [7, 56]]]
+    assert Array.zeros((0, 0), np.int32).cumprod(Axis(0)).shape == (0, 0)
+    assert Array.from_numpy(np.array([[5]])).cumprod(Axis(1)).to_numpy().tolist() == [[5]]
+    with pytest.raises(nd.NdbError, match="out of bounds"):
+        a2.cumprod(Axis(2))
+    # Zip::indexed (tests/azip.rs:320-457): a[i, j] = i * 10 + j built from the index producers
+    out = Array.zeros((5, 7), np.int64)
+    z = Zip.indexed(out)
+    assert len(z.parts) == 3
+    i, j = z.parts[1], z.parts[2]
+    ten = Array.from_elem((), 10, np.int64).broadcast((5, 7))
+    tmp = Zip.from_(i).and_(ten).map_collect(Op.MUL)
+    Zip.from_(out).and_(tmp).and_(j).for_each("a=b+c")
+    assert out.to_numpy().tolist() == [[r * 10 + c for c in range(7)] for r in range(5)]
