@@ -59,13 +59,23 @@ def run_extras(nd, ctx, torch, dist, rank, world, local, peak_gbs):
 
     med, best = _time(ctx, c1_zip, 40, 4)
     rec("C1_zip_a=b*c+a_f32_4096^2", 4 * 4 * n * n, med, best)
+    import ctypes as C
+    from ndarray_b200._ffi import lib, check
+    o1 = Array.zeros((n,), np.float32, ctx=ctx)
     for ax in (0, 1):
         def c1_sum(ax=ax):
             a = sets[it[0] % 4][0]
             it[0] += 1
             a.sum_axis(Axis(ax))
+
+        def c1_sum_into(ax=ax):
+            a = sets[it[0] % 4][0]
+            it[0] += 1
+            check(lib().ndb_reduce_axis(ctx.handle, 0, ax, C.byref(a.v), C.byref(o1.v), 0.0))
         med, best = _time(ctx, c1_sum, 40, 4)
         rec(f"C1_sum_axis{ax}_f32_4096^2", 4 * n * n + 4 * n, med, best)
+        med, best = _time(ctx, c1_sum_into, 40, 4)
+        rec(f"C1_sum_axis{ax}_f32_4096^2_into_preallocated", 4 * n * n + 4 * n, med, best)
     del sets
     # ---- C3 ---------------------------------------------------------------------------------------
     n = 16384

@@ -289,17 +289,17 @@ __global__ void __launch_bounds__(256) red_lanes(RedArgs a)
                 const V *vsrc = reinterpret_cast<const V *>(src);
                 const int64_t nv = a.n / N;
                 int64_t i = tid;
-                for (; i + 3 * (int64_t)nt < nv; i += 4 * (int64_t)nt) {
-                    V v0 = vsrc[i], v1 = vsrc[i + nt], v2 = vsrc[i + 2 * nt], v3 = vsrc[i + 3 * nt];
-                    T x[4 * N];
+                constexpr int U = (R == R_WELFORD) ? 4 : 8;  // vectors in flight per thread
+                for (; i + (U - 1) * (int64_t)nt < nv; i += U * (int64_t)nt) {
+                    V v[U];
 #pragma unroll
-                    for (int e = 0; e < N; ++e) {
-                        x[e] = v0.v[e];
-                        x[N + e] = v1.v[e];
-                        x[2 * N + e] = v2.v[e];
-                        x[3 * N + e] = v3.v[e];
-                    }
-                    acc.template add_batch<4 * N>(x);
+                    for (int u = 0; u < U; ++u) v[u] = vsrc[i + u * (int64_t)nt];
+                    T x[U * N];
+#pragma unroll
+                    for (int u = 0; u < U; ++u)
+#pragma unroll
+                        for (int e = 0; e < N; ++e) x[u * N + e] = v[u].v[e];
+                    acc.template add_batch<U * N>(x);
                 }
                 for (; i < nv; i += nt) {
                     V v0 = vsrc[i];
@@ -728,7 +728,7 @@ static int reduce_axis_launch(ndb_ctx *ctx, RedArgs &a, const ZipPlan &z)
     if (lanes) {
         bool vec = a.s == 1 && a.n % vecn == 0 && ((uintptr_t)a.in % 16) == 0 && a.n >= 4 * vecn;
         for (int d = 0; d < a.k.n && vec; ++d) vec = a.k.dim[d] == 1 || a.k.in_stride[d] % vecn == 0;
-        const bool warp = a.n <= 2048;
+        const bool warp = a.n <= (getenv("NDB_RED_WARP_MAX") ? atoll(getenv("NDB_RED_WARP_MAX")) : 8192);
         const int64_t groups = warp ? (a.n_out + 7) / 8 : a.n_out;
         const unsigned blocks = (unsigned)std::min<int64_t>(groups, (int64_t)1 << 30);
         if (warp) {
@@ -749,7 +749,9 @@ static int reduce_axis_launch(ndb_ctx *ctx, RedArgs &a, const ZipPlan &z)
         const int64_t tiles = (ncol + 32 * w - 1) / (32 * w);
         const int64_t total = tiles * (a.n_out / ncol);
         // enough blocks to fill the machine ~4 deep, but every split keeps >= 64 rows
-        int64_t want = ((int64_t)ctx->sm_count * 8 + total - 1) / total;
+        // blocks per SM to aim for: measured best 8 for the plain reducers, 6 for Welford (72 registers: 3 CTAs/SM, two waves)
+        const int per_sm = getenv("NDB_RED_COLS_PER_SM") ? atoi(getenv("NDB_RED_COLS_PER_SM")) : (R == R_WELFORD ? 6 : 8);
+        int64_t want = ((int64_t)ctx->sm_count * per_sm + total - 1) / total;
         int64_t max_splits = std::max<int64_t>(1, a.n / 64);
         int splits = (int)std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(want, max_splits), 256));
         a.splits = splits;
