@@ -366,3 +366,33 @@ def test_float_maths_maps(nd, oracle, dtype):
     assert nanarr.is_any_nan() and not nanarr.is_all_nan() and not nanarr.is_any_infinite()
     with pytest.raises(nd.NdbError):
         nd.Array.from_numpy(np.arange(4, dtype=np.int32)).map_math("exp")
+
+
+def test_config5_full_size_64bit_indexing(nd):
+    """BASELINE config 5 on one GPU: 2^32 + 40 f32 elements per array (64-bit indexing in every kernel class on the
+    way), a = b*c + a in place followed by sum(); checked through constants, sampled slices and the exact count."""
+    from ndarray_b200 import Array, Zip, Op, s_
+    n = (1 << 32) + 40
+    a, b, c = (Array.uninit((n,), np.float32) for _ in range(3))
+    a.fill(0.25)
+    b.fill(0.5)
+    c.fill(1.5)
+    Zip.from_(a).and_(b).and_(c).for_each("a=b*c+a")
+    for lo in (0, (1 << 31) - 3, (1 << 32) - 5, n - 7):
+        assert a.slice(s_[lo:lo + 7]).to_numpy().tolist() == [1.0] * 7
+    total = float(a.sum())
+    assert abs(total - n) <= 1e-6 * n
+    # a strided 2-d view over the same buffer whose offsets exceed 2^32: rows kernel with 64-bit strides
+    v = a.raw_view_with(8, (4096, 1 << 19), (1 << 20, 2))        # every other element of 4096 slabs 2^20 apart
+    w = Array.zeros((4096, 1 << 19), np.float32)
+    Zip.from_(w).and_(v).for_each("a=b")
+    assert float(w.sum()) == 4096.0 * (1 << 19)
+    v.fill(3.0)
+    assert a.slice(s_[8:12]).to_numpy().tolist() == [3.0, 1.0, 3.0, 1.0]
+    assert a.slice(s_[4095 * (1 << 20) + 8 + 2 * ((1 << 19) - 1) - 1:4095 * (1 << 20) + 8 + 2 * ((1 << 19) - 1) + 2]).to_numpy().tolist() == [1.0, 3.0, 1.0]
+    # transposed view with a 2^31-element row pitch: tile kernel with 64-bit offsets
+    t = a.raw_view_with(0, (2, 1 << 12), (1 << 31, 1)).t()            # shape (4096, 2), strides (1, 2^31)
+    o = Array.zeros((1 << 12, 2), np.float32)
+    Zip.from_(o).and_(t).for_each("a=b")
+    got = o.to_numpy()
+    assert got[:, 0].tolist()[:12] == [1.0] * 8 + [3.0, 1.0, 3.0, 1.0] and set(got[:, 1].tolist()) <= {1.0, 3.0}
