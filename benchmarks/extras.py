@@ -119,6 +119,18 @@ def run_extras(nd, ctx, torch, dist, rank, world, local, peak_gbs):
         e1.record()
         torch.cuda.synchronize(dev)
         out[f"C4_comparator_cublas_{name}_8192^3"] = {"TFLOP/s": round(flops / (e0.elapsed_time(e1) / 3 * 1e-3) / 1e12, 2)}
+        if tdt == torch.float32:
+            # what the tensor cores sustain for ONE tf32 MMA per logical MMA (cuBLAS TF32 mode): our 3xTF32 kernel
+            # issues three, so its tensor-pipe rate is 3x its reported TFLOP/s
+            torch.backends.cuda.matmul.allow_tf32 = True
+            torch.matmul(ta, tb)
+            e0.record()
+            for _ in range(3):
+                torch.matmul(ta, tb)
+            e1.record()
+            torch.cuda.synchronize(dev)
+            torch.backends.cuda.matmul.allow_tf32 = False
+            out["C4_comparator_cublas_1xtf32_8192^3"] = {"TFLOP/s": round(flops / (e0.elapsed_time(e1) / 3 * 1e-3) / 1e12, 2)}
         del ta, tb, tc
     torch.cuda.empty_cache()
     # ---- C5: sharded elementwise + global sum with an all-reduce ----------------------------------------

@@ -36,8 +36,8 @@ def main():
             ta, tb, tc = (torch.randn(n, n, device=dev, dtype=tdt) for _ in range(3))
             A, B, Cm = (Array.borrow(t.data_ptr(), (n, n), dt, "C", ctx, owner=t) for t in (ta, tb, tc))
             Bf = Array.borrow(tb.data_ptr(), (n, n), dt, "F", ctx, owner=tb)
-            for envs in ([{}] + ([{"NDB_GEMM_CHUNK_KB": g} for g in ("4", "16", "32", "100000")] if name == "f32" else [])):
-                for k in ("NDB_GEMM_GROUP_M", "NDB_GEMM_CHUNK_KB"):
+            for envs in ([{}] + ([{"NDB_GEMM_DEBUG": g} for g in ("1", "2")] if name == "f32" else [])):
+                for k in ("NDB_GEMM_GROUP_M", "NDB_GEMM_CHUNK_KB", "NDB_GEMM_DEBUG"):
                     os.environ.pop(k, None)
                 os.environ.update(envs)
                 med, best = timeit(ctx, lambda: nd.general_mat_mul(1.0, A, B, 0.0, Cm))

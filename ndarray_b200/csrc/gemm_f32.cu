@@ -50,6 +50,7 @@ struct F32Args {
     int64_t rsc, csc;
     float alpha, beta;
     int tiles_m, tiles_n, group_m, chunk_kb;
+    int debug;  // tuning probes only: 1 = no TMA traffic after the first ring fill, 2 = no MMAs (results are garbage)
 };
 
 // ---- PTX helpers -----------------------------------------------------------------------------
@@ -184,6 +185,10 @@ gemm_tf32x3(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
                 const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
                 mbar_wait(empty_bar + 8 * s, ph ^ 1u);
                 const uint32_t st = tiles + s * C::STAGE_BYTES;
+                if (p.debug == 1 && kb >= STAGES) {
+                    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(full_bar + 8 * s) : "memory");
+                    continue;
+                }
                 mbar_expect_tx(full_bar + 8 * s, C::STAGE_BYTES);
                 tma_load_2d(st, &map_a_hi, full_bar + 8 * s, kb * BK, m0);
                 tma_load_2d(st + C::A_BYTES, &map_a_lo, full_bar + 8 * s, kb * BK, m0);
@@ -209,6 +214,10 @@ gemm_tf32x3(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
                     const uint64_t da_hi = make_desc(st), da_lo = make_desc(st + C::A_BYTES);
                     const uint64_t db_hi = make_desc(st + 2 * C::A_BYTES), db_lo = make_desc(st + 2 * C::A_BYTES + C::B_BYTES);
                     const uint32_t first = (kb != ch * CHUNK_KB);
+                    if (p.debug == 2 && kb > 0) {
+                        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(empty_bar + 8 * s) : "memory");
+                        continue;
+                    }
 #pragma unroll
                     for (int k = 0; k < BK / UMMA_K; ++k) {
                         const uint64_t adv = (uint64_t)(k * UMMA_K * 4 >> 4);  // 32 bytes per slice inside the swizzle row
@@ -367,6 +376,7 @@ int launch(ndb_ctx *ctx, const GemmArgs &g, float alpha, float beta, const float
     p.tiles_m = (int)((g.m + BM - 1) / BM);
     p.tiles_n = (int)((g.n + BN - 1) / BN);
     p.group_m = getenv("NDB_GEMM_GROUP_M") ? std::max(1, atoi(getenv("NDB_GEMM_GROUP_M"))) : 12;
+    p.debug = getenv("NDB_GEMM_DEBUG") ? atoi(getenv("NDB_GEMM_DEBUG")) : 0;
     p.chunk_kb = getenv("NDB_GEMM_CHUNK_KB") ? std::max(1, atoi(getenv("NDB_GEMM_CHUNK_KB"))) : 8;
     static bool attr_done = false;
     if (!attr_done) {
