@@ -89,9 +89,9 @@ def test_slice_axis_matches_oracle(spec):
 def test_slice_errors():
     v = mk(0, np.float32, (4,), (1,))
     assert nd.lib().ndb_view_slice_axis(C.byref(v), 0, 5, 0, 0, 1) == _ffi.ERR_OOB
+    assert b"Slice begin 5 is past end of axis of length 4" in nd.lib().ndb_last_error()
     assert nd.lib().ndb_view_slice_axis(C.byref(v), 0, 0, 0, 0, 0) == _ffi.ERR_INVALID
     assert nd.lib().ndb_view_slice_axis(C.byref(v), 1, 0, 0, 0, 1) == _ffi.ERR_OOB
-    assert b"past end of axis" in nd.lib().ndb_last_error() or True
 
 
 def test_broadcast_matches_reference_rules():  # tests/broadcast.rs:4-33
@@ -161,8 +161,7 @@ def test_planner_kernel_classes():
     st, pl = plan(nd.Op.MUL_ADD, c2, c2, c2, c2)
     assert st == 0 and pl.kernel == 1 and pl.ndim == 1 and pl.dim[0] == 4096 * 4096
     # unaligned base -> scalar flat
-    st, pl = plan(nd.Op.ADD, mk(A + 4, np.float32, (64,), (1,)), c2 if False else mk(A, np.float32, (64,), (1,)),
-                  mk(A, np.float32, (64,), (1,)))
+    st, pl = plan(nd.Op.ADD, mk(A + 4, np.float32, (64,), (1,)), mk(A, np.float32, (64,), (1,)), mk(A, np.float32, (64,), (1,)))
     assert st == 0 and pl.kernel == 2
     # config 2 (i): x.t() + y -> tile transpose on the axis where x is dense
     xt = mk(A, np.float32, (n, n, n), f_strides((n, n, n)))
