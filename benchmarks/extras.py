@@ -154,4 +154,49 @@ def run_extras(nd, ctx, torch, dist, rank, world, local, peak_gbs):
         nbytes = (4 * 4 + 4) * rows * 65536 * world
         out["C5_zip+global_sum_f32"] = {"GB/s_aggregate": round(gbs(nbytes, float(t.item())), 1), "ms": round(float(t.item()), 3),
                                         "per_rank_elems": rows * 65536, "collective": "ncclAllReduce(sum, 1 elt) on the ctx stream"}
+    if rank == 0 and world == 1:
+        try:
+            out["cpu_stand_in"] = cpu_stand_ins()
+        except Exception as e:  # never break the bench line
+            out["cpu_stand_in"] = {"error": repr(e)}
     return out
+
+
+def cpu_stand_ins():
+    """The reference's CPU path for the other configs, timed on this box's host cores on bounded samples (the
+    in-image stand-in of BASELINE.md §3: the oracle port of ndarray's algorithms; OpenBLAS through numpy for GEMM,
+    which is what ndarray's `blas` feature would call).  ndarray has no parallel axis reductions, so those are serial."""
+    import time
+    from oracle import oracle as orc
+    orc.build()
+    threads = orc.max_threads()
+    res = {"threads": threads}
+    rng = np.random.default_rng(0)
+
+    def best(fn, reps=3):
+        t = []
+        for _ in range(reps):
+            t0 = time.perf_counter()
+            fn()
+            t.append(time.perf_counter() - t0)
+        return min(t)
+
+    n = 4096
+    a, b, c = (rng.random((n, n), dtype=np.float32) for _ in range(3))
+    dt = best(lambda: orc.zip_(7, a, [b, c, a], threads=threads))
+    res["C1_zip_a=b*c+a_f32_4096^2"] = {"GB/s": round(16 * n * n / dt / 1e9, 1), "threads": threads, "kind": "oracle port, OpenMP"}
+    for ax in (0, 1):
+        dt = best(lambda: orc.reduce_axis(0, a, ax))
+        res[f"C1_sum_axis{ax}_f32_4096^2"] = {"GB/s": round(4 * n * n / dt / 1e9, 1), "threads": 1, "kind": "oracle port (serial, as in ndarray)"}
+    f = rng.standard_normal((n, n))
+    for name, red in (("sum_axis", 0), ("var_axis", 5)):
+        for ax in (0, 1):
+            dt = best(lambda: orc.reduce_axis(red, f, ax, 1.0), 2)
+            res[f"C3_{name}{ax}_f64_sample_4096^2"] = {"GB/s": round(8 * n * n / dt / 1e9, 1), "threads": 1, "kind": "oracle port (serial), 1/16 of config 3"}
+    m = 2048
+    for dtp, name in ((np.float64, "f64"), (np.float32, "f32")):
+        A, B = rng.standard_normal((m, m)).astype(dtp), rng.standard_normal((m, m)).astype(dtp)
+        A @ B
+        dt = best(lambda: A @ B, 3)
+        res[f"C4_gemm_{name}_sample_2048^3"] = {"TFLOP/s": round(2 * m ** 3 / dt / 1e12, 3), "kind": "OpenBLAS via numpy (what ndarray's blas feature calls)"}
+    return res

@@ -75,6 +75,14 @@ def main():
                 med, best = timeit(ctx, fn, 10, 2)
                 print(f"  {name}_axis{ax} {np.dtype(dt).name} 16384^2 into: {med*1e3:8.1f} us {n*n*8/med/1e6:8.1f} GB/s")
         del big
+    n = 16384
+    for dt in (np.float32, np.float64):
+        for order in ("C", "F"):
+            A = Array.zeros((n, n), dt, order=order)
+            x, y = Array.zeros((n,), dt), Array.zeros((n,), dt)
+            med, best = timeit(ctx, lambda: nd.general_mat_vec_mul(1.0, A, x, 0.0, y), 10, 2)
+            print(f"  gemv {np.dtype(dt).name} {n}^2 A={order}: {med*1e3:8.1f} us {n*n*np.dtype(dt).itemsize/med/1e6:8.1f} GB/s")
+            del A
     if os.environ.get("NDB_PROBE_NO_GEMM"):
         return
     for dt in (np.float64, np.float32):

@@ -7,6 +7,7 @@
 //   everything else -> gemm_any below: a shared-memory tiled kernel that takes ANY signed strides and
 //                      element type (ndarray's own fallback for non-BLAS types is a naive i,j,k loop,
 //                      impl_linalg.rs:601-617; integers wrap).
+#include <algorithm>
 #include <mutex>
 
 #include "gemm.h"
@@ -102,7 +103,8 @@ __global__ void __launch_bounds__(256) gemm_any(GemmArgs g, T alpha, T beta)
 // ---- matrix-vector: y <- alpha * A x + beta * y (general_mat_vec_mul, impl_linalg.rs:657-743) ------------------
 // HBM-bound (A is read once).  Two forms, chosen by which axis of A is denser:
 //   gemv_rows: a warp per row, lanes stride along k (coalesced when A is row-major), shuffle reduction;
-//   gemv_cols: a thread per row, all threads walk k together (coalesced when A is column-major).
+//   gemv_cols_split: a thread per row, all threads walk k together (coalesced when A is column-major), k split
+//   across blockIdx.y so that a few thousand rows still fill 148 SMs.
 struct GemvArgs {
     const char *a, *x;
     char *y;
@@ -136,37 +138,146 @@ __global__ void __launch_bounds__(256) gemv_rows(GemvArgs g, T alpha, T beta)
     }
 }
 
+// 128-bit form of gemv_rows: A rows and x are dense and 16-byte aligned; 4 vectors of A (and of x) in flight per lane.
 template <typename T>
-__global__ void __launch_bounds__(256) gemv_cols(GemvArgs g, T alpha, T beta)
+__global__ void __launch_bounds__(256) gemv_rows_vec(GemvArgs g, T alpha, T beta)
+{
+    using V = Vec128<T>;
+    constexpr int N = V::N;
+    const int lane = threadIdx.x & 31;
+    const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (row >= g.m) return;
+    const V *A = reinterpret_cast<const V *>(reinterpret_cast<const T *>(g.a) + row * g.rsa);
+    const V *x = reinterpret_cast<const V *>(g.x);
+    const int64_t nv = g.k / N;
+    T acc[4] = {T(0), T(0), T(0), T(0)};
+    int64_t k = lane;
+    for (; k + 96 < nv; k += 128) {
+        V a[4], b[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            a[u] = A[k + 32 * u];
+            b[u] = x[k + 32 * u];
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+            for (int e = 0; e < N; ++e) acc[u] = mul_add(a[u].v[e], b[u].v[e], acc[u]);
+    }
+    for (; k < nv; k += 32) {
+        const V a = A[k], b = x[k];
+#pragma unroll
+        for (int e = 0; e < N; ++e) acc[0] = mul_add(a.v[e], b.v[e], acc[0]);
+    }
+    T r = w_add(w_add(acc[0], acc[1]), w_add(acc[2], acc[3]));
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) r = w_add(r, __shfl_down_sync(0xffffffffu, r, d));
+    if (lane == 0) {
+        T *dst = reinterpret_cast<T *>(g.y) + row * g.sy;
+        *dst = beta == T(0) ? w_mul(alpha, r) : w_add(w_mul(alpha, r), w_mul(beta, *dst));
+    }
+}
+
+// Column-major A with split-K: block (x) owns 256 rows, block (y) a slice of k; partial[split][row] is merged in split
+// order by gemv_cols_finish (deterministic), which also applies alpha / beta.
+template <typename T>
+__global__ void __launch_bounds__(256) gemv_cols_split(GemvArgs g, int splits, T *partial)
 {
     const int64_t row = (int64_t)blockIdx.x * 256 + threadIdx.x;
     if (row >= g.m) return;
+    const int64_t chunk = (g.k + splits - 1) / splits;
+    const int64_t k0 = (int64_t)blockIdx.y * chunk, k1 = k0 + chunk < g.k ? k0 + chunk : g.k;
     const T *A = reinterpret_cast<const T *>(g.a) + row * g.rsa;
     const T *x = reinterpret_cast<const T *>(g.x);
-    T acc0 = T(0), acc1 = T(0), acc2 = T(0), acc3 = T(0);
-    int64_t k = 0;
-    for (; k + 3 < g.k; k += 4) {
-        const T a0 = A[k * g.csa], a1 = A[(k + 1) * g.csa], a2 = A[(k + 2) * g.csa], a3 = A[(k + 3) * g.csa];
-        acc0 = mul_add(a0, x[k * g.sx], acc0);
-        acc1 = mul_add(a1, x[(k + 1) * g.sx], acc1);
-        acc2 = mul_add(a2, x[(k + 2) * g.sx], acc2);
-        acc3 = mul_add(a3, x[(k + 3) * g.sx], acc3);
+    T acc[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) acc[u] = T(0);
+    int64_t k = k0;
+    for (; k + 7 < k1; k += 8) {
+        T a[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) a[u] = A[(k + u) * g.csa];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) acc[u] = mul_add(a[u], x[(k + u) * g.sx], acc[u]);
     }
-    for (; k < g.k; ++k) acc0 = mul_add(A[k * g.csa], x[k * g.sx], acc0);
-    const T acc = w_add(w_add(acc0, acc1), w_add(acc2, acc3));
+    for (; k < k1; ++k) acc[0] = mul_add(A[k * g.csa], x[k * g.sx], acc[0]);
+    T r = acc[0];
+#pragma unroll
+    for (int u = 1; u < 8; ++u) r = w_add(r, acc[u]);
+    partial[(int64_t)blockIdx.y * g.m + row] = r;
+}
+
+// 128-bit form: A is dense column-major (rsa == 1), a thread owns Vec128<T>::N consecutive rows
+template <typename T>
+__global__ void __launch_bounds__(256) gemv_cols_split_vec(GemvArgs g, int splits, T *partial)
+{
+    using V = Vec128<T>;
+    constexpr int N = V::N;
+    const int64_t row = ((int64_t)blockIdx.x * 256 + threadIdx.x) * N;
+    if (row >= g.m) return;
+    const int64_t chunk = (g.k + splits - 1) / splits;
+    const int64_t k0 = (int64_t)blockIdx.y * chunk, k1 = k0 + chunk < g.k ? k0 + chunk : g.k;
+    const T *A = reinterpret_cast<const T *>(g.a) + row;
+    const T *x = reinterpret_cast<const T *>(g.x);
+    T acc[N];
+#pragma unroll
+    for (int e = 0; e < N; ++e) acc[e] = T(0);
+    int64_t k = k0;
+    for (; k + 7 < k1; k += 8) {
+        V a[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) a[u] = *reinterpret_cast<const V *>(A + (k + u) * g.csa);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const T xv = x[(k + u) * g.sx];
+#pragma unroll
+            for (int e = 0; e < N; ++e) acc[e] = mul_add(a[u].v[e], xv, acc[e]);
+        }
+    }
+    for (; k < k1; ++k) {
+        const V a = *reinterpret_cast<const V *>(A + k * g.csa);
+        const T xv = x[k * g.sx];
+#pragma unroll
+        for (int e = 0; e < N; ++e) acc[e] = mul_add(a.v[e], xv, acc[e]);
+    }
+#pragma unroll
+    for (int e = 0; e < N; ++e) partial[(int64_t)blockIdx.y * g.m + row + e] = acc[e];
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) gemv_cols_finish(GemvArgs g, int splits, const T *partial, T alpha, T beta)
+{
+    const int64_t row = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (row >= g.m) return;
+    T r = partial[row];
+    for (int s = 1; s < splits; ++s) r = w_add(r, partial[(int64_t)s * g.m + row]);
     T *dst = reinterpret_cast<T *>(g.y) + row * g.sy;
-    *dst = beta == T(0) ? w_mul(alpha, acc) : w_add(w_mul(alpha, acc), w_mul(beta, *dst));
+    *dst = beta == T(0) ? w_mul(alpha, r) : w_add(w_mul(alpha, r), w_mul(beta, *dst));
 }
 
 template <typename T>
 static int gemv_launch(ndb_ctx *ctx, const GemvArgs &g, T alpha, T beta)
 {
     if (g.m == 0) return NDB_OK;
+    constexpr int64_t N = Vec128<T>::N;
     if (llabs(g.csa) <= llabs(g.rsa) || g.m < 2048) {
-        gemv_rows<T><<<(unsigned)((g.m + 7) / 8), 256, 0, ctx->stream>>>(g, alpha, beta);
-    } else {
-        gemv_cols<T><<<(unsigned)((g.m + 255) / 256), 256, 0, ctx->stream>>>(g, alpha, beta);
+        const bool vec = g.csa == 1 && g.sx == 1 && g.k % N == 0 && g.k >= 4 * N && g.rsa % N == 0 &&
+                         ((uintptr_t)g.a % 16) == 0 && ((uintptr_t)g.x % 16) == 0;
+        if (vec) gemv_rows_vec<T><<<(unsigned)((g.m + 7) / 8), 256, 0, ctx->stream>>>(g, alpha, beta);
+        else gemv_rows<T><<<(unsigned)((g.m + 7) / 8), 256, 0, ctx->stream>>>(g, alpha, beta);
+        NDB_CHECK_LAUNCH();
+        return NDB_OK;
     }
+    const bool cvec = g.rsa == 1 && g.csa % N == 0 && g.m % N == 0 && ((uintptr_t)g.a % 16) == 0;
+    const int64_t row_blocks = cvec ? (g.m / N + 255) / 256 : (g.m + 255) / 256;
+    int splits = (int)std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(((int64_t)ctx->sm_count * 8 + row_blocks - 1) / row_blocks,
+                                                                                  std::max<int64_t>(1, g.k / 64)), 1024));
+    NDB_TRY(ensure_workspace(ctx, (size_t)splits * (size_t)g.m * sizeof(T)));
+    dim3 grid((unsigned)row_blocks, (unsigned)splits, 1);
+    if (cvec) gemv_cols_split_vec<T><<<grid, 256, 0, ctx->stream>>>(g, splits, (T *)ctx->workspace);
+    else gemv_cols_split<T><<<grid, 256, 0, ctx->stream>>>(g, splits, (T *)ctx->workspace);
+    NDB_CHECK_LAUNCH();
+    gemv_cols_finish<T><<<(unsigned)((g.m + 255) / 256), 256, 0, ctx->stream>>>(g, splits, (const T *)ctx->workspace, alpha, beta);
     NDB_CHECK_LAUNCH();
     return NDB_OK;
 }

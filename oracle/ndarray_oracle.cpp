@@ -395,7 +395,7 @@ static inline T math_fn(int fn, T x, T p)
 }
 
 template <typename T>
-static inline T apply(int op, int nin, const T *x, T s0, T s1, int *trap)
+__attribute__((always_inline)) static inline T apply(int op, int nin, const T *x, T s0, T s1, int *trap)
 {
     switch (op) {
     case OP_COPY: return x[0];
@@ -444,10 +444,13 @@ static inline T apply(int op, int nin, const T *x, T s0, T s1, int *trap)
 
 // The traversal of Zip::for_each_core (src/zip/mod.rs:309-424) for one Zip over `n_parts` producers
 // of identical shape.  parts[0] is written, the rest are read.
-template <typename T>
-static void zip_serial(int op, const void *scalars, int n_parts, const orc_view *parts, int *trap)
+// OP and NIN are compile-time so that, like the monomorphised Rust closure, the element function inlines and the
+// contiguous loops vectorise (NIN < 0: the n-ary sum, arity known at run time).
+template <typename T, int OP, int NIN>
+static void zip_serial_ct(const void *scalars, int n_parts, const orc_view *parts, int *trap)
 {
-    const int nin = n_parts - 1;
+    constexpr int op = OP;
+    const int nin = NIN >= 0 ? NIN : n_parts - 1;
     T s0 = 0, s1 = 0;
     if (scalars) {
         s0 = ((const T *)scalars)[0];
@@ -460,6 +463,7 @@ static void zip_serial(int op, const void *scalars, int n_parts, const orc_view 
     T *ptr[ORC_MAX_PARTS];
     for (int p = 0; p < n_parts; ++p) ptr[p] = (T *)parts[p].ptr;
     T x[ORC_MAX_PARTS];
+    (void)x;
     if (nd == 0) {  // :313-316
         for (int p = 0; p < nin; ++p) x[p] = *ptr[p + 1];
         *ptr[0] = apply<T>(op, nin, x, s0, s1, trap);
@@ -468,6 +472,26 @@ static void zip_serial(int op, const void *scalars, int n_parts, const orc_view 
     const ZipState zs = zip_state(n_parts, parts);
     if (zs.layout & (CORDER | FORDER)) {
         // for_each_core_contiguous :323-341 -> inner :343-357 with unit strides
+        if constexpr (NIN >= 0 && NIN <= 3) {
+            T *__restrict__ o_ = ptr[0];
+            const T *a_ = NIN > 0 ? ptr[1] : nullptr, *b_ = NIN > 1 ? ptr[2] : nullptr, *c_ = NIN > 2 ? ptr[3] : nullptr;
+            const bool alias = (NIN > 0 && a_ == o_) || (NIN > 1 && b_ == o_) || (NIN > 2 && c_ == o_);
+            if (!alias) {
+#pragma omp simd
+                for (int64_t i = 0; i < size; ++i) {
+                    T v[3] = {NIN > 0 ? a_[i] : T(0), NIN > 1 ? b_[i] : T(0), NIN > 2 ? c_[i] : T(0)};
+                    o_[i] = apply<T>(op, nin, v, s0, s1, trap);
+                }
+                return;
+            }
+            T *o2 = ptr[0];  // in-place form (a = b*c + a): same element read and written, still independent across i
+#pragma omp simd
+            for (int64_t i = 0; i < size; ++i) {
+                T v[3] = {NIN > 0 ? ptr[1][i] : T(0), NIN > 1 ? ptr[2][i] : T(0), NIN > 2 ? ptr[3][i] : T(0)};
+                o2[i] = apply<T>(op, nin, v, s0, s1, trap);
+            }
+            return;
+        }
         for (int64_t i = 0; i < size; ++i) {
             for (int p = 0; p < nin; ++p) x[p] = ptr[p + 1][i];
             ptr[0][i] = apply<T>(op, nin, x, s0, s1, trap);
@@ -489,9 +513,21 @@ static void zip_serial(int op, const void *scalars, int n_parts, const orc_view 
             off[p] = 0;
             for (int k = 0; k < nd; ++k) off[p] += idx[k] * parts[p].stride[k];
         }
-        for (int64_t i = 0; i < inner_len; ++i) {
-            for (int p = 0; p < nin; ++p) x[p] = ptr[p + 1][off[p + 1] + i * inner_stride[p + 1]];
-            ptr[0][off[0] + i * inner_stride[0]] = apply<T>(op, nin, x, s0, s1, trap);
+        if constexpr (NIN >= 0 && NIN <= 3) {
+            T *o_ = ptr[0] + off[0];
+            const int64_t so = inner_stride[0];
+            const T *a_ = NIN > 0 ? ptr[1] + off[1] : nullptr, *b_ = NIN > 1 ? ptr[2] + off[2] : nullptr,
+                    *c_ = NIN > 2 ? ptr[3] + off[3] : nullptr;
+            const int64_t sa = NIN > 0 ? inner_stride[1] : 0, sb = NIN > 1 ? inner_stride[2] : 0, sc = NIN > 2 ? inner_stride[3] : 0;
+            for (int64_t i = 0; i < inner_len; ++i) {
+                T v[3] = {NIN > 0 ? a_[i * sa] : T(0), NIN > 1 ? b_[i * sb] : T(0), NIN > 2 ? c_[i * sc] : T(0)};
+                o_[i * so] = apply<T>(op, nin, v, s0, s1, trap);
+            }
+        } else {
+            for (int64_t i = 0; i < inner_len; ++i) {
+                for (int p = 0; p < nin; ++p) x[p] = ptr[p + 1][off[p + 1] + i * inner_stride[p + 1]];
+                ptr[0][off[0] + i * inner_stride[0]] = apply<T>(op, nin, x, s0, s1, trap);
+            }
         }
         bool done = true;
         if (!f_order) {
@@ -506,6 +542,23 @@ static void zip_serial(int op, const void *scalars, int n_parts, const orc_view 
             }
         }
         if (done) break;
+    }
+}
+
+template <typename T>
+static void zip_serial(int op, const void *scalars, int n_parts, const orc_view *parts, int *trap)
+{
+    switch (op) {
+#define ORC_CASE(OP, NIN) \
+    case OP: zip_serial_ct<T, OP, NIN>(scalars, n_parts, parts, trap); return;
+        ORC_CASE(OP_COPY, 1) ORC_CASE(OP_FILL, 0) ORC_CASE(OP_ADD, 2) ORC_CASE(OP_SUB, 2) ORC_CASE(OP_MUL, 2)
+        ORC_CASE(OP_DIV, 2) ORC_CASE(OP_REM, 2) ORC_CASE(OP_MUL_ADD, 3) ORC_CASE(OP_ADD_S, 1) ORC_CASE(OP_SUB_S, 1)
+        ORC_CASE(OP_MUL_S, 1) ORC_CASE(OP_DIV_S, 1) ORC_CASE(OP_REM_S, 1) ORC_CASE(OP_RSUB_S, 1) ORC_CASE(OP_RDIV_S, 1)
+        ORC_CASE(OP_NEG, 1) ORC_CASE(OP_AXPY, 2) ORC_CASE(OP_ADD_N, -1) ORC_CASE(OP_ABS, 1) ORC_CASE(OP_SQRT, 1)
+        ORC_CASE(OP_MIN, 2) ORC_CASE(OP_MAX, 2) ORC_CASE(OP_SCALE_ADD, 2) ORC_CASE(OP_EQ, 2) ORC_CASE(OP_NE, 2)
+        ORC_CASE(OP_LT, 2) ORC_CASE(OP_LE, 2) ORC_CASE(OP_GT, 2) ORC_CASE(OP_GE, 2) ORC_CASE(OP_MATH, 1) ORC_CASE(OP_CLAMP, 1)
+#undef ORC_CASE
+    default: break;
     }
 }
 
@@ -697,6 +750,15 @@ static void for_each_index(const orc_view *a, const orc_view *b, Fn fn)
 {
     const int nd = a->ndim;
     if (vsize(a) == 0) return;
+    if (nd == 1) {  // the common shape of a sum_axis result: one tight loop (what zip_mut_with_same_shape's slice loop is)
+        const int64_t n = a->dim[0], sa = a->stride[0], sb = b->stride[0];
+        if (sa == 1 && sb == 1) {
+            for (int64_t i = 0; i < n; ++i) fn(i, i);
+        } else {
+            for (int64_t i = 0; i < n; ++i) fn(i * sa, i * sb);
+        }
+        return;
+    }
     int64_t idx[ORC_MAX_NDIM] = {0};
     for (;;) {
         int64_t oa = 0, ob = 0;
