@@ -75,6 +75,14 @@ def main():
                 med, best = timeit(ctx, fn, 10, 2)
                 print(f"  {name}_axis{ax} {np.dtype(dt).name} 16384^2 into: {med*1e3:8.1f} us {n*n*8/med/1e6:8.1f} GB/s")
         del big
+    for dt in (np.float32, np.float64):
+        nn = 1 << 28
+        x1, y1 = Array.zeros((nn,), dt), Array.zeros((nn,), dt)
+        med, best = timeit(ctx, lambda: x1.dot(y1), 10, 2)
+        print(f"  dot {np.dtype(dt).name} 2^28: {med*1e3:8.1f} us {2*nn*np.dtype(dt).itemsize/med/1e6:8.1f} GB/s")
+        med, best = timeit(ctx, lambda: x1.slice(s_[::2]).dot(y1.slice(s_[::-2])), 10, 2)
+        print(f"  dot {np.dtype(dt).name} 2^27 strided: {med*1e3:8.1f} us {nn*np.dtype(dt).itemsize/med/1e6:8.1f} GB/s (algorithmic)")
+        del x1, y1
     n = 16384
     for dt in (np.float32, np.float64):
         for order in ("C", "F"):

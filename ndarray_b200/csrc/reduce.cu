@@ -581,6 +581,46 @@ __global__ void __launch_bounds__(256) dot_partials(const T *x, int64_t sx, cons
     if (threadIdx.x == 0) reinterpret_cast<Acc<T, R_SUM> *>(partial)[blockIdx.x] = acc;
 }
 
+// dense, 16-byte aligned operands: 128-bit loads, 4 vector pairs in flight per thread
+template <typename T>
+__global__ void __launch_bounds__(256) dot_partials_vec(const T *x, const T *y, int64_t n, void *partial)
+{
+    using V = Vec128<T>;
+    constexpr int N = V::N;
+    __shared__ Acc<T, R_SUM> smem[32];
+    Acc<T, R_SUM> acc;
+    acc.reset();
+    const V *vx = reinterpret_cast<const V *>(x), *vy = reinterpret_cast<const V *>(y);
+    const int64_t nv = n / N;
+    const int64_t stride = (int64_t)gridDim.x * 256;
+    int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    T part[4] = {T(0), T(0), T(0), T(0)};
+    for (; i + 3 * stride < nv; i += 4 * stride) {
+        V a[4], b[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            a[u] = vx[i + u * stride];
+            b[u] = vy[i + u * stride];
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+            for (int e = 0; e < N; ++e) part[u] = w_add(part[u], w_mul(a[u].v[e], b[u].v[e]));
+    }
+    for (; i < nv; i += stride) {
+        const V a = vx[i], b = vy[i];
+#pragma unroll
+        for (int e = 0; e < N; ++e) part[0] = w_add(part[0], w_mul(a.v[e], b.v[e]));
+    }
+    acc.add(w_add(w_add(part[0], part[1]), w_add(part[2], part[3])));
+    if (blockIdx.x == 0) {  // ragged tail
+        const int64_t t = nv * N + threadIdx.x;
+        if (t < n) acc.add(w_mul(x[t], y[t]));
+    }
+    acc = block_reduce(acc, smem);
+    if (threadIdx.x == 0) reinterpret_cast<Acc<T, R_SUM> *>(partial)[blockIdx.x] = acc;
+}
+
 // ======================================================================================================
 // host side
 
@@ -1103,8 +1143,10 @@ int ndb_dot(ndb_ctx *ctx, const ndb_view *x, const ndb_view *y, void *out_host)
     void *dev_scalar = (char *)ctx->workspace + ctx->workspace_bytes - 64;
     const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>(max_blocks, (n + 1023) / 1024));
     const int64_t sx = n > 1 ? x->stride[0] : 1, sy = n > 1 ? y->stride[0] : 1;
+    const bool dense = sx == 1 && sy == 1 && ((uintptr_t)x->ptr % 16) == 0 && ((uintptr_t)y->ptr % 16) == 0 && n >= 64;
 #define NDB_DOT(T)                                                                                            \
-    dot_partials<T><<<blocks, 256, 0, ctx->stream>>>((const T *)x->ptr, sx, (const T *)y->ptr, sy, n,         \
+    if (dense) dot_partials_vec<T><<<blocks, 256, 0, ctx->stream>>>((const T *)x->ptr, (const T *)y->ptr, n, ctx->workspace); \
+    else dot_partials<T><<<blocks, 256, 0, ctx->stream>>>((const T *)x->ptr, sx, (const T *)y->ptr, sy, n,    \
                                                      ctx->workspace);                                         \
     NDB_CHECK_LAUNCH();                                                                                       \
     red_all_finish<T, R_SUM><<<1, 256, 0, ctx->stream>>>(ctx->workspace, blocks, (T *)dev_scalar, T(1), 0);   \
