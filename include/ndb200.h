@@ -238,6 +238,9 @@ int ndb_view_min_stride_axis(const ndb_view *v);
  * `scalars` points at 0..2 values of the element type (FILL, *_S, AXPY, SCALE_ADD).
  */
 int ndb_zip(ndb_ctx *ctx, int op, const void *scalars, int n_parts, const ndb_view *parts);
+/* out[i] = in[i] as <out dtype> — `mapv(|x| x as B)`: the one elementwise form with two element types.  Rust `as`
+ * semantics (float -> int truncates and saturates, NaN -> 0; int -> int wraps; f64 -> f32 rounds to nearest). */
+int ndb_cast(ndb_ctx *ctx, const ndb_view *out, const ndb_view *in);
 /* The plan ndb_zip would execute; pure host code (no device needed). */
 int ndb_zip_plan(int op, int n_parts, const ndb_view *parts, ndb_zip_plan_t *plan);
 /* Zip::all / Zip::any (src/zip/mod.rs:658-696): does the predicate `op` (NDB_OP_EQ..GE, or any op whose result is

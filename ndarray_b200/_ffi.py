@@ -100,6 +100,7 @@ def lib():
         "ndb_view_is_contiguous": (i32, [PV]),
         "ndb_view_min_stride_axis": (i32, [PV]),
         "ndb_zip": (i32, [vp, i32, vp, i32, PV]),
+        "ndb_cast": (i32, [vp, PV, PV]),
         "ndb_zip_plan": (i32, [i32, i32, PV, C.POINTER(ZipPlan)]),
         "ndb_zip_prefer_f": (i32, [i32, PV]),
         "ndb_zip_host": (i32, [vp, i32, vp, i32, PV]),

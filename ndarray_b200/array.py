@@ -489,6 +489,14 @@ class Array:
         _zip_call(self.ctx, op, out, [self], scalars)
         return out
 
+    def mapv_cast(self, dtype) -> "Array":
+        """`a.mapv(|x| x as B)`: element-type conversion with Rust's `as` semantics."""
+        out = Array._alloc(self.shape, dtype, "F" if lib().ndb_zip_prefer_f(1, C.byref(self.v)) else "C", self.ctx)
+        check(lib().ndb_cast(self.ctx.handle, C.byref(out.v), C.byref(self.v)))
+        return out
+
+    astype = mapv_cast
+
     def mapv_inplace(self, op: int, scalars=()) -> None:
         _zip_call(self.ctx, op, self, [self], scalars)
 

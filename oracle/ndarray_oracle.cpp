@@ -21,6 +21,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <limits>
 #include <type_traits>
 #include <vector>
 
@@ -1004,6 +1005,55 @@ extern "C" int orc_gemm(int mode, const void *alpha, const orc_view *a, const or
     case I32: return gemm_typed<int32_t>(mode, *(const int32_t *)alpha, a, b, *(const int32_t *)beta, c, threads);
     case I64: return gemm_typed<int64_t>(mode, *(const int64_t *)alpha, a, b, *(const int64_t *)beta, c, threads);
     }
+    return ORC_UNSUPPORTED;
+}
+
+// `x as B` with Rust semantics (saturating float -> int, NaN -> 0; wrapping int -> int)
+template <typename TO, typename TI>
+static inline TO cast_one(TI x)
+{
+    if constexpr (std::is_floating_point<TI>::value && std::is_integral<TO>::value) {
+        if (x != x) return 0;
+        const double lo = (double)std::numeric_limits<TO>::min(), hi = (double)std::numeric_limits<TO>::max();
+        const double d = std::trunc((double)x);
+        if (d <= lo) return std::numeric_limits<TO>::min();
+        if (d >= hi) return std::numeric_limits<TO>::max();
+        return (TO)d;
+    } else if constexpr (std::is_integral<TI>::value && std::is_integral<TO>::value) {
+        return (TO)(typename Un<TO>::type)(typename Un<TI>::type)x;
+    } else {
+        return (TO)x;
+    }
+}
+
+template <typename TO, typename TI>
+static void cast_typed(const orc_view *out, const orc_view *in)
+{
+    TO *o = (TO *)out->ptr;
+    const TI *i = (const TI *)in->ptr;
+    for_each_index(out, in, [&](int64_t oo, int64_t oi) { o[oo] = cast_one<TO, TI>(i[oi]); });
+}
+
+extern "C" int orc_cast(const orc_view *out, const orc_view *in)
+{
+    if (out->ndim != in->ndim) return ORC_SHAPE;
+    for (int k = 0; k < out->ndim; ++k)
+        if (out->dim[k] != in->dim[k]) return ORC_SHAPE;
+#define ORC_CAST_IN(TO)                                                  \
+    switch (in->dtype) {                                                 \
+    case F32: cast_typed<TO, float>(out, in); return ORC_OK;             \
+    case F64: cast_typed<TO, double>(out, in); return ORC_OK;            \
+    case I32: cast_typed<TO, int32_t>(out, in); return ORC_OK;           \
+    case I64: cast_typed<TO, int64_t>(out, in); return ORC_OK;           \
+    }                                                                    \
+    return ORC_UNSUPPORTED;
+    switch (out->dtype) {
+    case F32: ORC_CAST_IN(float)
+    case F64: ORC_CAST_IN(double)
+    case I32: ORC_CAST_IN(int32_t)
+    case I64: ORC_CAST_IN(int64_t)
+    }
+#undef ORC_CAST_IN
     return ORC_UNSUPPORTED;
 }
 

@@ -170,3 +170,8 @@ def zip_prefer_f(inputs) -> bool:
 
 def max_threads() -> int:
     return lib().orc_max_threads()
+
+
+def cast(out: np.ndarray, a: np.ndarray) -> int:
+    vo, va = view(out), view(a)
+    return lib().orc_cast(C.byref(vo), C.byref(va))

@@ -396,3 +396,25 @@ def test_config5_full_size_64bit_indexing(nd):
     Zip.from_(o).and_(t).for_each("a=b")
     got = o.to_numpy()
     assert got[:, 0].tolist()[:12] == [1.0] * 8 + [3.0, 1.0, 3.0, 1.0] and set(got[:, 1].tolist()) <= {1.0, 3.0}
+
+
+def test_mapv_cast_matches_rust_as_semantics(nd, oracle):
+    """`mapv(|x| x as B)` for every pair of element types on contiguous, transposed and reversed views."""
+    rng = np.random.default_rng(31)
+    src = {np.float32: rng.uniform(-3e9, 3e9, (37, 50)).astype(np.float32), np.float64: rng.uniform(-1e19, 1e19, (37, 50)),
+           np.int32: rng.integers(-2 ** 31, 2 ** 31 - 1, (37, 50), dtype=np.int32),
+           np.int64: rng.integers(-2 ** 63, 2 ** 63 - 1, (37, 50), dtype=np.int64)}
+    for f in (np.float32, np.float64):
+        src[f][0, :6] = [np.nan, np.inf, -np.inf, 0.5, -0.5, 2.0 ** 31]
+    for ti, h in src.items():
+        for fn in (lambda x: x, lambda x: x.T, lambda x: x[::-1, ::2]):
+            m = Mirror(nd, h)
+            hv, dv = m.view(fn)
+            for to in (np.float32, np.float64, np.int32, np.int64):
+                want = np.zeros(hv.shape, to)
+                with np.errstate(all="ignore"):
+                    assert oracle.cast(want, hv) == 0
+                got = dv.mapv_cast(to).to_numpy()
+                assert_bit_equal(got, want, f"{np.dtype(ti).name} as {np.dtype(to).name}")
+    assert nd.Array.from_numpy(np.array([np.nan, 1e30, -1e30, -1.9], np.float32)).mapv_cast(np.int32).to_numpy().tolist() == \
+        [0, 2 ** 31 - 1, -2 ** 31, -1]
