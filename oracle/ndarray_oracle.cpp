@@ -1020,7 +1020,7 @@ static inline TO cast_one(TI x)
         if (d >= hi) return std::numeric_limits<TO>::max();
         return (TO)d;
     } else if constexpr (std::is_integral<TI>::value && std::is_integral<TO>::value) {
-        return (TO)(typename Un<TO>::type)(typename Un<TI>::type)x;
+        return (TO)x;  // sign-extend when widening, keep the low bits when narrowing (two's complement, like `as`)
     } else {
         return (TO)x;
     }
