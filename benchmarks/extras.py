@@ -77,6 +77,25 @@ def run_extras(nd, ctx, torch, dist, rank, world, local, peak_gbs):
         med, best = _time(ctx, c1_sum_into, 40, 4)
         rec(f"C1_sum_axis{ax}_f32_4096^2_into_preallocated", 4 * n * n + 4 * n, med, best)
     del sets
+    # ---- C2 variants: inner-axis step, map_collect (fresh output), all three views combined ------------
+    n = 512
+    from ndarray_b200 import s_, Op
+    tx, ty = torch.rand(n, n, n, device=dev) * 2 - 1, torch.rand(n, n, n, device=dev) * 2 - 1
+    trow = torch.rand(n, device=dev) * 2 - 1
+    x, y, row = tarr(tx), tarr(ty), tarr(trow)
+    o_full = Array.uninit((n, n, n), np.float32, ctx=ctx)
+    o_in = o_full.slice(s_[:, :, : n // 2])
+    med, best = _time(ctx, lambda: Zip.from_(o_in).and_(x.slice(s_[:, :, ::-2])).and_(y.slice(s_[:, :, ::2])).for_each("a=b+c"), 20, 3)
+    rec("C2_inner_axis_step_s![..,..,..;-2]+s![..,..,..;2]", 3 * n ** 3 * 2, med, best)
+    out["C2_inner_axis_step_s![..,..,..;-2]+s![..,..,..;2]"]["note"] = "stride-2 reads fetch 2x the algorithmic bytes in sectors (cap ~0.5)"
+    med, best = _time(ctx, lambda: Zip.from_(x.t()).and_(y).map_collect(Op.ADD), 20, 3)
+    rec("C2_transposed_via_map_collect(fresh output)", 3 * n ** 3 * 4, med, best)
+    o_half = o_full.slice(s_[: n // 2, :, :])
+    rowb = row.broadcast((n // 2, n, n))
+    xts, ys = x.t().slice(s_[::-2, :, :]), y.slice(s_[::2, :, :])
+    med, best = _time(ctx, lambda: Zip.from_(o_half).and_(ys).and_(rowb).and_(xts).for_each("a=b*c+d"), 20, 3)
+    rec("C2_combined_y[::2]*row+x.t()[::-2]", 3 * n ** 3 * 2 + 4 * n, med, best)
+    del x, y, row, o_full, tx, ty
     # ---- C3 ---------------------------------------------------------------------------------------
     n = 16384
     tf = torch.randn(n, n, device=dev, dtype=torch.float64)

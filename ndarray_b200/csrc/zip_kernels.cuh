@@ -531,8 +531,10 @@ __global__ void __launch_bounds__(256) zip_tile(TileArgs<NIN + 1> a, T s0, T s1,
 // 128-bit form: staged producers have ys == 1, everything else xs == 1, all rows 16-byte aligned and the
 // tile extents multiples of the vector width (checked on the host).  Every thread first issues ALL its
 // global loads (PASSES vectors per producer), then the staged ones go through shared memory.
-template <typename T, int OP, int NIN>
-__global__ void __launch_bounds__(256, (NIN <= 1 ? 6 : (NIN <= 2 ? 4 : 2))) zip_tile_vec(TileArgs<NIN + 1> a, T s0, T s1, int *flag)
+// STEP2: a staged producer may also step by +-2 along its dense axis (x.t().slice(s![..;-2, ..])): two vectors are
+// loaded and every other lane kept.
+template <typename T, int OP, int NIN, bool STEP2>
+__global__ void __launch_bounds__(256, STEP2 ? 2 : (NIN <= 1 ? 6 : (NIN <= 2 ? 4 : 2))) zip_tile_vec(TileArgs<NIN + 1> a, T s0, T s1, int *flag)
 {
     using V = Vec128<T>;
     constexpr int N = V::N;
@@ -551,15 +553,25 @@ __global__ void __launch_bounds__(256, (NIN <= 1 ? 6 : (NIN <= 2 ? 4 : 2))) zip_
         tile_coords<NP>(a, vb, tx, ty, off);
         const int64_t x0 = tx * TS, y0 = ty * TS;
         V ld[NI][PASSES];
+        V ld2[STEP2 ? NI : 1][STEP2 ? PASSES : 1];  // second vector of a +-2-stepped staged producer
 #pragma unroll
         for (int p = 1; p < NP; ++p) {
             const T *src = reinterpret_cast<const T *>(a.ptr[p]) + off[p];
             if (a.slot[p] >= 0) {
-                const int64_t y = y0 + (int64_t)vl * N;  // lanes along Y
+                // lanes along Y.  The N logical elements y..y+N-1 live in |ys| * N consecutive memory elements starting
+                // at A (a backwards axis is read as the mirrored vectors); vectors are aligned by the host's rules.
+                const int64_t y = y0 + (int64_t)vl * N;
+                const int64_t sy = a.ys[p] < 0 ? -a.ys[p] : a.ys[p];
+                const int64_t A = a.ys[p] > 0 ? y * sy : -(y * sy) - (sy * N - 1);
 #pragma unroll
                 for (int ps = 0; ps < PASSES; ++ps) {
                     const int64_t x = x0 + hi + ps * RPP;
-                    if (x < a.nx && y < a.ny) ld[p - 1][ps] = *reinterpret_cast<const V *>(src + y + x * a.xs[p]);
+                    if (x < a.nx && y < a.ny) {
+                        ld[p - 1][ps] = *reinterpret_cast<const V *>(src + A + x * a.xs[p]);
+                        if constexpr (STEP2) {
+                            if (sy == 2) ld2[p - 1][ps] = *reinterpret_cast<const V *>(src + A + N + x * a.xs[p]);
+                        }
+                    }
                 }
             } else {
                 const int64_t x = x0 + (int64_t)vl * N;  // lanes along X
@@ -574,12 +586,25 @@ __global__ void __launch_bounds__(256, (NIN <= 1 ? 6 : (NIN <= 2 ? 4 : 2))) zip_
         for (int p = 1; p < NP; ++p) {
             const int sl = a.slot[p];
             if (sl >= 0) {
+                const int64_t ys = a.ys[p];
 #pragma unroll
                 for (int ps = 0; ps < PASSES; ++ps) {
                     const int lx = hi + ps * RPP;
                     if (x0 + lx < a.nx && y0 + (int64_t)vl * N < a.ny) {
+                        const V &v0 = ld[p - 1][ps];
 #pragma unroll
-                        for (int e = 0; e < N; ++e) tile[sl][lx][vl * N + e] = ld[p - 1][ps].v[e];
+                        for (int e = 0; e < N; ++e) {
+                            T val = ys > 0 ? v0.v[e] : v0.v[N - 1 - e];  // |ys| == 1
+                            if constexpr (STEP2) {
+                                const V &v1 = ld2[p - 1][ps];
+                                constexpr int NN = N;
+                                const T fwd = (2 * e < NN) ? v0.v[(2 * e) % NN] : v1.v[(2 * e) % NN];
+                                const T bwd = (2 * NN - 1 - 2 * e < NN) ? v0.v[(2 * NN - 1 - 2 * e) % NN] : v1.v[(2 * NN - 1 - 2 * e) % NN];
+                                if (ys == 2) val = fwd;
+                                if (ys == -2) val = bwd;
+                            }
+                            tile[sl][lx][vl * N + e] = val;
+                        }
                     }
                 }
             }
@@ -681,17 +706,24 @@ int launch_zip(ndb_ctx *ctx, const ZipPlan &z, const void *scalars)
         for (int k = 0; k < no; ++k) a.total_tiles *= a.odim[k];
         a.y_fastest = env_int("NDB_TILE_YFAST", 0);
         // vector form?
-        bool vec = a.nx % VN == 0 && a.ny % VN == 0;
+        bool vec = a.nx % VN == 0 && a.ny % VN == 0, step2 = false;
         for (int p = 0; p < NP && vec; ++p) {
-            vec = ((uintptr_t)a.ptr[p] % 16) == 0;
-            if (a.slot[p] >= 0) vec = vec && a.ys[p] == 1 && a.xs[p] % VN == 0;
-            else vec = vec && a.xs[p] == 1 && a.ys[p] % VN == 0;
+            if (a.slot[p] >= 0) {
+                // forwards: base aligned; backwards: the element AFTER the base is aligned (mirrored vectors)
+                const int64_t sy = llabs(a.ys[p]);
+                vec = a.xs[p] % VN == 0 && (sy == 1 || sy == 2) &&
+                      ((a.ys[p] > 0 && ((uintptr_t)a.ptr[p] % 16) == 0) || (a.ys[p] < 0 && ((uintptr_t)(a.ptr[p] + sizeof(T)) % 16) == 0));
+                step2 = step2 || sy == 2;
+            } else {
+                vec = ((uintptr_t)a.ptr[p] % 16) == 0 && a.xs[p] == 1 && a.ys[p] % VN == 0;
+            }
             for (int k = 0; k < no && vec; ++k) vec = a.ostride[p][k] % VN == 0;
         }
         if (env_int("NDB_TILE_SCALAR", 0)) vec = false;
         int64_t blocks = a.total_tiles < (int64_t)1 << 30 ? a.total_tiles : (int64_t)1 << 30;
         const size_t smem = (size_t)nslot * TS * (TS + 1) * sizeof(T);
-        if (vec) zip_tile_vec<T, OP, NIN><<<(unsigned)blocks, 256, smem, st>>>(a, s0, s1, ctx->dev_flag);
+        if (vec && step2) zip_tile_vec<T, OP, NIN, true><<<(unsigned)blocks, 256, smem, st>>>(a, s0, s1, ctx->dev_flag);
+        else if (vec) zip_tile_vec<T, OP, NIN, false><<<(unsigned)blocks, 256, smem, st>>>(a, s0, s1, ctx->dev_flag);
         else zip_tile<T, OP, NIN><<<(unsigned)blocks, 256, smem, st>>>(a, s0, s1, ctx->dev_flag);
         NDB_CHECK_LAUNCH();
         return NDB_OK;

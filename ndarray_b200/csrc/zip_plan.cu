@@ -202,25 +202,30 @@ int make_zip_plan(int op, int n_parts, const ndb_view *parts, ZipPlan *zp)
     // A producer that is strided along the output's fastest axis but dense along another axis is
     // what ndarray's strided loop handles worst (src/zip/mod.rs:376-424: one useful element per cache
     // line).  Stage it through shared memory instead.
+    // "Dense along k" = a stride of at most 4 elements (a stepped slice of a dense axis still packs >= 1/4 of
+    // every sector) that is smaller than the producer's stride along the output's fastest axis.
+    auto dense_along = [&](int p, int k) {
+        const int64_t sk = llabs(z.stride[p][k]), si = llabs(z.stride[p][inner]);
+        return sk >= 1 && sk <= 4 && si > sk && si > 4;
+    };
     if (z.stride[0][inner] == 1 && m >= 2) {
         int best_axis = -1;
-        int64_t best_len = 0;
+        int64_t best_score = 0;
         for (int k = 0; k < inner; ++k) {
-            bool some = false;
-            for (int p = 1; p < n_parts; ++p) {
-                const int64_t si = z.stride[p][inner];
-                if (llabs(si) > 1 && llabs(z.stride[p][k]) == 1) some = true;
-            }
-            if (some && z.dim[k] > best_len) {
-                best_len = z.dim[k];
+            int64_t score = 0;  // prefer the axis that rescues the most producers, then the longest one
+            for (int p = 1; p < n_parts; ++p)
+                if (dense_along(p, k)) score += ((int64_t)1 << 40) / llabs(z.stride[p][k]);
+            if (score > 0) score += z.dim[k];
+            if (score > best_score) {
+                best_score = score;
                 best_axis = k;
             }
         }
-        if (best_axis >= 0 && best_len >= 16 && z.dim[inner] >= 16) {
+        if (best_axis >= 0 && z.dim[best_axis] >= 16 && z.dim[inner] >= 16) {
             uint32_t mask = 0;
             int staged = 0;
             for (int p = 1; p < n_parts; ++p) {
-                if (llabs(z.stride[p][inner]) > 1 && llabs(z.stride[p][best_axis]) == 1) {
+                if (dense_along(p, best_axis)) {
                     mask |= 1u << p;
                     ++staged;
                 }

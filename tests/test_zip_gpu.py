@@ -130,6 +130,13 @@ VIEW_CASES = {
     "short_inner": ((5000, 3), ident, [((3, 5000), lambda a: a.T), ((5000, 3), ident)]),
     "long_rows": ((3, 40000), ident, [((3, 40000), lambda a: a[::-1]), ((3, 80000), lambda a: a[:, ::2])]),
     "tile_ragged": ((67, 129), ident, [((129, 67), lambda a: a.T), ((67, 129), ident)]),
+    "tile_step2": ((70, 80), ident, [((80, 140), lambda a: a.T[::2]), ((70, 80), ident)]),
+    "tile_step_neg2": ((70, 80), ident, [((80, 140), lambda a: a.T[::-2]), ((70, 80), ident)]),
+    "tile_rev_vec": ((64, 128), ident, [((128, 64), lambda a: a.T[::-1]), ((64, 128), ident)]),
+    "tile_3d_step": ((32, 20, 64), ident, [((64, 20, 64), lambda a: a.transpose(2, 1, 0)[::-2]), ((32, 20, 64), ident)]),
+    "tile_vec_step2": ((64, 128), ident, [((128, 128), lambda a: a.T[::2]), ((64, 128), ident)]),
+    "tile_vec_step_neg2": ((64, 128), ident, [((128, 128), lambda a: a.T[::-2]), ((64, 128), ident)]),
+    "tile_vec_two_staged": ((64, 128), ident, [((128, 128), lambda a: a.T[::-2]), ((128, 64), lambda a: a.T)]),
     "tile_reversed_dense_axis": ((70, 80), ident, [((80, 70), lambda a: a.T[::-1]), ((70, 80), ident)]),
 }
 
