@@ -192,6 +192,26 @@ def cpu_baseline_sample(budget_s=20.0):
             "sample": f"f32 {n}^3 views (same three Zips), {reps} passes in {dt:.1f} s, oracle/ndarray_oracle.cpp with OpenMP"}
 
 
+def bind_to_gpu_numa_node(local: int) -> None:
+    """Pin this process to the CPUs local to its GPU (PCIe root) so pinned host buffers are first-touched on that
+    NUMA node; only matters for the end-to-end (H2D/D2H) leg when several ranks share the host."""
+    try:
+        import pynvml as nv
+        nv.nvmlInit()
+        bus = nv.nvmlDeviceGetPciInfo(nv.nvmlDeviceGetHandleByIndex(local)).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        path = Path("/sys/bus/pci/devices") / bus.lower()[-12:] / "local_cpulist"
+        cpus = set()
+        for part in path.read_text().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = os.sched_getaffinity(0)
+        if cpus & allowed:
+            os.sched_setaffinity(0, cpus & allowed)
+    except Exception:
+        pass
+
+
 # -------------------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
@@ -216,6 +236,7 @@ def main():
     from ndarray_b200 import Array, Zip, s_, Op, Axis
     from ndarray_b200._ffi import View, lib, check
 
+    bind_to_gpu_numa_node(local)  # pinned staging buffers should live on the socket the GPU hangs off
     dist = None
     if world > 1:
         import torch.distributed as dist

@@ -52,6 +52,19 @@ def main():
                 continue
             med, best = timeit(ctx, fn)
             print(f"  {name:24s} {med*1e3:8.1f} us  {nbytes/med/1e6:8.1f} GB/s (best {nbytes/best/1e6:8.1f})")
+    # C1-size reductions, cold L2 (four 64 MiB arrays in rotation), preallocated output
+    import ctypes as C
+    from ndarray_b200._ffi import lib, check
+    arrs = [Array.zeros((4096, 4096), np.float32) for _ in range(4)]
+    o = Array.zeros((4096,), np.float32)
+    cnt = [0]
+    for ax in (0, 1):
+        def fn(ax=ax):
+            cnt[0] += 1
+            check(lib().ndb_reduce_axis(ctx.handle, 0, ax, C.byref(arrs[cnt[0] % 4].v), C.byref(o.v), 0.0))
+        med, best = timeit(ctx, fn, 40, 4)
+        print(f"  COLD sum_axis{ax} f32 4096^2 into: {med*1e3:8.1f} us {4096*4096*4/med/1e6:8.1f} GB/s")
+    del arrs
     # reductions at C1 size with preallocated outputs
     a = Array.zeros((4096, 4096), np.float32)
     for ax in (0, 1):

@@ -790,7 +790,9 @@ static int reduce_axis_launch(ndb_ctx *ctx, RedArgs &a, const ZipPlan &z)
         const int64_t total = tiles * (a.n_out / ncol);
         // enough blocks to fill the machine ~4 deep, but every split keeps >= 64 rows
         // blocks per SM to aim for: measured best 8 for the plain reducers, 6 for Welford (72 registers: 3 CTAs/SM, two waves)
-        const int per_sm = getenv("NDB_RED_COLS_PER_SM") ? atoi(getenv("NDB_RED_COLS_PER_SM")) : (R == R_WELFORD ? 6 : 8);
+        // (a problem that one wave of 4 CTAs/SM covers - e.g. 4096^2 f32 - is fastest as exactly that one wave)
+        const bool small = (double)a.n * (double)a.n_out * sizeof(T) <= 128.0 * 1024 * 1024;
+        const int per_sm = getenv("NDB_RED_COLS_PER_SM") ? atoi(getenv("NDB_RED_COLS_PER_SM")) : (small ? 4 : (R == R_WELFORD ? 6 : 8));
         int64_t want = ((int64_t)ctx->sm_count * per_sm + total - 1) / total;
         int64_t max_splits = std::max<int64_t>(1, a.n / 64);
         int splits = (int)std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(want, max_splits), 256));
