@@ -621,6 +621,101 @@ __global__ void __launch_bounds__(256) dot_partials_vec(const T *x, const T *y, 
     if (threadIdx.x == 0) reinterpret_cast<Acc<T, R_SUM> *>(partial)[blockIdx.x] = acc;
 }
 
+// Fused Zip + reduction over two dense, 16-byte aligned producers: reduce_R(op(x[i], y[i])).  This is the flat case
+// of Zip::all / Zip::any (predicate op, MIN / MAX) and of an additive Zip::fold (arithmetic op, SUM): no scratch array.
+template <typename T, int OP, int R>
+__global__ void __launch_bounds__(256) zip2_reduce_flat(const T *x, const T *y, int64_t n, void *partial)
+{
+    using V = Vec128<T>;
+    constexpr int N = V::N;
+    __shared__ Acc<T, R> smem[32];
+    Acc<T, R> acc;
+    acc.reset();
+    const V *vx = reinterpret_cast<const V *>(x), *vy = reinterpret_cast<const V *>(y);
+    const int64_t nv = n / N;
+    const int64_t stride = (int64_t)gridDim.x * 256;
+    int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    for (; i + 3 * stride < nv; i += 4 * stride) {
+        V a[4], b[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            a[u] = vx[i + u * stride];
+            b[u] = vy[i + u * stride];
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+            for (int e = 0; e < N; ++e) {
+                const T in[2] = {a[u].v[e], b[u].v[e]};
+                acc.add(apply_op<T, OP, 2>(in, T(0), T(0), nullptr));
+            }
+    }
+    for (; i < nv; i += stride) {
+        const V a = vx[i], b = vy[i];
+#pragma unroll
+        for (int e = 0; e < N; ++e) {
+            const T in[2] = {a.v[e], b.v[e]};
+            acc.add(apply_op<T, OP, 2>(in, T(0), T(0), nullptr));
+        }
+    }
+    if (blockIdx.x == 0) {  // ragged tail
+        const int64_t t = nv * N + threadIdx.x;
+        if (t < n) {
+            const T in[2] = {x[t], y[t]};
+            acc.add(apply_op<T, OP, 2>(in, T(0), T(0), nullptr));
+        }
+    }
+    acc = block_reduce(acc, smem);
+    if (threadIdx.x == 0) reinterpret_cast<Acc<T, R> *>(partial)[blockIdx.x] = acc;
+}
+
+template <typename T, int OP, int R>
+static int zip2_reduce_launch(ndb_ctx *ctx, const void *x, const void *y, int64_t n, void *out_host)
+{
+    const int max_blocks = ctx->sm_count * 8;
+    NDB_TRY(ensure_workspace(ctx, (size_t)max_blocks * sizeof(Acc<T, R>) + 4096));
+    void *dev_scalar = (char *)ctx->workspace + ctx->workspace_bytes - 64;
+    const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>(max_blocks, (n / Vec128<T>::N + 1023) / 1024));
+    zip2_reduce_flat<T, OP, R><<<blocks, 256, 0, ctx->stream>>>((const T *)x, (const T *)y, n, ctx->workspace);
+    NDB_CHECK_LAUNCH();
+    red_all_finish<T, R><<<1, 256, 0, ctx->stream>>>(ctx->workspace, blocks, (T *)dev_scalar, T(1), 0);
+    NDB_CHECK_LAUNCH();
+    NDB_CUDA(cudaMemcpyAsync(ctx->host_scalar, dev_scalar, sizeof(T), cudaMemcpyDeviceToHost, ctx->stream));
+    NDB_CUDA(cudaStreamSynchronize(ctx->stream));
+    memcpy(out_host, ctx->host_scalar, sizeof(T));
+    return NDB_OK;
+}
+
+template <typename T>
+static int zip2_reduce_typed(ndb_ctx *ctx, int op, int redop, const void *x, const void *y, int64_t n, void *out_host)
+{
+#define NDB_Z2R(OPC, RC, RT) \
+    if (op == OPC && redop == RC) return zip2_reduce_launch<T, OPC, RT>(ctx, x, y, n, out_host);
+    NDB_Z2R(NDB_OP_MUL, NDB_RED_SUM, R_SUM)
+    NDB_Z2R(NDB_OP_ADD, NDB_RED_SUM, R_SUM)
+    NDB_Z2R(NDB_OP_SUB, NDB_RED_SUM, R_SUM)
+    NDB_Z2R(NDB_OP_EQ, NDB_RED_MIN, R_MIN) NDB_Z2R(NDB_OP_EQ, NDB_RED_MAX, R_MAX)
+    NDB_Z2R(NDB_OP_NE, NDB_RED_MIN, R_MIN) NDB_Z2R(NDB_OP_NE, NDB_RED_MAX, R_MAX)
+    NDB_Z2R(NDB_OP_LT, NDB_RED_MIN, R_MIN) NDB_Z2R(NDB_OP_LT, NDB_RED_MAX, R_MAX)
+    NDB_Z2R(NDB_OP_LE, NDB_RED_MIN, R_MIN) NDB_Z2R(NDB_OP_LE, NDB_RED_MAX, R_MAX)
+    NDB_Z2R(NDB_OP_GT, NDB_RED_MIN, R_MIN) NDB_Z2R(NDB_OP_GT, NDB_RED_MAX, R_MAX)
+    NDB_Z2R(NDB_OP_GE, NDB_RED_MIN, R_MIN) NDB_Z2R(NDB_OP_GE, NDB_RED_MAX, R_MAX)
+#undef NDB_Z2R
+    return NDB_ERR_UNSUPPORTED;  // the caller falls back to scratch + reduction
+}
+
+// returns NDB_ERR_UNSUPPORTED (without setting an error) when no fused kernel exists for (op, redop)
+int zip2_reduce_dense(ndb_ctx *ctx, int op, int redop, int dtype, const void *x, const void *y, int64_t n, void *out_host)
+{
+    switch (dtype) {
+    case NDB_F32: return zip2_reduce_typed<float>(ctx, op, redop, x, y, n, out_host);
+    case NDB_F64: return zip2_reduce_typed<double>(ctx, op, redop, x, y, n, out_host);
+    case NDB_I32: return zip2_reduce_typed<int32_t>(ctx, op, redop, x, y, n, out_host);
+    case NDB_I64: return zip2_reduce_typed<int64_t>(ctx, op, redop, x, y, n, out_host);
+    }
+    return NDB_ERR_UNSUPPORTED;
+}
+
 // ======================================================================================================
 // host side
 

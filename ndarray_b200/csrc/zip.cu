@@ -106,6 +106,16 @@ static int zip_then_reduce(ndb_ctx *ctx, int op, const void *scalars, int n_inpu
         return NDB_OK;
     }
     DeviceGuard g(ctx->device);
+    if (n_inputs == 2 && !scalars) {
+        // both producers dense, identically laid out and aligned: one fused pass, no scratch
+        ndb_view two[2] = {inputs[0], inputs[1]};
+        ZipPlan z;
+        if (make_zip_plan(NDB_OP_COPY, 2, two, &z) == NDB_OK && z.kernel == NDB_KERNEL_FLAT_VEC) {
+            const int st = zip2_reduce_dense(ctx, op, redop, out.dtype, z.ptr[0], z.ptr[1], z.total, out_host);
+            if (st != NDB_ERR_UNSUPPORTED) return st;
+        }
+        clear_error();
+    }
     void *tmp = nullptr;
     NDB_CUDA(cudaMallocAsync(&tmp, (size_t)total * dtype_size(out.dtype), ctx->stream));
     out.ptr = tmp;

@@ -503,3 +503,30 @@ def test_zip_host_chunked_pipeline(nd, oracle):
     parts = (View * 3)(hview(outbuf[:, :, ::2]), hview(xv), hview(yv))
     check(lib().ndb_zip_host(nd.default_context().handle, OP["SUB"], None, 3, parts))
     assert_bit_equal(outbuf, want, "chunked host path")
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64, np.int32, np.int64])
+def test_fused_all_any_fold_paths_agree(nd, dtype):
+    """Zip::all / any / fold on dense operands take the fused kernel, on strided ones the scratch path: same answers."""
+    from ndarray_b200 import Array, Zip, Op
+    rng = np.random.default_rng(41)
+    n = 300007
+    h1 = rand(rng, (n,), dtype)
+    h2 = h1.copy()
+    h2[n - 3] = h2[n - 3] + np.dtype(dtype).type(1)
+    big1, big2 = np.zeros(2 * n, dtype), np.zeros(2 * n, dtype)
+    big1[::2], big2[::2] = h1, h2
+    for dense in (True, False):
+        a = Array.from_numpy(h1) if dense else Array.from_numpy(big1).slice(nd.s_[::2])
+        b = Array.from_numpy(h2) if dense else Array.from_numpy(big2).slice(nd.s_[::2])
+        assert not Zip.from_(a).and_(b).all(Op.EQ) and Zip.from_(a).and_(a).all(Op.EQ)
+        assert Zip.from_(a).and_(b).any(Op.NE) and not Zip.from_(a).and_(a).any(Op.NE)
+        assert Zip.from_(a).and_(b).all(Op.LE) and not Zip.from_(a).and_(b).all(Op.GE)
+        if np.dtype(dtype).kind == "i":
+            with np.errstate(over="ignore"):
+                assert Zip.from_(a).and_(b).fold_sum(Op.MUL) == (h1 * h2).sum(dtype=dtype)
+                assert Zip.from_(a).and_(b).fold_sum(Op.SUB) == (h1 - h2).sum(dtype=dtype)
+        else:
+            want = float((h1.astype(np.float64) * h2.astype(np.float64)).sum())
+            tol = (1e-5 if dtype == np.float32 else 1e-12) * np.sqrt(n) * float(np.abs(h1 * h2).max())
+            assert abs(float(Zip.from_(a).and_(b).fold_sum(Op.MUL)) - want) <= tol
