@@ -273,6 +273,9 @@ int ndb_welford_merge(ndb_ctx *ctx, int n_shards, const int64_t *counts, const n
                       double ddof, int want_std, const ndb_view *out);
 /* ArrayRef::var / std over every element (src/numeric/impl_numeric.rs:180-249), result to host (floats only). */
 int ndb_var(ndb_ctx *ctx, const ndb_view *in, double ddof, int want_std, void *out_host);
+/* accumulate_axis_inplace (src/impl_methods.rs:3243) with op NDB_OP_ADD (running sum) or NDB_OP_MUL (cumprod,
+ * src/numeric/impl_numeric.rs:125): v[.., i, ..] = op(v[.., i-1, ..], v[.., i, ..]) along `axis`, in place, one launch. */
+int ndb_accumulate_axis(ndb_ctx *ctx, int op, int axis, const ndb_view *v);
 /* 1-D dot product (src/linalg/impl_linalg.rs:74-133, numeric_util.rs:56), result to host. */
 int ndb_dot(ndb_ctx *ctx, const ndb_view *x, const ndb_view *y, void *out_host);
 

@@ -113,6 +113,7 @@ def lib():
         "ndb_reduce_axis": (i32, [vp, i32, i32, PV, PV, dbl]),
         "ndb_welford_axis": (i32, [vp, i32, PV, PV, PV]),
         "ndb_welford_merge": (i32, [vp, i32, C.POINTER(i64), PV, PV, dbl, i32, PV]),
+        "ndb_accumulate_axis": (i32, [vp, i32, i32, PV]),
         "ndb_dot": (i32, [vp, PV, PV, vp]),
         "ndb_gemm": (i32, [vp, vp, PV, PV, vp, PV]),
         "ndb_gemv": (i32, [vp, vp, PV, PV, vp, PV]),

@@ -662,14 +662,12 @@ class Array:
         return inp
 
     def accumulate_axis_inplace(self, axis, op: int) -> None:
-        """accumulate_axis_inplace (src/impl_methods.rs:3243): a[i] = op(a[i-1], a[i]) along `axis`, in axis order —
-        one Zip over the two adjacent subviews per step, the same sequence of elementwise passes ndarray performs."""
+        """accumulate_axis_inplace (src/impl_methods.rs:3243): a[i] = op(a[i-1], a[i]) along `axis` (op = Op.ADD or
+        Op.MUL), one scan launch."""
         axis = int(axis)
         if not 0 <= axis < self.ndim:
             raise _ffi.NdbError(_ffi.ERR_OOB, f"axis {axis} is out of bounds for array of dimension {self.ndim}")
-        for i in range(1, self.shape[axis]):
-            prev, cur = self.index_axis(axis, i - 1), self.index_axis(axis, i)
-            _zip_call(self.ctx, op, cur, [prev, cur])
+        check(lib().ndb_accumulate_axis(self.ctx.handle, op, axis, C.byref(self.v)))
 
     def cumprod(self, axis) -> "Array":
         """cumprod (src/numeric/impl_numeric.rs:125)."""

@@ -1,0 +1,164 @@
+// accumulate_axis_inplace (src/impl_methods.rs:3243) / cumprod (src/numeric/impl_numeric.rs:125) as a scan:
+//   a[.., i, ..] = op(a[.., i-1, ..], a[.., i, ..])   for i = 1 .. n-1 along `axis`, in place.
+// ndarray walks the axis sequentially with one elementwise pass per step.  Here:
+//   scan_cols   a kept axis is the dense one: a thread owns one lane and walks the scanned axis sequentially (exactly
+//               ndarray's association, so results are bit-identical for floats too); neighbouring threads touch
+//               neighbouring addresses, every step is coalesced.
+//   scan_lanes  the scanned axis is the dense one: a warp owns a lane and scans it 32 elements at a time with shuffles
+//               plus a running carry (coalesced; the association differs, so floats agree to rounding, integers exactly).
+#include "zip_kernels.cuh"
+#include "zip_plan.h"
+
+namespace ndb {
+
+namespace {
+
+struct ScanArgs {
+    char *base;
+    int n_kept;
+    int64_t kdim[NDB_MAX_NDIM], kstride[NDB_MAX_NDIM];
+    int64_t n_lanes;
+    int64_t n, s;  // scanned axis: length and stride (elements)
+};
+
+template <typename T, bool MUL>
+__device__ __forceinline__ T comb(T a, T b)
+{
+    return MUL ? w_mul(a, b) : w_add(a, b);
+}
+
+__device__ __forceinline__ int64_t lane_offset(const ScanArgs &a, int64_t lin)
+{
+    int64_t off = 0;
+    for (int d = a.n_kept - 1; d >= 0; --d) {
+        const int64_t q = lin / a.kdim[d];
+        off += (lin - q * a.kdim[d]) * a.kstride[d];
+        lin = q;
+    }
+    return off;
+}
+
+template <typename T, bool MUL>
+__global__ void __launch_bounds__(256) scan_cols(ScanArgs a)
+{
+    const int64_t lane = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (lane >= a.n_lanes) return;
+    T *p = reinterpret_cast<T *>(a.base) + lane_offset(a, lane);
+    T acc = p[0];
+    int64_t i = 1;
+    for (; i + 3 < a.n; i += 4) {  // four independent loads in flight, combined in order
+        const T x0 = p[i * a.s], x1 = p[(i + 1) * a.s], x2 = p[(i + 2) * a.s], x3 = p[(i + 3) * a.s];
+        acc = comb<T, MUL>(acc, x0);
+        p[i * a.s] = acc;
+        acc = comb<T, MUL>(acc, x1);
+        p[(i + 1) * a.s] = acc;
+        acc = comb<T, MUL>(acc, x2);
+        p[(i + 2) * a.s] = acc;
+        acc = comb<T, MUL>(acc, x3);
+        p[(i + 3) * a.s] = acc;
+    }
+    for (; i < a.n; ++i) {
+        acc = comb<T, MUL>(acc, p[i * a.s]);
+        p[i * a.s] = acc;
+    }
+}
+
+template <typename T, bool MUL>
+__global__ void __launch_bounds__(256) scan_lanes(ScanArgs a)
+{
+    const int lane_id = threadIdx.x & 31;
+    const int64_t lane = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (lane >= a.n_lanes) return;
+    T *p = reinterpret_cast<T *>(a.base) + lane_offset(a, lane);
+    T carry = MUL ? T(1) : T(0);
+    for (int64_t i0 = 0; i0 < a.n; i0 += 32) {
+        const int64_t i = i0 + lane_id;
+        const bool live = i < a.n;
+        T v = live ? p[i * a.s] : (MUL ? T(1) : T(0));
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const T up = __shfl_up_sync(0xffffffffu, v, d);
+            if (lane_id >= d) v = comb<T, MUL>(up, v);
+        }
+        v = comb<T, MUL>(carry, v);
+        if (live) p[i * a.s] = v;
+        carry = __shfl_sync(0xffffffffu, v, 31);
+    }
+}
+
+template <typename T>
+int scan_dispatch(ndb_ctx *ctx, int op, const ScanArgs &a, bool lanes)
+{
+    const bool mul = op == NDB_OP_MUL;
+    if (lanes) {
+        const unsigned blocks = (unsigned)((a.n_lanes + 7) / 8);
+        if (mul) scan_lanes<T, true><<<blocks, 256, 0, ctx->stream>>>(a);
+        else scan_lanes<T, false><<<blocks, 256, 0, ctx->stream>>>(a);
+    } else {
+        const unsigned blocks = (unsigned)((a.n_lanes + 255) / 256);
+        if (mul) scan_cols<T, true><<<blocks, 256, 0, ctx->stream>>>(a);
+        else scan_cols<T, false><<<blocks, 256, 0, ctx->stream>>>(a);
+    }
+    NDB_CHECK_LAUNCH();
+    return NDB_OK;
+}
+
+}  // namespace
+
+}  // namespace ndb
+
+using namespace ndb;
+
+extern "C" int ndb_accumulate_axis(ndb_ctx *ctx, int op, int axis, const ndb_view *v)
+{
+    clear_error();
+    if (!ctx) {
+        set_error("accumulate_axis: null context (no CPU fallback exists)");
+        return NDB_ERR_INVALID_ARG;
+    }
+    NDB_TRY(validate_view(v, "accumulate_axis"));
+    if (op != NDB_OP_ADD && op != NDB_OP_MUL) {
+        set_error("accumulate_axis: op must be NDB_OP_ADD (running sum) or NDB_OP_MUL (cumprod)");
+        return NDB_ERR_UNSUPPORTED;
+    }
+    if (axis < 0 || axis >= v->ndim) {
+        set_error("axis %d is out of bounds for array of dimension %d", axis, v->ndim);
+        return NDB_ERR_OUT_OF_BOUNDS;
+    }
+    const int64_t n = v->dim[axis];
+    for (int i = 0; i < v->ndim; ++i)
+        if (v->dim[i] == 0) return NDB_OK;
+    if (n <= 1) return NDB_OK;
+    // collapse the kept axes of the (written) view with the Zip planner: checks self-aliasing, flips, merges
+    ndb_view kept = *v;
+    for (int i = axis; i + 1 < v->ndim; ++i) {
+        kept.dim[i] = v->dim[i + 1];
+        kept.stride[i] = v->stride[i + 1];
+    }
+    kept.ndim = v->ndim - 1;
+    ndb_view parts[2] = {kept, kept};
+    ZipPlan z;
+    NDB_TRY(make_zip_plan(NDB_OP_COPY, 2, parts, &z));
+    ScanArgs a;
+    memset(&a, 0, sizeof(a));
+    a.base = z.ptr[0];
+    a.n_kept = z.ndim;
+    a.n_lanes = z.total;
+    int64_t min_kept = INT64_MAX;
+    for (int d = 0; d < z.ndim; ++d) {
+        a.kdim[d] = z.dim[d];
+        a.kstride[d] = z.stride[0][d];
+        if (z.dim[d] > 1) min_kept = std::min<int64_t>(min_kept, llabs(z.stride[0][d]));
+    }
+    a.n = n;
+    a.s = v->stride[axis];
+    const bool lanes = a.n_lanes == 1 || llabs(a.s) < min_kept;
+    DeviceGuard g(ctx->device);
+    switch (v->dtype) {
+    case NDB_F32: return scan_dispatch<float>(ctx, op, a, lanes);
+    case NDB_F64: return scan_dispatch<double>(ctx, op, a, lanes);
+    case NDB_I32: return scan_dispatch<int32_t>(ctx, op, a, lanes);
+    case NDB_I64: return scan_dispatch<int64_t>(ctx, op, a, lanes);
+    }
+    return NDB_ERR_UNSUPPORTED;
+}
