@@ -18,6 +18,18 @@ pub struct ndb_view {
 #[repr(C)]
 pub struct ndb_ctx { _private: [u8; 0] }
 
+/// mirrors `ndb_zip_plan_t` (include/ndb200.h): what the planner decided for a Zip
+#[repr(C)]
+pub struct ndb_zip_plan_t {
+    pub kernel: i32,
+    pub ndim: i32,
+    pub dim: [i64; NDB_MAX_NDIM],
+    pub stride: [[i64; NDB_MAX_NDIM]; NDB_MAX_PARTS],
+    pub offset: [i64; NDB_MAX_PARTS],
+    pub tile_axis: i32,
+    pub staged_mask: u32,
+}
+
 pub const NDB_OK: c_int = 0;
 pub const NDB_ERR_INCOMPATIBLE_SHAPE: c_int = 1;
 pub const NDB_ERR_EMPTY: c_int = 8;
@@ -45,4 +57,39 @@ extern "C" {
     pub fn ndb_dot(ctx: *mut ndb_ctx, x: *const ndb_view, y: *const ndb_view, out_host: *mut c_void) -> c_int;
     pub fn ndb_gemm(ctx: *mut ndb_ctx, alpha: *const c_void, a: *const ndb_view, b: *const ndb_view, beta: *const c_void, c: *const ndb_view) -> c_int;
     pub fn ndb_gemv(ctx: *mut ndb_ctx, alpha: *const c_void, a: *const ndb_view, x: *const ndb_view, beta: *const c_void, y: *const ndb_view) -> c_int;
+    pub fn ndb_launch_count() -> u64;
+    pub fn ndb_device_count(count: *mut c_int) -> c_int;
+    pub fn ndb_ctx_set_stream(ctx: *mut ndb_ctx, cuda_stream: *mut c_void) -> c_int;
+    pub fn ndb_ctx_stream(ctx: *mut ndb_ctx) -> *mut c_void;
+    pub fn ndb_d2d(ctx: *mut ndb_ctx, dst: *mut c_void, src: *const c_void, bytes: size_t) -> c_int;
+    pub fn ndb_host_alloc(bytes: size_t, hptr: *mut *mut c_void) -> c_int;
+    pub fn ndb_host_free(hptr: *mut c_void) -> c_int;
+    pub fn ndb_event_create(ev: *mut *mut c_void) -> c_int;
+    pub fn ndb_event_destroy(ev: *mut c_void) -> c_int;
+    pub fn ndb_event_record(ctx: *mut ndb_ctx, ev: *mut c_void) -> c_int;
+    pub fn ndb_event_elapsed_ms(start: *mut c_void, stop: *mut c_void, ms: *mut f32) -> c_int;
+    pub fn ndb_view_index_axis(v: *mut ndb_view, axis: c_int, index: i64) -> c_int;
+    pub fn ndb_view_merge_axes(v: *mut ndb_view, take: c_int, into: c_int) -> c_int;
+    pub fn ndb_view_collapse_axis(v: *mut ndb_view, axis: c_int, index: i64) -> c_int;
+    pub fn ndb_view_layout(v: *const ndb_view) -> u32;
+    pub fn ndb_view_is_contiguous(v: *const ndb_view) -> c_int;
+    pub fn ndb_view_min_stride_axis(v: *const ndb_view) -> c_int;
+    pub fn ndb_cast(ctx: *mut ndb_ctx, out: *const ndb_view, input: *const ndb_view) -> c_int;
+    pub fn ndb_zip_plan(op: c_int, n_parts: c_int, parts: *const ndb_view, plan: *mut ndb_zip_plan_t) -> c_int;
+    pub fn ndb_zip_all(ctx: *mut ndb_ctx, op: c_int, scalars: *const c_void, n_inputs: c_int, inputs: *const ndb_view, result: *mut c_int) -> c_int;
+    pub fn ndb_zip_any(ctx: *mut ndb_ctx, op: c_int, scalars: *const c_void, n_inputs: c_int, inputs: *const ndb_view, result: *mut c_int) -> c_int;
+    pub fn ndb_zip_fold_sum(ctx: *mut ndb_ctx, op: c_int, scalars: *const c_void, n_inputs: c_int, inputs: *const ndb_view, out_host: *mut c_void) -> c_int;
+    pub fn ndb_zip_host(ctx: *mut ndb_ctx, op: c_int, scalars: *const c_void, n_parts: c_int, parts: *const ndb_view) -> c_int;
+    pub fn ndb_reduce_all_dev(ctx: *mut ndb_ctx, redop: c_int, input: *const ndb_view, out_dev: *mut c_void) -> c_int;
+    pub fn ndb_welford_axis(ctx: *mut ndb_ctx, axis: c_int, input: *const ndb_view, mean_out: *const ndb_view, m2_out: *const ndb_view) -> c_int;
+    pub fn ndb_welford_merge(ctx: *mut ndb_ctx, n_shards: c_int, counts: *const i64, means: *const ndb_view, m2s: *const ndb_view, ddof: c_double, want_std: c_int, out: *const ndb_view) -> c_int;
+    pub fn ndb_var(ctx: *mut ndb_ctx, input: *const ndb_view, ddof: c_double, want_std: c_int, out_host: *mut c_void) -> c_int;
+    pub fn ndb_accumulate_axis(ctx: *mut ndb_ctx, op: c_int, axis: c_int, v: *const ndb_view) -> c_int;
+    // ndarray's own CBLAS boundary (src/linalg/impl_linalg.rs:466-491, :116-122); normally bound through cblas-sys
+    pub fn cblas_sgemm(layout: c_int, transa: c_int, transb: c_int, m: c_int, n: c_int, k: c_int, alpha: f32, a: *const f32, lda: c_int, b: *const f32, ldb: c_int, beta: f32, c: *mut f32, ldc: c_int);
+    pub fn cblas_dgemm(layout: c_int, transa: c_int, transb: c_int, m: c_int, n: c_int, k: c_int, alpha: f64, a: *const f64, lda: c_int, b: *const f64, ldb: c_int, beta: f64, c: *mut f64, ldc: c_int);
+    pub fn cblas_sgemv(layout: c_int, trans: c_int, m: c_int, n: c_int, alpha: f32, a: *const f32, lda: c_int, x: *const f32, incx: c_int, beta: f32, y: *mut f32, incy: c_int);
+    pub fn cblas_dgemv(layout: c_int, trans: c_int, m: c_int, n: c_int, alpha: f64, a: *const f64, lda: c_int, x: *const f64, incx: c_int, beta: f64, y: *mut f64, incy: c_int);
+    pub fn cblas_sdot(n: c_int, x: *const f32, incx: c_int, y: *const f32, incy: c_int) -> f32;
+    pub fn cblas_ddot(n: c_int, x: *const f64, incx: c_int, y: *const f64, incy: c_int) -> f64;
 }

@@ -33,20 +33,39 @@ def rand(rng, shape, dtype, nonzero=False):
     return a
 
 
+GUARD = 64  # guard elements either side of every mirrored buffer (compute-sanitizer is not available on the GPU pool)
+
+
 class Mirror:
-    """A host buffer and its device copy; views are taken on both with the same geometry."""
+    """A host buffer and its device copy; views are taken on both with the same geometry.  The device copy sits between
+    two guard bands holding a sentinel; `download` fails if a kernel wrote outside the buffer."""
 
     def __init__(self, nd, host: np.ndarray):
         self.nd = nd
         self.host = np.array(host, copy=True, order="C")
-        self.dev = nd.Array.from_numpy(self.host)
+        self.upload()
+
+    def upload(self):
+        flat = self.host.reshape(-1)
+        padded = np.empty(flat.size + 2 * GUARD, dtype=self.host.dtype)
+        padded.view(np.uint8)[...] = 0x5A
+        padded[GUARD:GUARD + flat.size] = flat
+        self.padded_dev = self.nd.Array.from_numpy(padded)
+        # the device array the tests see: same shape/strides as the host buffer, inside the guards
+        self.dev = self.padded_dev.raw_view_with(GUARD, self.host.shape, [st // self.host.itemsize for st in self.host.strides])
 
     def view(self, fn):
         hv = fn(self.host)
-        return hv, device_view_of(self.nd, self.dev, self.host, hv)
+        item = self.host.itemsize
+        off = (hv.__array_interface__["data"][0] - self.host.__array_interface__["data"][0]) // item
+        return hv, self.padded_dev.raw_view_with(GUARD + off, hv.shape, [st // item for st in hv.strides])
 
     def download(self):
-        return self.dev.to_numpy()
+        padded = self.padded_dev.to_numpy()
+        g = padded.view(np.uint8)
+        gb = GUARD * self.host.itemsize
+        assert (g[:gb] == 0x5A).all() and (g[g.size - gb:] == 0x5A).all(), "kernel wrote outside the buffer (guard band hit)"
+        return padded[GUARD:GUARD + self.host.size].reshape(self.host.shape)
 
 
 def run_case(nd, oracle, opname, dtype, shape, out_fn, in_fns, rng, scalars=None):
@@ -59,7 +78,7 @@ def run_case(nd, oracle, opname, dtype, shape, out_fn, in_fns, rng, scalars=None
     if opname == "SQRT":
         for m in mins:
             m.host[...] = np.abs(m.host)
-            m.dev = nd.Array.from_numpy(m.host)
+            m.upload()
     ho, do = mo.view(out_fn)
     hins, dins = [], []
     for m, fn in zip(mins, in_fns):
