@@ -6,6 +6,7 @@
 // instruction retires 256 FMAs from 4 registers per thread, so the register file and issue slots stop
 // being the limit and a 4-stage cp.async pipeline can keep the pipe fed.
 //
+// This file holds the cp.async-fed kernel (the fallback of gemm_f64_tma.cu, which is ~10 % faster: see its header).
 // Tiling: 128x128x32 block tile (3-stage ring, 216 KB; measured 32.5 vs 31.0 TFLOP/s for 128x128x16 x 4 stages),
 // 256 threads = 8 warps as 2(m) x 4(n), 64x32 warp tile = 8x4 DMMA tiles,
 // 64 accumulator doubles per thread.  Operands are staged with 16-byte cp.async in whichever orientation
@@ -32,11 +33,25 @@ namespace {
 #ifndef NDB_F64_STAGES
 #define NDB_F64_STAGES 3
 #endif
-constexpr int BM = 128, BN = 128, BK = NDB_F64_BK, STAGES = NDB_F64_STAGES, THREADS = 256;
+#ifndef NDB_F64_WARPS_M
+#define NDB_F64_WARPS_M 2
+#endif
+#ifndef NDB_F64_BM
+#define NDB_F64_BM 128
+#endif
+#ifndef NDB_F64_MIN_CTAS
+#define NDB_F64_MIN_CTAS 1
+#endif
+constexpr int BM = NDB_F64_BM, BN = 128, BK = NDB_F64_BK, STAGES = NDB_F64_STAGES;
+constexpr int WARPS_M = NDB_F64_WARPS_M, WARPS_N = 4, THREADS = 32 * WARPS_M * WARPS_N;
+constexpr int MI = BM / (WARPS_M * 8), NJ = BN / (WARPS_N * 8);  // DMMA tiles per warp: 8 x 4 (64x32 warp tile)
+#ifndef NDB_F64_DEBUG
+#define NDB_F64_DEBUG 0  // experiments only (wrong results), bit mask: 1 = no global loads in the main loop, 2 = fragments loaded at kk = 0 only, 4 = no barrier
+#endif
 constexpr int LDK = BK + 4;   // [row][k] layout: 20 doubles per row
-constexpr int LDM = BM + 4;   // [k][row] layout: 132 doubles per k
-constexpr int A_STAGE = (BM * LDK > BK * LDM) ? BM * LDK : BK * LDM;  // doubles
-constexpr int B_STAGE = (BN * LDK > BK * LDM) ? BN * LDK : BK * LDM;
+constexpr int LDMA = BM + 4, LDMB = BN + 4;  // [k][row] layout: 132 doubles per k
+constexpr int A_STAGE = (BM * LDK > BK * LDMA) ? BM * LDK : BK * LDMA;  // doubles
+constexpr int B_STAGE = (BN * LDK > BK * LDMB) ? BN * LDK : BK * LDMB;
 constexpr size_t SMEM_BYTES = (size_t)STAGES * (A_STAGE + B_STAGE) * sizeof(double);
 
 struct F64Args {
@@ -59,61 +74,94 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 
 __device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double b)
 {
-    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+    asm volatile(
+        "mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
                  : "+d"(c0), "+d"(c1)
                  : "d"(a), "d"(b));
 }
 
-// Stage one operand tile.  ROWS x BK logical tile of an operand whose logical element (r, k) lives at
-// base[r * ld + k] (K_CONTIG) or base[k * ld + r] (!K_CONTIG).  Out-of-range parts are zero-filled.
-template <bool K_CONTIG>
-__device__ __forceinline__ void load_tile(double *smem, const double *base, int64_t ld, int64_t r0, int64_t k0,
-                                          int64_t rows_total, int64_t k_total, int tid)
-{
-    if constexpr (K_CONTIG) {
-        // 128 rows x BK/2 chunks of 2 doubles
+// Stages one operand tile with 16-byte cp.async, one chunk (2 doubles) at a time so that the main loop can slot single
+// chunks between DMMA groups.  ROWS x BK logical tile of an operand whose logical element (r, k) lives at
+// base[r * ld + k] (K_CONTIG) or base[k * ld + r] (!K_CONTIG); out-of-range parts are zero-filled (src-size < 16).
+// Everything that does not change from one k-tile to the next is computed once per thread: chunk c = tid + i * THREADS
+// sits at a fixed (row, k) offset plus i * istep, so issuing chunk i costs one 64-bit multiply-add and a select.
+template <bool K_CONTIG, int ROWS>
+struct TileLoader {
+    static constexpr int CHUNKS = (ROWS * BK / 2) / THREADS;  // per thread per k-tile
+    static_assert((ROWS * BK / 2) % THREADS == 0, "tile chunks must divide over the threads");
+    static_assert(K_CONTIG ? THREADS % (BK / 2) == 0 : THREADS % (ROWS / 2) == 0, "chunk i must keep its column");
+    const double *base;
+    const double *src;   // chunk 0 of the k-tile to be loaded next
+    int64_t istep;       // elements from chunk i to chunk i + 1
+    int64_t kstep;       // elements from one k-tile to the next
+    int64_t k_left;      // K_CONTIG: k elements left at this thread's k offset; else at chunk 0's k row
+    int smem0;           // element offset of chunk 0 inside a stage
+    uint32_t row_info;   // K_CONTIG: bit i = chunk i's row is inside the matrix; else bytes available along the row (0/8/16)
+
+    __device__ __forceinline__ TileLoader(const double *b, int64_t ld, int64_t r0, int64_t rows_total, int64_t k_total, int tid)
+        : base(b)
+    {
+        if constexpr (K_CONTIG) {
+            const int r = tid / (BK / 2), kc = (tid % (BK / 2)) * 2;
+            src = b + (r0 + r) * ld + kc;
+            istep = (int64_t)(THREADS / (BK / 2)) * ld;
+            kstep = BK;
+            k_left = k_total - kc;
+            smem0 = r * LDK + kc;
+            row_info = 0;
 #pragma unroll
-        for (int i = 0; i < (BM * BK / 2) / THREADS; ++i) {
-            const int c = tid + i * THREADS;
-            const int r = c / (BK / 2), kc = (c % (BK / 2)) * 2;
-            const int64_t gr = r0 + r, gk = k0 + kc;
-            int bytes = 0;
-            if (gr < rows_total && gk < k_total) bytes = (gk + 1 < k_total) ? 16 : 8;
-            const double *src = bytes ? base + gr * ld + gk : base;
-            cp_async16(smem + r * LDK + kc, src, bytes);
-        }
-    } else {
-        // BK k x 64 chunks of 2 doubles
-#pragma unroll
-        for (int i = 0; i < (BM * BK / 2) / THREADS; ++i) {
-            const int c = tid + i * THREADS;
-            const int kk = c >> 6, rc = (c & 63) * 2;
-            const int64_t gk = k0 + kk, gr = r0 + rc;
-            int bytes = 0;
-            if (gk < k_total && gr < rows_total) bytes = (gr + 1 < rows_total) ? 16 : 8;
-            const double *src = bytes ? base + gk * ld + gr : base;
-            cp_async16(smem + kk * LDM + rc, src, bytes);
+            for (int i = 0; i < CHUNKS; ++i)
+                if (r0 + r + i * (THREADS / (BK / 2)) < rows_total) row_info |= 1u << i;
+        } else {
+            const int kk = tid / (ROWS / 2), rc = (tid % (ROWS / 2)) * 2;
+            src = b + (int64_t)kk * ld + r0 + rc;
+            istep = (int64_t)(THREADS / (ROWS / 2)) * ld;
+            kstep = (int64_t)BK * ld;
+            k_left = k_total - kk;
+            smem0 = kk * (ROWS + 4) + rc;
+            const int64_t left = rows_total - (r0 + rc);
+            row_info = left >= 2 ? 16u : left == 1 ? 8u : 0u;
         }
     }
-}
+    // chunk i of the current k-tile into the stage starting at `stage`
+    __device__ __forceinline__ void issue(double *stage, int i) const
+    {
+        int bytes;
+        int soff;
+        if constexpr (K_CONTIG) {
+            bytes = ((row_info >> i) & 1u) ? (k_left >= 2 ? 16 : k_left == 1 ? 8 : 0) : 0;
+            soff = smem0 + i * (THREADS / (BK / 2)) * LDK;
+        } else {
+            bytes = (k_left - i * (THREADS / (ROWS / 2)) > 0) ? (int)row_info : 0;
+            soff = smem0 + i * (THREADS / (ROWS / 2)) * (ROWS + 4);
+        }
+        cp_async16(stage + soff, bytes ? src + i * istep : base, bytes);
+    }
+    __device__ __forceinline__ void next_ktile()
+    {
+        src += kstep;
+        k_left -= BK;
+    }
+};
 
-template <bool K_CONTIG>
+template <bool K_CONTIG, int ROWS>
 __device__ __forceinline__ double frag(const double *smem, int row, int k)
 {
     if constexpr (K_CONTIG) return smem[row * LDK + k];
-    else return smem[k * LDM + row];
+    else return smem[k * (ROWS + 4) + row];
 }
 
 // C (row-major, ldc) <- alpha * A * B + beta * C
 template <bool A_KC, bool B_KC>
-__global__ void __launch_bounds__(THREADS, 1) gemm_f64_dmma(F64Args p)
+__global__ void __launch_bounds__(THREADS, NDB_F64_MIN_CTAS) gemm_f64_dmma(F64Args p)
 {
     extern __shared__ __align__(16) double smem[];
     double *As = smem;
     double *Bs = smem + STAGES * A_STAGE;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = lane >> 2, t = lane & 3;
-    const int wm = warp >> 2, wn = warp & 3;  // 2 x 4 warps
+    const int wm = warp >> 2, wn = warp & 3;  // WARPS_M x 4 warps
+    constexpr int WTM = MI * 8, WTN = NJ * 8;
 
     // rasterise in groups of 8 tile-rows so that concurrently resident blocks share A and B panels in L2
     constexpr int GROUP = 8;
@@ -127,60 +175,89 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_f64_dmma(F64Args p)
     const int tile_n = in_grp / gsize;
     const int64_t m0 = (int64_t)tile_m * BM, n0 = (int64_t)tile_n * BN;
 
-    double acc[8][4][2];
+    double acc[MI][NJ][2];
 #pragma unroll
-    for (int i = 0; i < 8; ++i)
+    for (int i = 0; i < MI; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+        for (int j = 0; j < NJ; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
     const int ktiles = (int)((p.k + BK - 1) / BK);
+    TileLoader<A_KC, BM> la(p.a, p.lda, m0, p.m, p.k, tid);
+    TileLoader<B_KC, BN> lb(p.b, p.ldb, n0, p.n, p.k, tid);
+    constexpr int NA = TileLoader<A_KC, BM>::CHUNKS, NB = TileLoader<B_KC, BN>::CHUNKS;
     // prologue
 #pragma unroll
     for (int s = 0; s < STAGES - 1; ++s) {
         if (s < ktiles) {
-            load_tile<A_KC>(As + s * A_STAGE, p.a, p.lda, m0, (int64_t)s * BK, p.m, p.k, tid);
-            load_tile<B_KC>(Bs + s * B_STAGE, p.b, p.ldb, n0, (int64_t)s * BK, p.n, p.k, tid);
+#pragma unroll
+            for (int c = 0; c < NA; ++c) la.issue(As + s * A_STAGE, c);
+#pragma unroll
+            for (int c = 0; c < NB; ++c) lb.issue(Bs + s * B_STAGE, c);
+            la.next_ktile();
+            lb.next_ktile();
         }
         cp_async_commit();
     }
+    // The two warps of an SM sub-partition leave the barrier together, so anything both of them do between DMMAs idles
+    // the tensor pipe (measured: the block of 16 cp.async per thread with its address arithmetic cost 8 %).  The refill
+    // of the stage freed by the barrier is therefore cut into single chunks, one after every SLOT-th group of NJ DMMAs,
+    // where it disappears in the 16-cycle issue shadow of the DMMA in front of it.
+    constexpr int GROUPS = (BK / 4) * MI;  // DMMA row groups per k-tile
+    constexpr int SLOT = GROUPS / (NA + NB) > 0 ? GROUPS / (NA + NB) : 1;
+    static_assert(SLOT * (NA + NB) <= GROUPS, "more load chunks than DMMA groups to hide them behind");
     for (int kt = 0; kt < ktiles; ++kt) {
+        const int cs = kt % STAGES;
         cp_async_wait<STAGES - 2>();
-        __syncthreads();
-        {
-            const int nk = kt + STAGES - 1;
-            if (nk < ktiles) {
-                const int s = nk % STAGES;
-                load_tile<A_KC>(As + s * A_STAGE, p.a, p.lda, m0, (int64_t)nk * BK, p.m, p.k, tid);
-                load_tile<B_KC>(Bs + s * B_STAGE, p.b, p.ldb, n0, (int64_t)nk * BK, p.n, p.k, tid);
-            }
-            cp_async_commit();
-        }
-        const double *as = As + (kt % STAGES) * A_STAGE;
-        const double *bs = Bs + (kt % STAGES) * B_STAGE;
+        if (!(NDB_F64_DEBUG & 4)) __syncthreads();
+        const double *as = As + cs * A_STAGE;
+        const double *bs = Bs + cs * B_STAGE;
+        const int nk = kt + STAGES - 1;
+        const bool refill = !(NDB_F64_DEBUG & 1) && nk < ktiles;
+        double *an = As + (nk % STAGES) * A_STAGE;
+        double *bn = Bs + (nk % STAGES) * B_STAGE;
+        double af[2][MI], bf[2][NJ];
+#pragma unroll
+        for (int i = 0; i < MI; ++i) af[0][i] = frag<A_KC, BM>(as, wm * WTM + i * 8 + g, t);
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) bf[0][j] = frag<B_KC, BN>(bs, wn * WTN + j * 8 + g, t);
 #pragma unroll
         for (int kk = 0; kk < BK; kk += 4) {
-            double af[8], bf[4];
+            const int cur = (kk >> 2) & 1, nxt = cur ^ 1;
+            if (kk + 4 < BK && (!(NDB_F64_DEBUG & 2) || kk == 0)) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) af[i] = frag<A_KC>(as, wm * 64 + i * 8 + g, kk + t);
+                for (int i = 0; i < MI; ++i) af[nxt][i] = frag<A_KC, BM>(as, wm * WTM + i * 8 + g, kk + 4 + t);
 #pragma unroll
-            for (int j = 0; j < 4; ++j) bf[j] = frag<B_KC>(bs, wn * 32 + j * 8 + g, kk + t);
+                for (int j = 0; j < NJ; ++j) bf[nxt][j] = frag<B_KC, BN>(bs, wn * WTN + j * 8 + g, kk + 4 + t);
+            }
 #pragma unroll
-            for (int i = 0; i < 8; ++i)
+            for (int i = 0; i < MI; ++i) {
 #pragma unroll
-                for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+                for (int j = 0; j < NJ; ++j) dmma884(acc[i][j][0], acc[i][j][1], af[cur][i], bf[cur][j]);
+                const int group = (kk / 4) * MI + i;
+                if (group % SLOT == SLOT - 1 && group / SLOT < NA + NB && refill) {
+                    const int c = group / SLOT;
+                    if (c < NA) la.issue(an, c);
+                    else lb.issue(bn, c - NA);
+                }
+            }
         }
+        if (refill) {
+            la.next_ktile();
+            lb.next_ktile();
+        }
+        cp_async_commit();
     }
     cp_async_wait<0>();
 
     // epilogue: thread owns rows i*8+g, column pairs j*8+2t
     const bool even_ld = (p.ldc & 1) == 0;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        const int64_t row = m0 + wm * 64 + i * 8 + g;
+    for (int i = 0; i < MI; ++i) {
+        const int64_t row = m0 + wm * WTM + i * 8 + g;
         if (row >= p.m) continue;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int64_t col = n0 + wn * 32 + j * 8 + 2 * t;
+        for (int j = 0; j < NJ; ++j) {
+            const int64_t col = n0 + wn * WTN + j * 8 + 2 * t;
             if (col >= p.n) continue;
             double *dst = p.c + row * p.ldc + col;
             double v0 = p.alpha * acc[i][j][0], v1 = p.alpha * acc[i][j][1];
@@ -271,6 +348,10 @@ int launch_dense(ndb_ctx *ctx, const GemmArgs &g, double alpha, double beta)
     p.tiles_n = (int)((g.n + BN - 1) / BN);
     const bool a_kc = a.unit_inner;    // A(m,k): unit inner stride = k contiguous
     const bool b_kc = !b.unit_inner;   // B(k,n): unit ROW stride = k contiguous
+    {
+        const int st = gemm_f64_tma_launch(ctx, a.ptr, a.ld, a_kc, b.ptr, b.ld, b_kc, (double *)c.ptr, c.ld, g.m, g.n, g.k, alpha, beta);
+        if (st != NDB_ERR_UNSUPPORTED) return st;
+    }
     const unsigned blocks = (unsigned)(p.tiles_m * p.tiles_n);
     static bool attr_done = false;
     if (!attr_done) {

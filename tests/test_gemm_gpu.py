@@ -262,3 +262,31 @@ def test_strided_operands_take_the_tensor_path(nd, oracle, dtype, tol):
     bb = nd.Array.from_numpy(row).broadcast((k, n))
     c = nd.Array.from_numpy(a).dot(bb).to_numpy()
     assert rel_norm(c, a.astype(np.float64) @ np.broadcast_to(row.astype(np.float64), (k, n))) < tol * math.sqrt(k)
+
+
+def test_f64_tma_and_cpasync_kernels_agree_bitwise(nd, monkeypatch):
+    """The TMA-fed and the cp.async-fed f64 kernels run the same DMMA sequence per output element, so they must agree to
+    the bit on every layout combination, with tile overhang (m, n not multiples of 128) and a partial last k-tile."""
+    rng = np.random.default_rng(11)
+    for (m, k, n) in [(256, 256, 256), (1000, 520, 776), (132, 36, 388)]:
+        a = rng.standard_normal((m, k))
+        b = rng.standard_normal((k, n))
+        c0 = rng.standard_normal((m, n))
+        for af in (False, True):
+            for bf in (False, True):
+                for cf in (False, True):
+                    outs = []
+                    for force_cpasync in (False, True):
+                        if force_cpasync:
+                            monkeypatch.setenv("NDB_GEMM_F64_CPASYNC", "1")
+                        else:
+                            monkeypatch.delenv("NDB_GEMM_F64_CPASYNC", raising=False)
+                        da = nd.Array.from_numpy(np.asfortranarray(a) if af else a)
+                        db = nd.Array.from_numpy(np.asfortranarray(b) if bf else b)
+                        dc = nd.Array.from_numpy(np.asfortranarray(c0) if cf else c0)
+                        nd.general_mat_mul(-2.3, da, db, math.pi, dc)
+                        outs.append(dc.to_numpy())
+                    monkeypatch.delenv("NDB_GEMM_F64_CPASYNC", raising=False)
+                    assert np.array_equal(outs[0], outs[1]), (m, k, n, af, bf, cf)
+                    ref = -2.3 * (a @ b) + math.pi * c0
+                    assert rel_norm(outs[0], ref) < 1e-12 * math.sqrt(k)
