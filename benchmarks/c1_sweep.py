@@ -1,0 +1,47 @@
+"""C1 sum_axis (f32 4096^2, cold L2) under the reduction split knobs."""
+import os
+import statistics
+import sys
+from pathlib import Path
+
+import numpy as np
+
+sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
+import torch  # noqa: E402
+import ndarray_b200 as nd  # noqa: E402
+from ndarray_b200 import Array, Axis  # noqa: E402
+
+ctx = nd.default_context()
+dev = torch.device("cuda", 0)
+n = 4096
+bufs = [torch.rand(n, n, device=dev) for _ in range(8)]  # 8 x 64 MiB rotate through the 126 MB L2
+arrs = [Array.borrow(t.data_ptr(), (n, n), np.float32, "C", ctx, owner=t) for t in bufs]
+outs = [Array.uninit((n,), np.float32, ctx=ctx) for _ in bufs]
+
+
+def run(ax, iters=40):
+    from ndarray_b200.array import Red
+    import ctypes as C
+    L = nd.lib()
+    evs = [(ctx.event(), ctx.event()) for _ in range(iters)]
+    for i in range(8):
+        L.ndb_reduce_axis(ctx.handle, Red.SUM, ax, C.byref(arrs[i].v), C.byref(outs[i].v), 0.0)
+    ctx.sync()
+    for i, (a, b) in enumerate(evs):
+        ctx.record(a)
+        L.ndb_reduce_axis(ctx.handle, Red.SUM, ax, C.byref(arrs[i % 8].v), C.byref(outs[i % 8].v), 0.0)
+        ctx.record(b)
+    ctx.sync()
+    ms = [ctx.elapsed_ms(a, b) for a, b in evs]
+    return statistics.median(ms) * 1e3, min(ms) * 1e3
+
+
+for per_sm in ("1", "2", "3", "4", "6", "8"):
+    os.environ["NDB_RED_COLS_PER_SM"] = per_sm
+    med, best = run(0)
+    print(f"axis0 per_sm={per_sm}: median {med:5.1f} us best {best:5.1f} us", flush=True)
+os.environ.pop("NDB_RED_COLS_PER_SM")
+for wm in ("1024", "4096", "8192"):
+    os.environ["NDB_RED_WARP_MAX"] = wm
+    med, best = run(1)
+    print(f"axis1 warp_max={wm}: median {med:5.1f} us best {best:5.1f} us", flush=True)

@@ -42,6 +42,23 @@ def main():
     assert np.max(np.abs(par.mean_axis0(sf, n0, dist).to_numpy() - f.mean(axis=0))) <= tol
     assert np.max(np.abs(par.var_axis0(sf, 1.0, dist).to_numpy() - f.var(axis=0, ddof=1))) <= tol * 8
     assert np.max(np.abs(par.var_axis0(sf, 0.0, dist, want_std=True).to_numpy() - f.std(axis=0))) <= tol * 8
+    # general_mat_mul: A and C row-sharded, B broadcast from rank 0 (one shot and pipelined in 4 row blocks of B)
+    for dt, tol_mm in ((np.float64, 1e-12), (np.float32, 1e-5)):
+        A = rng.standard_normal((n0, 512)).astype(dt)
+        B = rng.standard_normal((512, 300)).astype(dt)
+        C0 = rng.standard_normal((n0, 300)).astype(dt)
+        ref = (-2.3 * (A.astype(np.float64) @ B.astype(np.float64)) + np.pi * C0)[lo:hi]
+        for chunks in (1, 4):
+            dA = par.shard_axis0(Array.from_numpy(A, ctx), rank, world)
+            dC = par.shard_axis0(Array.from_numpy(C0, ctx), rank, world)
+            dB = Array.from_numpy(B if rank == 0 else np.zeros_like(B), ctx)  # only rank 0 holds B
+            par.general_mat_mul_rowsharded(-2.3, dA, dB, np.pi, dC, dist, src=0, k_chunks=chunks)
+            err = np.max(np.abs(dC.to_numpy() - ref)) / np.max(np.abs(ref))
+            assert err <= tol_mm * np.sqrt(512), (dt, chunks, err)
+    x = rng.standard_normal(n0 * 300)
+    lo1, hi1 = par.shard_bounds(x.size, rank, world)
+    dx = Array.from_numpy(x[lo1:hi1], ctx)
+    assert abs(par.global_dot(dx, dx, dist) - x @ x) <= 1e-12 * np.sqrt(x.size) * 8 * (x @ x)
     ctx.sync()
     dist.barrier()
     if rank == 0:

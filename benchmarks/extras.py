@@ -4,6 +4,7 @@ C1  f32 4096^2 contiguous  a = b*c + a  and sum_axis (buffers rotated so the 64 
 C3  16384^2 f64 sum/mean/var_axis and i64 sum_axis / fold_axis(min), both axes
 C4  general_mat_mul f64 / f32 at 8192^3 (C- and F-order operands)
 C5  (N > 1) per-rank f32 elementwise + global sum() finished by an NCCL all-reduce
+C4  (N > 1) row-sharded general_mat_mul with B broadcast over NCCL, one shot and pipelined in 8 row blocks
 All timed with CUDA events on the context stream after warm-up; algorithmic bytes per SURVEY.md §8d.
 """
 from __future__ import annotations
@@ -173,6 +174,22 @@ def run_extras(nd, ctx, torch, dist, rank, world, local, peak_gbs):
         nbytes = (4 * 4 + 4) * rows * 65536 * world
         out["C5_zip+global_sum_f32"] = {"GB/s_aggregate": round(gbs(nbytes, float(t.item())), 1), "ms": round(float(t.item()), 3),
                                         "per_rank_elems": rows * 65536, "collective": "ncclAllReduce(sum, 1 elt) on the ctx stream"}
+    # ---- C4 at N GPUs: A and C row-sharded (8192 rows per rank, weak), B broadcast from rank 0 EVERY step ----------
+    if dist is not None and world > 1:
+        from ndarray_b200 import parallel as par
+        n = 8192
+        for tdt, name in ((torch.float64, "f64"), (torch.float32, "f32")):
+            ta, tb, tc = (torch.randn(n, n, device=dev, dtype=tdt) for _ in range(3))
+            A, B, Cm = (tarr(t) for t in (ta, tb, tc))
+            for chunks in (1, 8):
+                med, best = _time(ctx, lambda: par.general_mat_mul_rowsharded(1.0, A, B, 0.0, Cm, dist, 0, chunks), 3, 1)
+                t = torch.tensor([med], device=dev, dtype=torch.float64)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                out[f"C4_gemm_{name}_rowsharded_{world}gpu_bcast_chunks{chunks}"] = {
+                    "TFLOP/s_aggregate": round(world * 2.0 * n ** 3 / (float(t.item()) * 1e-3) / 1e12, 1), "ms": round(float(t.item()), 3),
+                    "collective": "ncclBroadcast of B (%d MiB) inside the timed step" % (n * n * ta.element_size() >> 20)}
+            del ta, tb, tc
+        torch.cuda.empty_cache()
     if rank == 0 and world == 1:
         try:
             out["cpu_stand_in"] = cpu_stand_ins()

@@ -64,6 +64,8 @@ int validate_view(const ndb_view *v, const char *what);
 }  // namespace ndb
 
 // ---- context ------------------------------------------------------------------
+constexpr int NDB_TICKETS = 65536;
+
 struct ndb_ctx {
     int device = 0;
     cudaStream_t own_stream = nullptr;
@@ -74,6 +76,7 @@ struct ndb_ctx {
     int *host_flag = nullptr;       // pinned mirror
     void *host_scalar = nullptr;    // pinned 64-byte buffer for scalar results
     int sm_count = 148;
+    unsigned *tickets = nullptr;    // NDB_TICKETS zeroed counters: 'last block finishes' hand-over in split reductions (self-resetting)
     // staging buffers for the host-pointer (end-to-end / cblas) entry points
     void *stage[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     size_t stage_bytes[8] = {0, 0, 0, 0, 0, 0, 0, 0};

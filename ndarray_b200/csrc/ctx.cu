@@ -183,6 +183,11 @@ int ndb_ctx_create(int device, ndb_ctx **out)
         uint64_t keep = UINT64_MAX;
         NDB_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
     }
+    if (cudaMalloc((void **)&ctx->tickets, NDB_TICKETS * sizeof(unsigned)) != cudaSuccess ||
+        cudaMemset(ctx->tickets, 0, NDB_TICKETS * sizeof(unsigned)) != cudaSuccess) {
+        set_error("ctx_create: cannot allocate the ticket counters");
+        return NDB_ERR_CUDA;
+    }
     int st = ensure_workspace(ctx, size_t(8) << 20);
     if (st != NDB_OK) return st;
     *out = ctx;
@@ -197,6 +202,7 @@ int ndb_ctx_destroy(ndb_ctx *ctx)
     if (ctx->workspace) cudaFree(ctx->workspace);
     for (int i = 0; i < 8; ++i)
         if (ctx->stage[i]) cudaFree(ctx->stage[i]);
+    if (ctx->tickets) cudaFree(ctx->tickets);
     if (ctx->dev_flag) cudaFree(ctx->dev_flag);
     if (ctx->host_flag) cudaFreeHost(ctx->host_flag);
     if (ctx->host_scalar) cudaFreeHost(ctx->host_scalar);

@@ -236,6 +236,7 @@ struct RedArgs {
     double dof;     // n - ddof in the element type
     int splits;     // red_cols: blocks along the reduced axis
     void *partial;  // [splits][n_out] states
+    unsigned *tickets;  // red_cols: one zeroed counter per column tile; non-null = the last split to finish merges (one launch)
 };
 
 __device__ __forceinline__ void kept_offsets(const Kept &k, int64_t lin, int64_t &in_off, int64_t &out_off,
@@ -322,6 +323,37 @@ __global__ void __launch_bounds__(256) red_lanes(RedArgs a)
             if (threadIdx.x == 0) store_result<T, R, FIN>(a, acc, out_off, out2_off);
         }
     }
+}
+
+// a partial state written by another block: read through L2 (ld.global.cg), never from this SM's L1
+template <typename A>
+__device__ __forceinline__ A ldcg_state(const A *p)
+{
+    static_assert(sizeof(A) % 4 == 0, "partial states are whole words");
+    A r;
+    const unsigned *s = reinterpret_cast<const unsigned *>(p);
+    unsigned *d = reinterpret_cast<unsigned *>(&r);
+#pragma unroll
+    for (int i = 0; i < (int)(sizeof(A) / 4); ++i) d[i] = __ldcg(s + i);
+    return r;
+}
+
+// states p[0], p[pitch], ... merged in split order; loads are issued eight at a time so that the chain costs one L2
+// round trip per eight splits instead of one per split (it sits on the kernel's critical path)
+template <typename A>
+__device__ __forceinline__ A merge_splits(const A *p, int splits, int64_t pitch)
+{
+    A r = ldcg_state(p);
+    int sidx = 1;
+    for (; sidx + 8 <= splits; sidx += 8) {
+        A b[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) b[u] = ldcg_state(p + (int64_t)(sidx + u) * pitch);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) r.merge(b[u]);
+    }
+    for (; sidx < splits; ++sidx) r.merge(ldcg_state(p + (int64_t)sidx * pitch));
+    return r;
 }
 
 // ---- cols: a kept axis is unit-stride ------------------------------------------------------------
@@ -413,6 +445,25 @@ __global__ void __launch_bounds__(256) red_cols(RedArgs a)
                 }
             }
         }
+        if (a.splits > 1 && a.tickets != nullptr) {
+            // One launch instead of two: the block that takes the last ticket of this column tile merges all splits'
+            // partial states IN SPLIT ORDER (so the result does not depend on which block came last) and stores.
+            __shared__ unsigned ticket;
+            __threadfence();  // this block's partials are visible device-wide before its ticket is
+            __syncthreads();
+            if (t == 0) ticket = atomicAdd(a.tickets + vb, 1u);
+            __syncthreads();
+            if (ticket == (unsigned)a.splits - 1) {
+                __threadfence();
+                const int64_t c = tile * (32 * W) + t;
+                if (t < 32 * W && c < ncol) {
+                    const Acc<T, R> *p = reinterpret_cast<const Acc<T, R> *>(a.partial) + o * ncol + c;
+                    Acc<T, R> r = merge_splits(p, a.splits, a.n_out);
+                    store_result<T, R, FIN>(a, r, out_off + c * a.k.out_stride[last], out2_off + c * a.k.out2_stride[last]);
+                }
+                if (t == 0) a.tickets[vb] = 0;  // ready for the next launch
+            }
+        }
         __syncthreads();
     }
 }
@@ -424,8 +475,7 @@ __global__ void __launch_bounds__(256) red_finish_cols(RedArgs a)
     const int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (o >= a.n_out) return;
     const Acc<T, R> *p = reinterpret_cast<const Acc<T, R> *>(a.partial);
-    Acc<T, R> r = p[o];
-    for (int sidx = 1; sidx < a.splits; ++sidx) r.merge(p[(int64_t)sidx * a.n_out + o]);
+    Acc<T, R> r = merge_splits(p + o, a.splits, a.n_out);
     int64_t in_off, out_off, out2_off;
     kept_offsets(a.k, o, in_off, out_off, out2_off);
     store_result<T, R, FIN>(a, r, out_off, out2_off);
@@ -892,15 +942,17 @@ static int reduce_axis_launch(ndb_ctx *ctx, RedArgs &a, const ZipPlan &z)
         int64_t max_splits = std::max<int64_t>(1, a.n / 64);
         int splits = (int)std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(want, max_splits), 256));
         a.splits = splits;
+        a.tickets = nullptr;
         if (splits > 1) {
             NDB_TRY(ensure_workspace(ctx, (size_t)splits * (size_t)a.n_out * sizeof(Acc<T, R>)));
             a.partial = ctx->workspace;
+            if (total <= NDB_TICKETS && !getenv("NDB_RED_TWO_KERNELS")) a.tickets = ctx->tickets;
         }
         dim3 grid((unsigned)std::min<int64_t>(total, (int64_t)1 << 30), (unsigned)splits, 1), block(32, 8, 1);
         if (vec) red_cols<T, R, FIN, Vec128<T>::N><<<grid, block, 0, st>>>(a);
         else red_cols<T, R, FIN, 1><<<grid, block, 0, st>>>(a);
         NDB_CHECK_LAUNCH();
-        if (splits > 1) {
+        if (splits > 1 && a.tickets == nullptr) {
             red_finish_cols<T, R, FIN><<<(unsigned)((a.n_out + 255) / 256), 256, 0, st>>>(a);
             NDB_CHECK_LAUNCH();
         }

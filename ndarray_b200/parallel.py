@@ -13,7 +13,7 @@ import ctypes as C
 import numpy as np
 
 from ._ffi import View, check, lib
-from .array import Array, Red
+from .array import Array, Red, Slice
 
 
 def shard_bounds(n: int, rank: int, world: int) -> tuple[int, int]:
@@ -108,3 +108,60 @@ def var_axis0(local: Array, ddof: float, dist=None, want_std: bool = False) -> A
     cv = (C.c_int64 * len(counts))(*counts)
     check(lib().ndb_welford_merge(local.ctx.handle, len(counts), cv, mv, sv, float(ddof), int(want_std), C.byref(out.v)))
     return out
+
+
+def global_dot(x_local: Array, y_local: Array, dist=None):
+    """1-D dot over sharded vectors: per-GPU dot (src/linalg/impl_linalg.rs:74-133), then all-reduce of one element."""
+    import torch
+    part = x_local.dot(y_local)
+    if dist is not None and dist.is_initialized() and dist.get_world_size() > 1:
+        t = torch.tensor([part], dtype=_torch_view(x_local).dtype, device=torch.device("cuda", x_local.ctx.device))
+        dist.all_reduce(t)
+        return t.cpu().numpy()[0]
+    return part
+
+
+def general_mat_mul_rowsharded(alpha, a_local: Array, b: Array, beta, c_local: Array, dist=None, src: int = 0,
+                               k_chunks: int = 1) -> None:
+    """general_mat_mul with A and C sharded along Axis(0) and B replicated: `b` is a C-order [k, n]
+    buffer on every rank whose contents are valid on rank `src`; it is broadcast over NCCL and each rank multiplies its
+    own rows.  With k_chunks > 1 the broadcast is cut into row blocks of B on a second stream and the GEMM on block j
+    (C += alpha * A[:, kj] * B[kj, :]) overlaps the transfer of block j + 1, so the link time hides behind the tensor
+    pipe; the chunked sum differs from the one-shot result only in rounding order (GEMM parity is to tolerance)."""
+    from .linalg import general_mat_mul
+    world = dist.get_world_size() if dist is not None and dist.is_initialized() else 1
+    k = b.shape[0]
+    if world == 1:
+        general_mat_mul(alpha, a_local, b, beta, c_local)
+        return
+    import torch
+    assert b.is_standard_layout(), "the replicated operand is broadcast as one dense C-order buffer"
+    dev = torch.device("cuda", b.ctx.device)
+    tb = _torch_view(b).view(k, -1)
+    compute = torch.cuda.ExternalStream(b.ctx.stream_ptr(), device=dev)
+    k_chunks = max(1, min(int(k_chunks), k))
+    if k_chunks == 1:
+        with torch.cuda.stream(compute):
+            dist.broadcast(tb, src)
+        general_mat_mul(alpha, a_local, b, beta, c_local)
+        return
+    comm = torch.cuda.Stream(device=dev)
+    ready = torch.cuda.Event()
+    ready.record(compute)        # B was produced on the context stream
+    comm.wait_event(ready)
+    bounds = [k * j // k_chunks for j in range(k_chunks + 1)]
+    for j in range(k_chunks):
+        lo, hi = bounds[j], bounds[j + 1]
+        if hi == lo:
+            continue
+        with torch.cuda.stream(comm):
+            dist.broadcast(tb[lo:hi], src)
+            landed = torch.cuda.Event()
+            landed.record(comm)
+        compute.wait_event(landed)
+        a_blk = a_local.slice_axis(1, Slice(lo, hi, 1))
+        b_blk = b.slice_axis(0, Slice(lo, hi, 1))
+        general_mat_mul(alpha, a_blk, b_blk, beta if j == 0 else 1.0, c_local)
+    done = torch.cuda.Event()
+    done.record(compute)
+    comm.wait_event(done)        # the comm stream (and its tensors) must outlive the last GEMM

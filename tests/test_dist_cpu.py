@@ -3,7 +3,8 @@
 * the partition: `shard_bounds` + `ndb_view_split_at` through the C ABI give disjoint slabs that tile the array;
 * elementwise Zip on shards needs no exchange: per-shard oracle results concatenate to the unsharded result bit-exactly;
 * sum / sum_axis(Axis(0)): per-shard partials + all-reduce reproduce the unsharded oracle (exactly for integers);
-* var_axis(Axis(0)): per-shard (n, mean, M2) + all-gather + Chan merge in rank order reproduces Welford.
+* var_axis(Axis(0)): per-shard (n, mean, M2) + all-gather + Chan merge in rank order reproduces Welford;
+* general_mat_mul: A and C row-sharded, B broadcast from rank 0 (one shot, and accumulated in row blocks of B).
 Local compute uses the oracle here (no GPU); on the GPU box the same protocol runs in ndarray_b200/parallel.py."""
 import ctypes as C
 import os
@@ -84,6 +85,24 @@ def _worker(rank, world, port, q):
         want = orc.reduce_axis(5, f, 0, 1.0)[1]
         assert n == 37
         assert np.max(np.abs(m2 / (n - 1.0) - want)) <= 1e-12 * np.sqrt(37) * np.abs(want).max() * 8
+        # general_mat_mul: A and C row-sharded, B valid on rank 0 only and broadcast; slabs concatenate to the full product
+        A = rng.standard_normal((37, 16))
+        B = rng.standard_normal((16, 9))
+        C0 = rng.standard_normal((37, 9))
+        tb = torch.from_numpy(B.copy() if rank == 0 else np.zeros_like(B))
+        dist.broadcast(tb, 0)
+        c_loc = C0[lo:hi].copy()
+        assert orc.gemm(-2.3, A[lo:hi], tb.numpy(), np.pi, c_loc) == 0
+        slabs = [None] * world
+        dist.all_gather_object(slabs, c_loc)
+        c_full = C0.copy()
+        assert orc.gemm(-2.3, A, B, np.pi, c_full) == 0
+        assert np.array_equal(np.concatenate(slabs, axis=0), c_full)  # row sharding does not change any row's arithmetic
+        # the pipelined form adds B's row blocks one at a time: same result within rounding
+        c_chunk = C0[lo:hi].copy()
+        for j, (k0, k1) in enumerate(((0, 4), (4, 8), (8, 12), (12, 16))):
+            assert orc.gemm(-2.3, A[lo:hi, k0:k1], B[k0:k1], np.pi if j == 0 else 1.0, c_chunk) == 0
+        assert np.max(np.abs(c_chunk - c_full[lo:hi])) <= 1e-12 * np.sqrt(16) * np.abs(c_full).max()
         q.put((rank, "ok"))
     except Exception as e:  # pragma: no cover
         q.put((rank, repr(e)))

@@ -317,3 +317,27 @@ def test_accumulate_axis_scan(nd, dtype):
     d = Array.from_numpy(long)
     d.accumulate_axis_inplace(1, Op.ADD)
     assert np.array_equal(d.to_numpy(), np.cumsum(long, axis=1))
+
+
+def test_split_column_reduction_one_launch_equals_two_launches(nd, monkeypatch):
+    """sum/var along Axis(0) of a C-order matrix split the reduced axis over blocks.  The single-launch form (the last
+    block per column tile merges the partial states in split order) must give the bits of the two-launch form, twice in
+    a row (the ticket counters reset themselves)."""
+    from ndarray_b200 import Array, Axis
+    rng = np.random.default_rng(5)
+    for shape, dtype in (((4096, 4096), np.float32), ((3000, 1000), np.float64), ((5000, 96), np.int64)):
+        h = (rng.standard_normal(shape) * 100).astype(dtype)
+        d = Array.from_numpy(h)
+        got = []
+        for two in (False, True, False):
+            if two:
+                monkeypatch.setenv("NDB_RED_TWO_KERNELS", "1")
+            else:
+                monkeypatch.delenv("NDB_RED_TWO_KERNELS", raising=False)
+            res = [d.sum_axis(Axis(0)).to_numpy()]
+            if np.dtype(dtype).kind == "f":
+                res.append(d.var_axis(Axis(0), 1.0).to_numpy())
+            got.append(res)
+        monkeypatch.delenv("NDB_RED_TWO_KERNELS", raising=False)
+        for a, b, c in zip(*got):
+            assert np.array_equal(a, b) and np.array_equal(a, c)
