@@ -19,6 +19,7 @@ def main():
     os.environ["NDB_DEVICE"] = str(local)
     import ndarray_b200 as nd
     from ndarray_b200 import Array, Zip, parallel as par
+    from ndarray_b200.array import Red
     ctx = nd.Context(local)
     rng = np.random.default_rng(7)
     n0 = 1001
@@ -42,6 +43,24 @@ def main():
     assert np.max(np.abs(par.mean_axis0(sf, n0, dist).to_numpy() - f.mean(axis=0))) <= tol
     assert np.max(np.abs(par.var_axis0(sf, 1.0, dist).to_numpy() - f.var(axis=0, ddof=1))) <= tol * 8
     assert np.max(np.abs(par.var_axis0(sf, 0.0, dist, want_std=True).to_numpy() - f.std(axis=0))) <= tol * 8
+    # the same reductions with the exchange done through peer memory (CUDA IPC windows over NVLink), no NCCL call
+    peers = par.PeerGroup(ctx, dist, slot_bytes=1 << 16)
+    for rep in range(3):  # repeated: the two slot sets and the arrival counter must keep working
+        with np.errstate(over="ignore"):
+            assert par.global_sum(sa, dist, peers) == a.sum(dtype=np.int64)
+            assert np.array_equal(par.sum_axis0(sa, dist, peers).to_numpy(), a.sum(axis=0, dtype=np.int64))
+        assert abs(par.global_sum(sf, dist, peers) - f.sum()) <= tol * 300 * 8
+        assert np.max(np.abs(par.sum_axis0(sf, dist, peers).to_numpy() - f.sum(axis=0))) <= tol * 8
+        assert np.max(np.abs(par.mean_axis0(sf, n0, dist, peers).to_numpy() - f.mean(axis=0))) <= tol
+        assert np.max(np.abs(par.var_axis0(sf, 1.0, dist, peers=peers).to_numpy() - f.var(axis=0, ddof=1))) <= tol * 8
+    # peer exchange and NCCL agree to the bit for integers and (same rank order) for this float case too
+    g_peer = par.sum_axis0(sa, dist, peers).to_numpy()
+    g_nccl = par.sum_axis0(sa, dist).to_numpy()
+    assert np.array_equal(g_peer, g_nccl)
+    gathered = peers.allgather(Array.from_numpy(np.full(5, rank, dtype=np.int32), ctx)).to_numpy()
+    assert np.array_equal(gathered, np.repeat(np.arange(world, dtype=np.int32)[:, None], 5, axis=1))
+    mx = peers.allreduce_(Array.from_numpy(np.array([rank, -rank], dtype=np.float64), ctx), Red.MAX).to_numpy()
+    assert np.array_equal(mx, [world - 1, 0.0])
     # general_mat_mul: A and C row-sharded, B broadcast from rank 0 (one shot and pipelined in 4 row blocks of B)
     for dt, tol_mm in ((np.float64, 1e-12), (np.float32, 1e-5)):
         A = rng.standard_normal((n0, 512)).astype(dt)
@@ -61,6 +80,7 @@ def main():
     assert abs(par.global_dot(dx, dx, dist) - x @ x) <= 1e-12 * np.sqrt(x.size) * 8 * (x @ x)
     ctx.sync()
     dist.barrier()
+    peers.close()
     if rank == 0:
         print(f"dist_check ok on {world} GPUs")
     dist.destroy_process_group()

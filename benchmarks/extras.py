@@ -174,6 +174,50 @@ def run_extras(nd, ctx, torch, dist, rank, world, local, peak_gbs):
         nbytes = (4 * 4 + 4) * rows * 65536 * world
         out["C5_zip+global_sum_f32"] = {"GB/s_aggregate": round(gbs(nbytes, float(t.item())), 1), "ms": round(float(t.item()), 3),
                                         "per_rank_elems": rows * 65536, "collective": "ncclAllReduce(sum, 1 elt) on the ctx stream"}
+        if world > 1:
+            # the same step with the exchange fused into the reduction's finishing kernel (peer windows over NVLink)
+            import ctypes as C
+            from ndarray_b200 import parallel as par
+            from ndarray_b200.array import Red
+            peers = par.PeerGroup(ctx, dist, slot_bytes=1 << 18)
+            L = nd.lib()
+
+            def c5_peer():
+                Zip.from_(a).and_(b).and_(c).for_each("a=b*c+a")
+                L.ndb_reduce_all_peer(ctx.handle, Red.SUM, C.byref(a.v), C.c_void_p(accv.v.ptr))
+
+            med, best = _time(ctx, c5_peer, 10, 2)
+            t = torch.tensor([med], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            out["C5_zip+global_sum_f32_peer_fused"] = {"GB/s_aggregate": round(gbs(nbytes, float(t.item())), 1), "ms": round(float(t.item()), 3),
+                                                       "collective": "none: the sum's finishing kernel exchanges the scalar through peer memory"}
+            # exchange latency alone: one element and the C3 sum_axis(Axis(0)) vector (16384 f64 = 128 KiB)
+            vec_t = torch.zeros(16384, device=dev, dtype=torch.float64)
+            vec = tarr(vec_t)
+            for label, arr, tt in (("1elt", accv, acc), ("128KiB", vec, vec_t)):
+                def nccl(tt=tt):
+                    with torch.cuda.stream(stream):
+                        dist.all_reduce(tt)
+                med_n, _ = _time(ctx, nccl, 50, 5)
+                med_p, _ = _time(ctx, lambda arr=arr: peers.allreduce_(arr), 50, 5)
+                tn = torch.tensor([med_n, med_p], device=dev, dtype=torch.float64)
+                dist.all_reduce(tn, op=dist.ReduceOp.MAX)
+                out[f"allreduce_latency_{label}"] = {"nccl_us": round(float(tn[0].item()) * 1e3, 1), "peer_memory_us": round(float(tn[1].item()) * 1e3, 1)}
+            # C3 sharded: sum_axis(Axis(0)) of a [2048, 16384] f64 slab per rank + exchange of the 128 KiB vector
+            slab_t = torch.randn(2048, 16384, device=dev, dtype=torch.float64)
+            slab = tarr(slab_t)
+            for label, fn in (("nccl", lambda: par.sum_axis0(slab, dist)), ("peer", lambda: par.sum_axis0(slab, dist, peers))):
+                med_s, _ = _time(ctx, fn, 20, 3)
+                ts = torch.tensor([med_s], device=dev, dtype=torch.float64)
+                dist.all_reduce(ts, op=dist.ReduceOp.MAX)
+                out[f"C3_sum_axis0_sharded_f64_{label}"] = {"GB/s_aggregate": round(gbs(world * (8 * 2048 * 16384 + 8 * 16384), float(ts.item())), 1),
+                                                           "ms": round(float(ts.item()), 4)}
+            ctx.sync()
+            dist.barrier()
+            peers.close()
+            del slab, slab_t, vec, vec_t
+        del a, b, c, ts
+        torch.cuda.empty_cache()
     # ---- C4 at N GPUs: A and C row-sharded (8192 rows per rank, weak), B broadcast from rank 0 EVERY step ----------
     if dist is not None and world > 1:
         from ndarray_b200 import parallel as par

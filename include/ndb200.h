@@ -273,6 +273,23 @@ int ndb_welford_merge(ndb_ctx *ctx, int n_shards, const int64_t *counts, const n
                       double ddof, int want_std, const ndb_view *out);
 /* ArrayRef::var / std over every element (src/numeric/impl_numeric.rs:180-249), result to host (floats only). */
 int ndb_var(ndb_ctx *ctx, const ndb_view *in, double ddof, int want_std, void *out_host);
+/* ---- multi-GPU exchange over peer memory (NVLink), one process per GPU -------------------------------------------
+ * The sharded reductions of SURVEY.md 8e end in a small exchange: sum()/dot -> one element, sum_axis(Axis(0)) -> the
+ * [n_out] vector, var_axis(Axis(0)) -> per-shard (mean, M2).  Each rank creates a window in its own HBM and publishes its
+ * 64-byte CUDA IPC handle; after every rank has attached all handles, an exchange is ONE kernel launch per rank that
+ * stores this rank's contribution into every rank's window, signals, waits for the others and combines in rank order
+ * (deterministic).  All ranks must issue the same sequence of exchanges with the same sizes.  slot_bytes bounds the size
+ * of one contribution.  (NCCL through torch.distributed remains available in ndarray_b200/parallel.py as the fallback.) */
+int ndb_peer_window_create(ndb_ctx *ctx, int rank, int world, size_t slot_bytes, void *handle_out /* 64 bytes */);
+int ndb_peer_window_attach(ndb_ctx *ctx, const void *handles /* world x 64 bytes, in rank order */);
+int ndb_peer_window_destroy(ndb_ctx *ctx);
+/* out[i] = redop over ranks (rank order) of local[i]; redop in {SUM, PROD, MIN, MAX}; out may alias local. */
+int ndb_peer_allreduce(ndb_ctx *ctx, int redop, int dtype, const void *local_dev, void *out_dev, int64_t n);
+/* out[r*n + i] = rank r's local[i]. */
+int ndb_peer_allgather(ndb_ctx *ctx, int dtype, const void *local_dev, void *out_dev, int64_t n);
+/* ndb_reduce_all_dev over ALL shards: the kernel that finishes this rank's reduction tree also performs the exchange. */
+int ndb_reduce_all_peer(ndb_ctx *ctx, int redop, const ndb_view *in, void *out_dev);
+
 /* accumulate_axis_inplace (src/impl_methods.rs:3243) with op NDB_OP_ADD (running sum) or NDB_OP_MUL (cumprod,
  * src/numeric/impl_numeric.rs:125): v[.., i, ..] = op(v[.., i-1, ..], v[.., i, ..]) along `axis`, in place, one launch. */
 int ndb_accumulate_axis(ndb_ctx *ctx, int op, int axis, const ndb_view *v);

@@ -113,6 +113,12 @@ def lib():
         "ndb_reduce_axis": (i32, [vp, i32, i32, PV, PV, dbl]),
         "ndb_welford_axis": (i32, [vp, i32, PV, PV, PV]),
         "ndb_welford_merge": (i32, [vp, i32, C.POINTER(i64), PV, PV, dbl, i32, PV]),
+        "ndb_peer_window_create": (i32, [vp, i32, i32, C.c_size_t, vp]),
+        "ndb_peer_window_attach": (i32, [vp, vp]),
+        "ndb_peer_window_destroy": (i32, [vp]),
+        "ndb_peer_allreduce": (i32, [vp, i32, i32, vp, vp, C.c_int64]),
+        "ndb_peer_allgather": (i32, [vp, i32, vp, vp, C.c_int64]),
+        "ndb_reduce_all_peer": (i32, [vp, i32, PV, vp]),
         "ndb_accumulate_axis": (i32, [vp, i32, i32, PV]),
         "ndb_dot": (i32, [vp, PV, PV, vp]),
         "ndb_gemm": (i32, [vp, vp, PV, PV, vp, PV]),

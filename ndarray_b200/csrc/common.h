@@ -76,6 +76,13 @@ struct ndb_ctx {
     int *host_flag = nullptr;       // pinned mirror
     void *host_scalar = nullptr;    // pinned 64-byte buffer for scalar results
     int sm_count = 148;
+    // peer window (peer.cu): this rank's window and every peer's, mapped through CUDA IPC
+    int peer_rank = -1, peer_world = 0;
+    bool peer_attached = false;
+    size_t peer_slot_bytes = 0;
+    void *peer_win[16] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    unsigned long long peer_expected = 0;  // arrivals my counter will have seen once every exchange issued so far is complete
+    unsigned long long peer_calls = 0;
     unsigned *tickets = nullptr;    // NDB_TICKETS zeroed counters: 'last block finishes' hand-over in split reductions (self-resetting)
     // staging buffers for the host-pointer (end-to-end / cblas) entry points
     void *stage[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -86,6 +93,8 @@ struct ndb_ctx {
 namespace ndb {
 int ensure_workspace(ndb_ctx *ctx, size_t bytes);
 int ensure_stage(ndb_ctx *ctx, int slot, size_t bytes);
+struct PeerArgs;
+int peer_begin(ndb_ctx *ctx, int blocks, size_t bytes, PeerArgs *out);  // peer.cu
 struct DeviceGuard {
     int prev = -1;
     bool ok = true;

@@ -197,6 +197,7 @@ int ndb_ctx_create(int device, ndb_ctx **out)
 int ndb_ctx_destroy(ndb_ctx *ctx)
 {
     if (!ctx) return NDB_OK;
+    ndb_peer_window_destroy(ctx);
     DeviceGuard g(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     if (ctx->workspace) cudaFree(ctx->workspace);

@@ -23,6 +23,7 @@
 #include <vector>
 
 #include "zip_kernels.cuh"  // w_add & friends, Vec128
+#include "peer.cuh"
 #include "zip_plan.h"
 
 namespace ndb {
@@ -609,6 +610,38 @@ __global__ void __launch_bounds__(256) red_all_finish(const void *partial, int n
     }
 }
 
+// The sharded sum()/product()/min/max: the block that finishes this rank's tree also does the exchange (peer.cuh): its
+// scalar goes into slot[rank] of every rank's window over NVLink, and once all ranks have arrived the slots are merged in
+// rank order.  Local reduction + "all-reduce" of one element cost the same two launches as the local reduction alone.
+template <typename T, int R>
+__global__ void __launch_bounds__(256) red_all_finish_peer(const void *partial, int n, T *out, PeerArgs pa)
+{
+    __shared__ Acc<T, R> smem[32];
+    const Acc<T, R> *p = reinterpret_cast<const Acc<T, R> *>(partial);
+    Acc<T, R> acc;
+    acc.reset();
+    for (int i = threadIdx.x; i < n; i += blockDim.x) acc.merge(p[i]);
+    acc = block_reduce(acc, smem);
+    __shared__ T total;
+    if (threadIdx.x == 0) total = acc.s;
+    __syncthreads();
+    if ((int)threadIdx.x < pa.world) *reinterpret_cast<T *>(peer_slot(pa, threadIdx.x, pa.rank)) = total;
+    peer_arrive(pa);
+    peer_wait(pa);
+    if (threadIdx.x == 0) {
+        Acc<T, R> tot;
+        tot.reset();
+        tot.s = __ldcg(reinterpret_cast<const T *>(peer_slot(pa, pa.rank, 0)));
+        for (int r = 1; r < pa.world; ++r) {
+            Acc<T, R> b;
+            b.reset();
+            b.s = __ldcg(reinterpret_cast<const T *>(peer_slot(pa, pa.rank, r)));
+            tot.merge(b);
+        }
+        *out = tot.s;
+    }
+}
+
 // dot product partials: x[i*sx] * y[i*sy], separately rounded product then sum (numeric_util.rs:56)
 template <typename T>
 __global__ void __launch_bounds__(256) dot_partials(const T *x, int64_t sx, const T *y, int64_t sy, int64_t n, void *partial)
@@ -816,7 +849,7 @@ static void collapse_for_all(const ndb_view *v, AllArgs *a)
 }
 
 template <typename T, int R>
-static int reduce_all_typed(ndb_ctx *ctx, const ndb_view *v, T *out_dev, T dof = T(1), int want_std = 0)
+static int reduce_all_typed(ndb_ctx *ctx, const ndb_view *v, T *out_dev, T dof = T(1), int want_std = 0, bool peer = false)
 {
     AllArgs a;
     memset(&a, 0, sizeof(a));
@@ -837,19 +870,28 @@ static int reduce_all_typed(ndb_ctx *ctx, const ndb_view *v, T *out_dev, T dof =
         red_all_rows<T, R><<<blocks, 256, 0, ctx->stream>>>(a);
     }
     NDB_CHECK_LAUNCH();
+    if constexpr (R != R_WELFORD) {
+        if (peer) {
+            PeerArgs pa;
+            NDB_TRY(peer_begin(ctx, 1, sizeof(T), &pa));
+            red_all_finish_peer<T, R><<<1, 256, 0, ctx->stream>>>(a.partial, blocks, out_dev, pa);
+            NDB_CHECK_LAUNCH();
+            return NDB_OK;
+        }
+    }
     red_all_finish<T, R><<<1, 256, 0, ctx->stream>>>(a.partial, blocks, out_dev, dof, want_std);
     NDB_CHECK_LAUNCH();
     return NDB_OK;
 }
 
 template <typename T>
-static int reduce_all_dispatch(ndb_ctx *ctx, int redop, const ndb_view *v, void *out_dev)
+static int reduce_all_dispatch(ndb_ctx *ctx, int redop, const ndb_view *v, void *out_dev, bool peer = false)
 {
     switch (redop) {
-    case NDB_RED_SUM: return reduce_all_typed<T, R_SUM>(ctx, v, (T *)out_dev);
-    case NDB_RED_PROD: return reduce_all_typed<T, R_PROD>(ctx, v, (T *)out_dev);
-    case NDB_RED_MIN: return reduce_all_typed<T, R_MIN>(ctx, v, (T *)out_dev);
-    case NDB_RED_MAX: return reduce_all_typed<T, R_MAX>(ctx, v, (T *)out_dev);
+    case NDB_RED_SUM: return reduce_all_typed<T, R_SUM>(ctx, v, (T *)out_dev, T(1), 0, peer);
+    case NDB_RED_PROD: return reduce_all_typed<T, R_PROD>(ctx, v, (T *)out_dev, T(1), 0, peer);
+    case NDB_RED_MIN: return reduce_all_typed<T, R_MIN>(ctx, v, (T *)out_dev, T(1), 0, peer);
+    case NDB_RED_MAX: return reduce_all_typed<T, R_MAX>(ctx, v, (T *)out_dev, T(1), 0, peer);
     default: break;
     }
     set_error("reduce_all: redop %d is not a whole-array reduction", redop);
@@ -880,19 +922,28 @@ static int write_identity(ndb_ctx *ctx, int dtype, int redop, void *out_dev)
     return NDB_OK;
 }
 
-static int reduce_all_dev_impl(ndb_ctx *ctx, int redop, const ndb_view *in, void *out_dev)
+static int reduce_all_dev_impl(ndb_ctx *ctx, int redop, const ndb_view *in, void *out_dev, bool peer = false)
 {
     NDB_TRY(validate_view(in, "reduce_all"));
     if (view_len(in) == 0) {
+        if (peer) {
+            // an empty shard still has to take part in the exchange: contribute the identity
+            if (redop != NDB_RED_SUM && redop != NDB_RED_PROD) {
+                set_error("reduce_all: min/max of an empty shard");
+                return NDB_ERR_EMPTY;
+            }
+            NDB_TRY(write_identity(ctx, in->dtype, redop, out_dev));
+            return ndb_peer_allreduce(ctx, redop, in->dtype, out_dev, out_dev, 1);
+        }
         if (redop == NDB_RED_SUM || redop == NDB_RED_PROD) return write_identity(ctx, in->dtype, redop, out_dev);
         set_error("reduce_all: min/max of an empty array");
         return NDB_ERR_EMPTY;
     }
     switch (in->dtype) {
-    case NDB_F32: return reduce_all_dispatch<float>(ctx, redop, in, out_dev);
-    case NDB_F64: return reduce_all_dispatch<double>(ctx, redop, in, out_dev);
-    case NDB_I32: return reduce_all_dispatch<int32_t>(ctx, redop, in, out_dev);
-    case NDB_I64: return reduce_all_dispatch<int64_t>(ctx, redop, in, out_dev);
+    case NDB_F32: return reduce_all_dispatch<float>(ctx, redop, in, out_dev, peer);
+    case NDB_F64: return reduce_all_dispatch<double>(ctx, redop, in, out_dev, peer);
+    case NDB_I32: return reduce_all_dispatch<int32_t>(ctx, redop, in, out_dev, peer);
+    case NDB_I64: return reduce_all_dispatch<int64_t>(ctx, redop, in, out_dev, peer);
     }
     return NDB_ERR_UNSUPPORTED;
 }
@@ -1136,6 +1187,17 @@ int ndb_reduce_all_dev(ndb_ctx *ctx, int redop, const ndb_view *in, void *out_de
     clear_error();
     DeviceGuard g(ctx->device);
     return reduce_all_dev_impl(ctx, redop, in, out_dev);
+}
+
+int ndb_reduce_all_peer(ndb_ctx *ctx, int redop, const ndb_view *in, void *out_dev)
+{
+    if (!ctx || !out_dev) {
+        set_error("reduce_all_peer: null context or output (no CPU fallback exists)");
+        return NDB_ERR_INVALID_ARG;
+    }
+    clear_error();
+    DeviceGuard g(ctx->device);
+    return reduce_all_dev_impl(ctx, redop, in, out_dev, true);
 }
 
 int ndb_reduce_all(ndb_ctx *ctx, int redop, const ndb_view *in, void *out_host)

@@ -53,36 +53,100 @@ def _on_ctx_stream(arr: Array):
     return torch.cuda.stream(torch.cuda.ExternalStream(arr.ctx.stream_ptr(), device=torch.device("cuda", arr.ctx.device)))
 
 
-def global_sum(local: Array, dist=None):
-    """sum() over all shards: per-GPU tree reduction, then all-reduce of ONE element on the same stream."""
+class PeerGroup:
+    """Peer windows over NVLink for one context per rank (include/ndb200.h, csrc/peer.cu): every rank allocates a window
+    in its own HBM, the 64-byte CUDA IPC handles are exchanged once through torch.distributed (host side, any backend),
+    and from then on the small exchanges that end the sharded reductions are single kernel launches with no NCCL call.
+    All ranks must issue the same sequence of exchanges."""
+
+    def __init__(self, ctx, dist, slot_bytes: int = 1 << 20):
+        self.ctx, self.rank, self.world = ctx, dist.get_rank(), dist.get_world_size()
+        handle = (C.c_ubyte * 64)()
+        check(lib().ndb_peer_window_create(ctx.handle, self.rank, self.world, slot_bytes, handle))
+        handles = [None] * self.world
+        dist.all_gather_object(handles, bytes(handle))
+        blob = (C.c_ubyte * (64 * self.world)).from_buffer_copy(b"".join(handles))
+        check(lib().ndb_peer_window_attach(ctx.handle, blob))
+        dist.barrier()  # nobody stores into a window before everybody has mapped it
+        self.slot_bytes = slot_bytes
+
+    def allreduce_(self, arr: Array, redop: int = Red.SUM) -> Array:
+        """In-place all-reduce (rank order) of a dense device array of at most slot_bytes."""
+        from .array import DTYPE_CODE as _DTYPE_CODE
+        assert arr.is_standard_layout() or arr.ndim == 0
+        check(lib().ndb_peer_allreduce(self.ctx.handle, redop, _DTYPE_CODE[arr.dtype], C.c_void_p(arr.v.ptr), C.c_void_p(arr.v.ptr),
+                                       max(arr.len(), 1)))
+        return arr
+
+    def allgather(self, arr: Array) -> Array:
+        """[world, *arr.shape] with every rank's dense array, in rank order."""
+        from .array import DTYPE_CODE as _DTYPE_CODE
+        assert arr.is_standard_layout() or arr.ndim == 0
+        out = Array.uninit((self.world,) + tuple(arr.shape), arr.dtype, ctx=self.ctx)
+        check(lib().ndb_peer_allgather(self.ctx.handle, _DTYPE_CODE[arr.dtype], C.c_void_p(arr.v.ptr), C.c_void_p(out.v.ptr),
+                                       max(arr.len(), 1)))
+        return out
+
+    def close(self):
+        check(lib().ndb_peer_window_destroy(self.ctx.handle))
+
+
+def _multi(dist) -> bool:
+    return dist is not None and dist.is_initialized() and dist.get_world_size() > 1
+
+
+def global_sum(local: Array, dist=None, peers: PeerGroup | None = None):
+    """sum() over all shards.  With a PeerGroup the kernel that finishes this rank's reduction tree also exchanges the
+    scalar through peer memory (ndb_reduce_all_peer: no extra launch, no NCCL); otherwise an NCCL all-reduce of ONE
+    element follows on the same stream."""
     out = Array.zeros((), local.dtype, ctx=local.ctx)
+    if peers is not None and peers.world > 1:
+        check(lib().ndb_reduce_all_peer(local.ctx.handle, Red.SUM, C.byref(local.v), C.c_void_p(out.v.ptr)))
+        return out.to_numpy()[()]
     check(lib().ndb_reduce_all_dev(local.ctx.handle, Red.SUM, C.byref(local.v), C.c_void_p(out.v.ptr)))
-    if dist is not None and dist.is_initialized() and dist.get_world_size() > 1:
+    if _multi(dist):
         with _on_ctx_stream(out):
             dist.all_reduce(_torch_view(out))
     return out.to_numpy()[()]
 
 
-def sum_axis0(local: Array, dist=None) -> Array:
-    """sum_axis(Axis(0)) when axis 0 is the sharded axis: local partial vector, then all-reduce(sum)."""
+def sum_axis0(local: Array, dist=None, peers: PeerGroup | None = None) -> Array:
+    """sum_axis(Axis(0)) when axis 0 is the sharded axis: local partial vector, then all-reduce(sum) — one peer-memory
+    exchange kernel with a PeerGroup, NCCL otherwise."""
     part = local.sum_axis(0)
-    if dist is not None and dist.is_initialized() and dist.get_world_size() > 1:
+    if peers is not None and peers.world > 1 and part.len() * part.dtype.itemsize <= peers.slot_bytes:
+        return peers.allreduce_(part)
+    if _multi(dist):
         with _on_ctx_stream(part):
             dist.all_reduce(_torch_view(part))
     return part
 
 
-def mean_axis0(local: Array, n_global: int, dist=None) -> Array:
+def mean_axis0(local: Array, n_global: int, dist=None, peers: PeerGroup | None = None) -> Array:
     """mean_axis(Axis(0)): divide by the GLOBAL length after the all-reduce (impl_numeric.rs:342-355)."""
-    s = sum_axis0(local, dist)
+    s = sum_axis0(local, dist, peers)
     s /= local.dtype.type(n_global)
     return s
 
 
-def var_axis0(local: Array, ddof: float, dist=None, want_std: bool = False) -> Array:
+def var_axis0(local: Array, ddof: float, dist=None, want_std: bool = False, peers: PeerGroup | None = None) -> Array:
     """var_axis(Axis(0), ddof): per-shard Welford state (n, mean, M2), all-gather, Chan merge in rank order."""
     import torch
     shape = local.shape[1:]
+    if peers is not None and peers.world > 1 and max(int(np.prod(shape)), 1) * local.dtype.itemsize <= peers.slot_bytes:
+        mean, m2 = Array.uninit(shape, local.dtype, ctx=local.ctx), Array.uninit(shape, local.dtype, ctx=local.ctx)
+        check(lib().ndb_welford_axis(local.ctx.handle, 0, C.byref(local.v), C.byref(mean.v), C.byref(m2.v)))
+        gm, g2 = peers.allgather(mean), peers.allgather(m2)
+        cnt = peers.allgather(Array.from_numpy(np.array(local.shape[0], dtype=np.int64), local.ctx))
+        counts = [int(x) for x in cnt.to_numpy().reshape(-1)]
+        means = [gm.index_axis(0, r) for r in range(peers.world)]
+        m2s = [g2.index_axis(0, r) for r in range(peers.world)]
+        out = Array.uninit(shape, local.dtype, ctx=local.ctx)
+        mv = (View * len(means))(*[m.v for m in means])
+        sv = (View * len(m2s))(*[m.v for m in m2s])
+        cv = (C.c_int64 * len(counts))(*counts)
+        check(lib().ndb_welford_merge(local.ctx.handle, len(counts), cv, mv, sv, float(ddof), int(want_std), C.byref(out.v)))
+        return out
     mean, m2 = Array.uninit(shape, local.dtype, ctx=local.ctx), Array.uninit(shape, local.dtype, ctx=local.ctx)
     check(lib().ndb_welford_axis(local.ctx.handle, 0, C.byref(local.v), C.byref(mean.v), C.byref(m2.v)))
     world = dist.get_world_size() if dist is not None and dist.is_initialized() else 1

@@ -84,6 +84,12 @@ extern "C" {
     pub fn ndb_welford_axis(ctx: *mut ndb_ctx, axis: c_int, input: *const ndb_view, mean_out: *const ndb_view, m2_out: *const ndb_view) -> c_int;
     pub fn ndb_welford_merge(ctx: *mut ndb_ctx, n_shards: c_int, counts: *const i64, means: *const ndb_view, m2s: *const ndb_view, ddof: c_double, want_std: c_int, out: *const ndb_view) -> c_int;
     pub fn ndb_var(ctx: *mut ndb_ctx, input: *const ndb_view, ddof: c_double, want_std: c_int, out_host: *mut c_void) -> c_int;
+    pub fn ndb_peer_window_create(ctx: *mut ndb_ctx, rank: c_int, world: c_int, slot_bytes: size_t, handle_out: *mut c_void) -> c_int;
+    pub fn ndb_peer_window_attach(ctx: *mut ndb_ctx, handles: *const c_void) -> c_int;
+    pub fn ndb_peer_window_destroy(ctx: *mut ndb_ctx) -> c_int;
+    pub fn ndb_peer_allreduce(ctx: *mut ndb_ctx, redop: c_int, dtype: c_int, local_dev: *const c_void, out_dev: *mut c_void, n: i64) -> c_int;
+    pub fn ndb_peer_allgather(ctx: *mut ndb_ctx, dtype: c_int, local_dev: *const c_void, out_dev: *mut c_void, n: i64) -> c_int;
+    pub fn ndb_reduce_all_peer(ctx: *mut ndb_ctx, redop: c_int, input: *const ndb_view, out_dev: *mut c_void) -> c_int;
     pub fn ndb_accumulate_axis(ctx: *mut ndb_ctx, op: c_int, axis: c_int, v: *const ndb_view) -> c_int;
     // ndarray's own CBLAS boundary (src/linalg/impl_linalg.rs:466-491, :116-122); normally bound through cblas-sys
     pub fn cblas_sgemm(layout: c_int, transa: c_int, transb: c_int, m: c_int, n: c_int, k: c_int, alpha: f32, a: *const f32, lda: c_int, b: *const f32, ldb: c_int, beta: f32, c: *mut f32, ldc: c_int);

@@ -341,3 +341,50 @@ def test_split_column_reduction_one_launch_equals_two_launches(nd, monkeypatch):
         monkeypatch.delenv("NDB_RED_TWO_KERNELS", raising=False)
         for a, b, c in zip(*got):
             assert np.array_equal(a, b) and np.array_equal(a, c)
+
+
+def test_peer_window_world1_and_symbols(nd):
+    """The peer-memory exchange with a one-rank world: all-reduce is the identity, all-gather a copy and the fused
+    sum + exchange equals the plain sum (the multi-rank protocol runs under torchrun: benchmarks/dist_check.py)."""
+    import ctypes as C
+    from ndarray_b200 import Array
+    from ndarray_b200._ffi import check, lib
+    from ndarray_b200.array import DTYPE_CODE, Red
+    ctx = nd.Context(0)
+    try:
+        handle = (C.c_ubyte * 64)()
+        check(lib().ndb_peer_window_create(ctx.handle, 0, 1, 1 << 16, handle))
+        assert lib().ndb_peer_window_create(ctx.handle, 0, 1, 1 << 16, handle) != 0  # one window per context
+        h = np.arange(1000, dtype=np.float64) - 300.0
+        d = Array.from_numpy(h, ctx)
+        for _ in range(3):
+            check(lib().ndb_peer_allreduce(ctx.handle, Red.SUM, DTYPE_CODE[d.dtype], C.c_void_p(d.v.ptr), C.c_void_p(d.v.ptr), 1000))
+        assert np.array_equal(d.to_numpy(), h)
+        out = Array.uninit((1, 1000), np.float64, ctx=ctx)
+        check(lib().ndb_peer_allgather(ctx.handle, DTYPE_CODE[d.dtype], C.c_void_p(d.v.ptr), C.c_void_p(out.v.ptr), 1000))
+        assert np.array_equal(out.to_numpy()[0], h)
+        s = Array.zeros((), np.float64, ctx=ctx)
+        check(lib().ndb_reduce_all_peer(ctx.handle, Red.SUM, C.byref(d.v), C.c_void_p(s.v.ptr)))
+        assert s.to_numpy()[()] == d.sum()
+        big = Array.zeros((1 << 16,), np.float64, ctx=ctx)  # 512 KiB > the 64 KiB slot
+        st = lib().ndb_peer_allreduce(ctx.handle, Red.SUM, 1, C.c_void_p(big.v.ptr), C.c_void_p(big.v.ptr), 1 << 16)
+        assert st == 6  # NDB_ERR_OVERFLOW
+        check(lib().ndb_peer_window_destroy(ctx.handle))
+        assert lib().ndb_peer_allreduce(ctx.handle, Red.SUM, 1, C.c_void_p(d.v.ptr), C.c_void_p(d.v.ptr), 10) == 7  # no window
+    finally:
+        ctx.close()
+
+
+def test_multi_gpu_protocol_under_torchrun():
+    """Two ranks on two GPUs: sharded reductions with NCCL and with peer-memory exchanges, row-sharded GEMM
+    (benchmarks/dist_check.py).  Skipped on a single-GPU box."""
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    from pathlib import Path
+    root = Path(__file__).resolve().parent.parent
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29577", str(root / "benchmarks" / "dist_check.py")], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "dist_check ok on 2 GPUs" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
