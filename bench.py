@@ -170,7 +170,7 @@ def cpu_baseline_sample(budget_s=20.0):
     from oracle import oracle as orc
     orc.build()
     threads = orc.max_threads()
-    n = 256
+    n = N3  # the bench workload itself (512^3), fewer passes: a smaller cube would sit in the CPU's last-level cache
     x, y, row = host_inputs(n, 3)
     out = np.empty((n, n, n), np.float32)
     half = np.empty((n // 2, n, n), np.float32)
@@ -184,7 +184,7 @@ def cpu_baseline_sample(budget_s=20.0):
     step()
     t0 = time.perf_counter()
     reps = 0
-    while reps < 3 or (time.perf_counter() - t0 < budget_s / 2 and reps < 50):
+    while reps < 3 or (time.perf_counter() - t0 < budget_s / 2 and reps < 60):
         step()
         reps += 1
     dt = time.perf_counter() - t0

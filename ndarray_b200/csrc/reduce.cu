@@ -344,24 +344,33 @@ __device__ __forceinline__ A ldcg_state(const A *p)
 template <typename A>
 __device__ __forceinline__ A merge_splits(const A *p, int splits, int64_t pitch)
 {
+    // batch size by state size: eight 24-byte Welford states in flight cost 48 registers and the third CTA per SM
+    // (var_axis 6.6 -> 4.8 TB/s), so wide states go two at a time
+    constexpr int B = sizeof(A) > 8 ? 2 : 8;
     A r = ldcg_state(p);
     int sidx = 1;
-    for (; sidx + 8 <= splits; sidx += 8) {
-        A b[8];
+    for (; sidx + B <= splits; sidx += B) {
+        A b[B];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) b[u] = ldcg_state(p + (int64_t)(sidx + u) * pitch);
+        for (int u = 0; u < B; ++u) b[u] = ldcg_state(p + (int64_t)(sidx + u) * pitch);
 #pragma unroll
-        for (int u = 0; u < 8; ++u) r.merge(b[u]);
+        for (int u = 0; u < B; ++u) r.merge(b[u]);
     }
     for (; sidx < splits; ++sidx) r.merge(ldcg_state(p + (int64_t)sidx * pitch));
     return r;
 }
 
+#ifndef NDB_RED_COLS_MINB_W
+#define NDB_RED_COLS_MINB_W 3
+#endif
+#ifndef NDB_RED_COLS_WU
+#define NDB_RED_COLS_WU 8
+#endif
 // ---- cols: a kept axis is unit-stride ------------------------------------------------------------
 // blockDim = (32, 8).  A block owns 32*W consecutive outputs along the last kept axis (in_stride 1) and
 // rows [split*chunk, ...) of the reduced axis; thread (tx, ty) strides rows ty, ty+8, ...
 template <typename T, int R, int FIN, int W>
-__global__ void __launch_bounds__(256) red_cols(RedArgs a)
+__global__ void __launch_bounds__(256, R == R_WELFORD ? NDB_RED_COLS_MINB_W : 3) red_cols(RedArgs a)  // 3 CTAs/SM register budget (<= 85): f64 sum 6.52 -> 6.95 TB/s vs the default allocation
 {
     using V = Vec128<T>;
     static_assert(W == 1 || W == V::N, "W is 1 or one 128-bit vector");
@@ -399,7 +408,7 @@ __global__ void __launch_bounds__(256) red_cols(RedArgs a)
         const T *src = reinterpret_cast<const T *>(a.in) + in_off + c0;
         if (c0 < ncol) {  // ncol % W == 0 when W > 1 (host check), so a vector is all-in or all-out
             int64_t r = r0 + ty;
-            constexpr int U = (R == R_WELFORD) ? 4 : 8;  // rows in flight per thread
+            constexpr int U = (R == R_WELFORD) ? NDB_RED_COLS_WU : 8;  // rows in flight per thread
             if constexpr (W > 1) {
                 for (; r + 8 * (U - 1) < r1; r += 8 * U) {
                     V v[U];
