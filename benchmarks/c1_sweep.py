@@ -19,6 +19,22 @@ arrs = [Array.borrow(t.data_ptr(), (n, n), np.float32, "C", ctx, owner=t) for t 
 outs = [Array.uninit((n,), np.float32, ctx=ctx) for _ in bufs]
 
 
+def run_batch(ax, rounds=10):
+    """8 back-to-back launches (one per 64 MiB buffer, so each input is cold in L2) between one event pair."""
+    from ndarray_b200.array import Red
+    import ctypes as C
+    L = nd.lib()
+    evs = [(ctx.event(), ctx.event()) for _ in range(rounds)]
+    for a, b in evs:
+        ctx.record(a)
+        for i in range(8):
+            L.ndb_reduce_axis(ctx.handle, Red.SUM, ax, C.byref(arrs[i].v), C.byref(outs[i].v), 0.0)
+        ctx.record(b)
+    ctx.sync()
+    ms = [ctx.elapsed_ms(a, b) / 8 for a, b in evs]
+    return statistics.median(ms) * 1e3, min(ms) * 1e3
+
+
 def run(ax, iters=40):
     from ndarray_b200.array import Red
     import ctypes as C
@@ -36,12 +52,24 @@ def run(ax, iters=40):
     return statistics.median(ms) * 1e3, min(ms) * 1e3
 
 
-for per_sm in ("1", "2", "3", "4", "6", "8"):
-    os.environ["NDB_RED_COLS_PER_SM"] = per_sm
-    med, best = run(0)
-    print(f"axis0 per_sm={per_sm}: median {med:5.1f} us best {best:5.1f} us", flush=True)
-os.environ.pop("NDB_RED_COLS_PER_SM")
-for wm in ("1024", "4096", "8192"):
-    os.environ["NDB_RED_WARP_MAX"] = wm
+for wpb in ("8", "4", "2", "1"):
+    os.environ["NDB_RED_WPB"] = wpb
     med, best = run(1)
-    print(f"axis1 warp_max={wm}: median {med:5.1f} us best {best:5.1f} us", flush=True)
+    print(f"axis1 warps/block={wpb}: median {med:5.1f} us best {best:5.1f} us", flush=True)
+os.environ.pop("NDB_RED_WPB")
+med, best = run(1)
+print(f"axis1 default: median {med:5.1f} us best {best:5.1f} us", flush=True)
+med, best = run(0)
+print(f"axis0 default: median {med:5.1f} us best {best:5.1f} us", flush=True)
+for ax in (0, 1):
+    med, best = run_batch(ax)
+    print(f"axis{ax} back-to-back x8: median {med:5.2f} us per launch ({4 * n * n / med / 1e3:6.0f} GB/s), best {best:5.2f}", flush=True)
+for wpb in ("8", "4", "2"):
+    os.environ["NDB_RED_WPB"] = wpb
+    med, best = run_batch(1)
+    print(f"axis1 back-to-back warps/block={wpb}: {med:5.2f} us", flush=True)
+os.environ.pop("NDB_RED_WPB")
+for per_sm in ("2", "3", "4", "6", "8"):
+    os.environ["NDB_RED_COLS_PER_SM"] = per_sm
+    med, best = run_batch(0)
+    print(f"axis0 back-to-back per_sm={per_sm}: {med:5.2f} us", flush=True)

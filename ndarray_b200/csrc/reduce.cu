@@ -24,6 +24,17 @@
 
 #include "zip_kernels.cuh"  // w_add & friends, Vec128
 #include "peer.cuh"
+
+// tuning knobs (compile-time so that benchmarks/build_variant.sh can sweep them)
+#ifndef NDB_RED_LANES_U
+#define NDB_RED_LANES_U 8
+#endif
+#ifndef NDB_RED_COLS_MINB_W
+#define NDB_RED_COLS_MINB_W 3
+#endif
+#ifndef NDB_RED_COLS_WU
+#define NDB_RED_COLS_WU 8
+#endif
 #include "zip_plan.h"
 
 namespace ndb {
@@ -274,9 +285,10 @@ __global__ void __launch_bounds__(256) red_lanes(RedArgs a)
     constexpr int N = V::N;
     __shared__ Acc<T, R> smem[32];
     const int lane = threadIdx.x & 31;
-    const int64_t groups = WARP ? (a.n_out + 7) / 8 : a.n_out;
+    const int wpb = blockDim.x >> 5;  // WARP: one lane per warp, wpb lanes per block
+    const int64_t groups = WARP ? (a.n_out + wpb - 1) / wpb : a.n_out;
     for (int64_t g = blockIdx.x; g < groups; g += gridDim.x) {
-        const int64_t o = WARP ? g * 8 + (threadIdx.x >> 5) : g;
+        const int64_t o = WARP ? g * wpb + (threadIdx.x >> 5) : g;
         const bool live = o < a.n_out;
         int64_t in_off = 0, out_off = 0, out2_off = 0;
         if (live) kept_offsets(a.k, o, in_off, out_off, out2_off);
@@ -291,7 +303,7 @@ __global__ void __launch_bounds__(256) red_lanes(RedArgs a)
                 const V *vsrc = reinterpret_cast<const V *>(src);
                 const int64_t nv = a.n / N;
                 int64_t i = tid;
-                constexpr int U = (R == R_WELFORD) ? 4 : 8;  // vectors in flight per thread
+                constexpr int U = (R == R_WELFORD) ? 4 : NDB_RED_LANES_U;  // vectors in flight per thread
                 for (; i + (U - 1) * (int64_t)nt < nv; i += U * (int64_t)nt) {
                     V v[U];
 #pragma unroll
@@ -360,12 +372,6 @@ __device__ __forceinline__ A merge_splits(const A *p, int splits, int64_t pitch)
     return r;
 }
 
-#ifndef NDB_RED_COLS_MINB_W
-#define NDB_RED_COLS_MINB_W 3
-#endif
-#ifndef NDB_RED_COLS_WU
-#define NDB_RED_COLS_WU 8
-#endif
 // ---- cols: a kept axis is unit-stride ------------------------------------------------------------
 // blockDim = (32, 8).  A block owns 32*W consecutive outputs along the last kept axis (in_stride 1) and
 // rows [split*chunk, ...) of the reduced axis; thread (tx, ty) strides rows ty, ty+8, ...
@@ -974,11 +980,17 @@ static int reduce_axis_launch(ndb_ctx *ctx, RedArgs &a, const ZipPlan &z)
         bool vec = a.s == 1 && a.n % vecn == 0 && ((uintptr_t)a.in % 16) == 0 && a.n >= 4 * vecn;
         for (int d = 0; d < a.k.n && vec; ++d) vec = a.k.dim[d] == 1 || a.k.in_stride[d] % vecn == 0;
         const bool warp = a.n <= (getenv("NDB_RED_WARP_MAX") ? atoll(getenv("NDB_RED_WARP_MAX")) : 8192);
-        const int64_t groups = warp ? (a.n_out + 7) / 8 : a.n_out;
-        const unsigned blocks = (unsigned)std::min<int64_t>(groups, (int64_t)1 << 30);
+        // warp-per-lane: smaller blocks when 8 lanes per block would leave the SMs unevenly loaded (4096 lanes = 3.46
+        // blocks of 8 per SM: the SMs holding 4 set the pace)
+        int wpb = 8;
+        if (getenv("NDB_RED_WPB")) wpb = atoi(getenv("NDB_RED_WPB"));
+        else while (wpb > 2 && (a.n_out + wpb - 1) / wpb < (int64_t)ctx->sm_count * 6) wpb >>= 1;
+        const int64_t groups = warp ? (a.n_out + wpb - 1) / wpb : a.n_out;
+        unsigned blocks = (unsigned)std::min<int64_t>(groups, (int64_t)1 << 30);
+        if (getenv("NDB_RED_LANES_BLOCKS")) blocks = std::min<unsigned>(blocks, (unsigned)atoi(getenv("NDB_RED_LANES_BLOCKS")));
         if (warp) {
-            if (vec) red_lanes<T, R, FIN, true, true><<<blocks, 256, 0, st>>>(a);
-            else red_lanes<T, R, FIN, true, false><<<blocks, 256, 0, st>>>(a);
+            if (vec) red_lanes<T, R, FIN, true, true><<<blocks, 32 * wpb, 0, st>>>(a);
+            else red_lanes<T, R, FIN, true, false><<<blocks, 32 * wpb, 0, st>>>(a);
         } else {
             if (vec) red_lanes<T, R, FIN, false, true><<<blocks, 256, 0, st>>>(a);
             else red_lanes<T, R, FIN, false, false><<<blocks, 256, 0, st>>>(a);
@@ -993,14 +1005,16 @@ static int reduce_axis_launch(ndb_ctx *ctx, RedArgs &a, const ZipPlan &z)
         const int w = vec ? (int)vecn : 1;
         const int64_t tiles = (ncol + 32 * w - 1) / (32 * w);
         const int64_t total = tiles * (a.n_out / ncol);
-        // enough blocks to fill the machine ~4 deep, but every split keeps >= 64 rows
-        // blocks per SM to aim for: measured best 8 for the plain reducers, 6 for Welford (72 registers: 3 CTAs/SM, two waves)
-        // (a problem that one wave of 4 CTAs/SM covers - e.g. 4096^2 f32 - is fastest as exactly that one wave)
+        // Large problems: enough blocks to fill the machine several deep (measured best 8 per SM for the plain reducers, 6
+        // for Welford); every split keeps >= 64 rows.  A problem of at most 128 MiB (C1: 4096^2 f32) is fastest as ONE
+        // resident wave of at most two fat blocks per SM (ncu durations for C1, splits 5/8/9/10/14/19/37:
+        // 18.6 / 15.6 / 15.8 / 16.2 / 20.2 / 19.7 / 21.6 us), so there the split count is rounded DOWN to 2 per SM.
         const bool small = (double)a.n * (double)a.n_out * sizeof(T) <= 128.0 * 1024 * 1024;
-        const int per_sm = getenv("NDB_RED_COLS_PER_SM") ? atoi(getenv("NDB_RED_COLS_PER_SM")) : (small ? 4 : (R == R_WELFORD ? 6 : 8));
-        int64_t want = ((int64_t)ctx->sm_count * per_sm + total - 1) / total;
+        const int per_sm = getenv("NDB_RED_COLS_PER_SM") ? atoi(getenv("NDB_RED_COLS_PER_SM")) : (small ? 2 : (R == R_WELFORD ? 6 : 8));
+        int64_t want = small ? std::max<int64_t>(1, (int64_t)ctx->sm_count * per_sm / total) : ((int64_t)ctx->sm_count * per_sm + total - 1) / total;
         int64_t max_splits = std::max<int64_t>(1, a.n / 64);
         int splits = (int)std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(want, max_splits), 256));
+        if (getenv("NDB_RED_COLS_SPLITS")) splits = (int)std::max<int64_t>(1, std::min<int64_t>(atoi(getenv("NDB_RED_COLS_SPLITS")), max_splits));
         a.splits = splits;
         a.tickets = nullptr;
         if (splits > 1) {
