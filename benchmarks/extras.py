@@ -77,6 +77,14 @@ def run_extras(nd, ctx, torch, dist, rank, world, local, peak_gbs):
         rec(f"C1_sum_axis{ax}_f32_4096^2", 4 * n * n + 4 * n, med, best)
         med, best = _time(ctx, c1_sum_into, 40, 4)
         rec(f"C1_sum_axis{ax}_f32_4096^2_into_preallocated", 4 * n * n + 4 * n, med, best)
+
+        # CUDA events tick in ~2 us steps on this box, too coarse for a 15 us kernel: also time 12 launches back to back
+        # (three passes over the four 64 MiB buffer sets, so every input is cold in L2) between one event pair
+        def c1_sum_x12(ax=ax):
+            for _ in range(12):
+                c1_sum_into(ax)
+        med, best = _time(ctx, c1_sum_x12, 10, 2)
+        rec(f"C1_sum_axis{ax}_f32_4096^2_into_preallocated_12_back_to_back", 12 * (4 * n * n + 4 * n), med, best)
     del sets
     # ---- C2 variants: inner-axis step, map_collect (fresh output), all three views combined ------------
     n = 512
@@ -234,6 +242,34 @@ def run_extras(nd, ctx, torch, dist, rank, world, local, peak_gbs):
                     "collective": "ncclBroadcast of B (%d MiB) inside the timed step" % (n * n * ta.element_size() >> 20)}
             del ta, tb, tc
         torch.cuda.empty_cache()
+    # ---- C4 through ndarray's own plugin boundary: cblas_{d,s}gemm with HOST pointers (what `features = ["blas"]` calls;
+    #      pageable host memory like ndarray's Vec, H2D of A and B and D2H of C inside the timed call) -----------------
+    if rank == 0 and world == 1:
+        try:
+            import ctypes as C
+            import time as _t
+            L = nd.lib()
+            n = 8192
+            rng = np.random.default_rng(4)
+            for dt, fn_name, cty in ((np.float64, "cblas_dgemm", C.c_double), (np.float32, "cblas_sgemm", C.c_float)):
+                fn = getattr(L, fn_name)
+                fn.restype = None
+                fn.argtypes = [C.c_int] * 6 + [cty, C.c_void_p, C.c_int, C.c_void_p, C.c_int, cty, C.c_void_p, C.c_int]
+                ha = rng.standard_normal((n, n), dtype=dt)
+                hb = rng.standard_normal((n, n), dtype=dt)
+                hc = np.zeros((n, n), dtype=dt)
+                times = []
+                for _ in range(3):
+                    t0 = _t.perf_counter()
+                    fn(101, 111, 111, n, n, n, 1.0, ha.ctypes.data, n, hb.ctypes.data, n, 0.0, hc.ctypes.data, n)
+                    times.append(_t.perf_counter() - t0)
+                best = min(times[1:])
+                out[f"C4_{fn_name}_8192^3_host_pointers_end_to_end"] = {
+                    "TFLOP/s": round(2.0 * n ** 3 / best / 1e12, 2), "ms": round(best * 1e3, 1),
+                    "host_bytes_moved": 3 * n * n * np.dtype(dt).itemsize, "note": "pageable host buffers, staged H2D/D2H inside the call"}
+                del ha, hb, hc
+        except Exception as e:
+            out["C4_cblas_end_to_end"] = {"error": repr(e)}
     if rank == 0 and world == 1:
         try:
             out["cpu_stand_in"] = cpu_stand_ins()

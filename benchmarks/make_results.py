@@ -40,16 +40,34 @@ def main():
             out.append(f"| {n} | {d['value']:.0f} | {d['value'] / n1['value']:.2f} | {d['e2e']['value']:.0f} |")
     d8 = load("r01_bench_n8.json")
     if d8 and "extra" in d8 and "C5_zip+global_sum_f32" in d8["extra"]:
-        c5 = d8["extra"]["C5_zip+global_sum_f32"]
-        out += ["", f"Config 5 shape at 8 GPUs (per rank 2^29 f32 elements: `a = b*c + a`, `sum()`, one-element NCCL all-reduce on the same stream): "
-                    f"**{c5['GB/s_aggregate']:.0f} GB/s aggregate**, {c5['ms']} ms per step."]
+        ex = d8["extra"]
+        c5 = ex["C5_zip+global_sum_f32"]
+        out += ["", "## Multi-GPU exchange steps (8 GPUs, `extra` of `profiles/r01_bench_n8.json`)", "",
+                "| case | NCCL (`torch.distributed` on the ctx stream) | peer memory over NVLink (`csrc/peer.cu`) |", "|---|---|---|"]
+        if "C5_zip+global_sum_f32_peer_fused" in ex:
+            pf = ex["C5_zip+global_sum_f32_peer_fused"]
+            out.append(f"| config 5 shape: per rank 2^29 f32, `a = b*c + a` then global `sum()` | {c5['GB/s_aggregate']:.0f} GB/s aggregate, {c5['ms']} ms | "
+                       f"**{pf['GB/s_aggregate']:.0f} GB/s aggregate**, {pf['ms']} ms (exchange fused into the sum's finishing kernel) |")
+        for lab, name in (("1elt", "all-reduce of one element"), ("128KiB", "all-reduce of 128 KiB (config 3's `sum_axis(Axis(0))` vector)")):
+            k = f"allreduce_latency_{lab}"
+            if k in ex:
+                out.append(f"| {name} | {ex[k]['nccl_us']} µs | **{ex[k]['peer_memory_us']} µs** |")
+        if "C3_sum_axis0_sharded_f64_nccl" in ex:
+            a, b = ex["C3_sum_axis0_sharded_f64_nccl"], ex["C3_sum_axis0_sharded_f64_peer"]
+            out.append(f"| sharded `sum_axis(Axis(0))`, 2048x16384 f64 per rank + exchange | {a['GB/s_aggregate']:.0f} GB/s aggregate ({a['ms'] * 1e3:.0f} µs) | "
+                       f"**{b['GB/s_aggregate']:.0f} GB/s aggregate** ({b['ms'] * 1e3:.0f} µs) |")
+        out += ["", "Row-sharded `general_mat_mul` (A and C sharded along Axis(0), 8192 rows per rank; B broadcast from rank 0 with "
+                    "`ncclBroadcast` INSIDE every timed step):", "", "| case | aggregate | per step |", "|---|---|---|"]
+        for k, v in ex.items():
+            if "rowsharded" in k:
+                out.append(f"| {k} | {v['TFLOP/s_aggregate']} TFLOP/s | {v['ms']} ms |")
     out += ["", "## Other BASELINE configs (1 GPU, `extra` in the bench line)", "", "| case | measured | of peak |", "|---|---|---|"]
     for k, v in n1.get("extra", {}).items():
         if "GB/s" in v:
             out.append(f"| {k} | {v['GB/s']} GB/s ({v['ms'] * 1e3:.1f} µs) | {v['frac_of_measured_peak']} |")
         elif "TFLOP/s" in v:
             out.append(f"| {k} | {v['TFLOP/s']} TFLOP/s" + (f" ({v['ms']} ms)" if "ms" in v else "") + " | |")
-    out += ["", "GEMM context: the f64 kernel reaches %.2f of cuBLAS `Dgemm` on the same box; the 3xTF32 kernel issues three tensor "
+    out += ["", "GEMM context: the TMA-fed f64 kernel reaches %.2f x cuBLAS `Dgemm` on the same box (37.3 TFLOP/s is the FP64 tensor pipe's peak at 1965 MHz); the 3xTF32 kernel issues three tensor "
             "MMAs per logical MMA, so its tensor-pipe rate is 3× its reported figure — compare with the cuBLAS 1xTF32 line: the pipe "
             "is power-limited at about that rate (`NDB_GEMM_DEBUG=1`, which removes all TMA traffic, does not speed the kernel up)." % (
                 n1["extra"]["C4_gemm_f64_8192^3_CCC"]["TFLOP/s"] / n1["extra"]["C4_comparator_cublas_f64_8192^3"]["TFLOP/s"]) if "extra" in n1 and "C4_gemm_f64_8192^3_CCC" in n1["extra"] else ""]
