@@ -28,18 +28,29 @@ namespace ndb {
 
 namespace {
 
-constexpr int BM = 128, BN = 128, BK = 32, STAGES = 3;
-constexpr int CONSUMER_WARPS = 8, THREADS = 32 * (CONSUMER_WARPS + 1);
-constexpr int MI = 8, NJ = 4;  // DMMA tiles per warp: 64 x 32 warp tile, warps 2 (m) x 4 (n)
-constexpr int A_STAGE = BM * BK, B_STAGE = BN * BK;  // doubles
-constexpr uint32_t STAGE_BYTES = (A_STAGE + B_STAGE) * sizeof(double);
-constexpr size_t SMEM_BYTES = (size_t)STAGES * STAGE_BYTES + 1024 /* alignment slack */ + 2 * STAGES * sizeof(uint64_t);
+constexpr int BK = 32, STAGES = 3;
+
+// Two tile shapes: 128 x 128 (8 DMMA warps as 2 x 4, 64 x 32 warp tiles, one CTA per SM) for problems that fill the
+// machine, and 64 x 64 (4 DMMA warps as 2 x 2, 32 x 32 warp tiles, two CTAs per SM) when 128 x 128 tiles would leave
+// SMs idle (a 1024^2 output is only 64 big tiles on 148 SMs).
+template <int TILE>
+struct Shape {
+    static constexpr int BM = TILE, BN = TILE;
+    static constexpr int WARPS_M = 2, WARPS_N = TILE == 128 ? 4 : 2;
+    static constexpr int CONSUMER_WARPS = WARPS_M * WARPS_N, THREADS = 32 * (CONSUMER_WARPS + 1);
+    static constexpr int MI = BM / (WARPS_M * 8), NJ = BN / (WARPS_N * 8);  // DMMA tiles per warp
+    static constexpr int A_STAGE = BM * BK, B_STAGE = BN * BK;              // doubles
+    static constexpr uint32_t STAGE_BYTES = (A_STAGE + B_STAGE) * sizeof(double);
+    static constexpr size_t SMEM_BYTES = (size_t)STAGES * STAGE_BYTES + 1024 /* alignment slack */ + 2 * STAGES * sizeof(uint64_t);
+    static constexpr int MIN_CTAS = TILE == 128 ? 1 : 2;
+};
 
 struct TmaArgs {
     double *c;
     int64_t m, n, k, ldc;
     double alpha, beta;
     int tiles_m, tiles_n;
+    int csize;  // thread-block cluster size along K (1 = every CTA owns a whole output tile)
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -71,6 +82,18 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap *map
         "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
         : "memory");
 }
+__device__ __forceinline__ void cluster_sync_all()
+{
+    asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ double ld_cluster_f64(uint32_t local_addr, uint32_t rank)
+{
+    uint32_t remote;
+    double v;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local_addr), "r"(rank));
+    asm volatile("ld.shared::cluster.f64 %0, [%1];" : "=d"(v) : "r"(remote) : "memory");
+    return v;
+}
 __device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double b)
 {
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
@@ -78,18 +101,23 @@ __device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double
                  : "d"(a), "d"(b));
 }
 
-// element (row, k) of a staged 128 x BK tile, k = kk + t with kk a multiple of 4
-template <bool K_CONTIG>
+// element (row, k) of a staged ROWS x BK tile, k = kk + t with kk a multiple of 4
+template <bool K_CONTIG, int ROWS>
 __device__ __forceinline__ double frag(const double *st, int row, int kk, int t)
 {
-    if constexpr (K_CONTIG) return st[((kk >> 2) * 128 + row) * 4 + t];
+    if constexpr (K_CONTIG) return st[((kk >> 2) * ROWS + row) * 4 + t];
     else return st[((row >> 2) * BK + kk + t) * 4 + (row & 3)];
 }
 
-template <bool A_KC, bool B_KC>
-__global__ void __launch_bounds__(THREADS, 1)
+template <bool A_KC, bool B_KC, int TILE>
+__global__ void __launch_bounds__(Shape<TILE>::THREADS, Shape<TILE>::MIN_CTAS)
 gemm_f64_tma(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, TmaArgs p)
 {
+    using S = Shape<TILE>;
+    constexpr int BM = S::BM, BN = S::BN, MI = S::MI, NJ = S::NJ, CONSUMER_WARPS = S::CONSUMER_WARPS;
+    constexpr int A_STAGE = S::A_STAGE, B_STAGE = S::B_STAGE;
+    constexpr uint32_t STAGE_BYTES = S::STAGE_BYTES;
+    constexpr int WTM = MI * 8, WTN = NJ * 8;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t pad = ((raw + 1023u) & ~1023u) - raw;
@@ -100,7 +128,11 @@ gemm_f64_tma(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
 
     // rasterise in groups of 8 tile-rows so that concurrently resident blocks share A and B panels in L2
     constexpr int GROUP = 8;
-    const int bid = blockIdx.x;
+    constexpr bool SPLIT = TILE == 64;  // split-K clusters exist for the small tile only: the big one keeps its registers
+    const int csize = SPLIT ? p.csize : 1;
+    uint32_t crank = 0;
+    if (SPLIT && csize > 1) asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(crank));
+    const int bid = SPLIT ? blockIdx.x / csize : blockIdx.x;
     const int per_group = GROUP * p.tiles_n;
     const int grp = bid / per_group;
     const int first_m = grp * GROUP;
@@ -109,7 +141,10 @@ gemm_f64_tma(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
     const int tile_m = first_m + in_grp % gsize;
     const int tile_n = in_grp / gsize;
     const int64_t m0 = (int64_t)tile_m * BM, n0 = (int64_t)tile_n * BN;
-    const int ktiles = (int)((p.k + BK - 1) / BK);
+    // split-K over the cluster: rank r accumulates k-tiles [kt0, kt0 + ktiles)
+    const int all_ktiles = (int)((p.k + BK - 1) / BK);
+    const int kt0 = SPLIT ? (int)((int64_t)all_ktiles * crank / csize) : 0;
+    const int ktiles = SPLIT ? (int)((int64_t)all_ktiles * (crank + 1) / csize) - kt0 : all_ktiles;
 
     if (tid == 0) {
 #pragma unroll
@@ -121,33 +156,33 @@ gemm_f64_tma(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
     }
     __syncthreads();
 
-    if (warp == CONSUMER_WARPS) {
-        // ---- producer: one thread feeds the TMA engine ----
-        if (lane == 0) {
-            for (int kt = 0; kt < ktiles; ++kt) {
-                const int s = kt % STAGES;
-                if (kt >= STAGES) mbar_wait(empty0 + 8 * s, (uint32_t)(kt / STAGES - 1) & 1u);
-                const uint32_t a_dst = smem_u32(tiles + (size_t)s * (A_STAGE + B_STAGE));
-                const uint32_t b_dst = a_dst + A_STAGE * sizeof(double);
-                mbar_expect_tx(full0 + 8 * s, STAGE_BYTES);
-                if constexpr (A_KC) tma_load_3d(a_dst, &map_a, full0 + 8 * s, 0, (int)m0, kt * (BK / 4));
-                else tma_load_3d(a_dst, &map_a, full0 + 8 * s, 0, kt * BK, (int)(m0 >> 2));
-                if constexpr (B_KC) tma_load_3d(b_dst, &map_b, full0 + 8 * s, 0, (int)n0, kt * (BK / 4));
-                else tma_load_3d(b_dst, &map_b, full0 + 8 * s, 0, kt * BK, (int)(n0 >> 2));
-            }
-        }
-        return;
-    }
-
-    // ---- consumers: 8 warps as 2 (m) x 4 (n), 64 x 32 warp tile ----
+    const bool producer = warp == CONSUMER_WARPS;
     const int g = lane >> 2, t = lane & 3;
-    const int wm = warp >> 2, wn = warp & 3;
+    const int wm = warp / S::WARPS_N, wn = warp % S::WARPS_N;
     double acc[MI][NJ][2];
 #pragma unroll
     for (int i = 0; i < MI; ++i)
 #pragma unroll
         for (int j = 0; j < NJ; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
+    if (producer) {
+        // ---- producer: one thread feeds the TMA engine ----
+        if (lane == 0) {
+            for (int kt = 0; kt < ktiles; ++kt) {
+                const int s = kt % STAGES;
+                const int gk = kt0 + kt;
+                if (kt >= STAGES) mbar_wait(empty0 + 8 * s, (uint32_t)(kt / STAGES - 1) & 1u);
+                const uint32_t a_dst = smem_u32(tiles + (size_t)s * (A_STAGE + B_STAGE));
+                const uint32_t b_dst = a_dst + A_STAGE * sizeof(double);
+                mbar_expect_tx(full0 + 8 * s, STAGE_BYTES);
+                if constexpr (A_KC) tma_load_3d(a_dst, &map_a, full0 + 8 * s, 0, (int)m0, gk * (BK / 4));
+                else tma_load_3d(a_dst, &map_a, full0 + 8 * s, 0, gk * BK, (int)(m0 >> 2));
+                if constexpr (B_KC) tma_load_3d(b_dst, &map_b, full0 + 8 * s, 0, (int)n0, gk * (BK / 4));
+                else tma_load_3d(b_dst, &map_b, full0 + 8 * s, 0, gk * BK, (int)(n0 >> 2));
+            }
+        }
+    } else
+    // ---- consumers: WARPS_M x WARPS_N warps, (MI*8) x (NJ*8) warp tile ----
     for (int kt = 0; kt < ktiles; ++kt) {
         const int s = kt % STAGES;
         mbar_wait(full0 + 8 * s, (uint32_t)(kt / STAGES) & 1u);
@@ -155,17 +190,17 @@ gemm_f64_tma(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
         const double *bs = as + A_STAGE;
         double af[2][MI], bf[2][NJ];
 #pragma unroll
-        for (int i = 0; i < MI; ++i) af[0][i] = frag<A_KC>(as, wm * 64 + i * 8 + g, 0, t);
+        for (int i = 0; i < MI; ++i) af[0][i] = frag<A_KC, BM>(as, wm * WTM + i * 8 + g, 0, t);
 #pragma unroll
-        for (int j = 0; j < NJ; ++j) bf[0][j] = frag<B_KC>(bs, wn * 32 + j * 8 + g, 0, t);
+        for (int j = 0; j < NJ; ++j) bf[0][j] = frag<B_KC, BN>(bs, wn * WTN + j * 8 + g, 0, t);
 #pragma unroll
         for (int kk = 0; kk < BK; kk += 4) {
             const int cur = (kk >> 2) & 1, nxt = cur ^ 1;
             if (kk + 4 < BK) {
 #pragma unroll
-                for (int i = 0; i < MI; ++i) af[nxt][i] = frag<A_KC>(as, wm * 64 + i * 8 + g, kk + 4, t);
+                for (int i = 0; i < MI; ++i) af[nxt][i] = frag<A_KC, BM>(as, wm * WTM + i * 8 + g, kk + 4, t);
 #pragma unroll
-                for (int j = 0; j < NJ; ++j) bf[nxt][j] = frag<B_KC>(bs, wn * 32 + j * 8 + g, kk + 4, t);
+                for (int j = 0; j < NJ; ++j) bf[nxt][j] = frag<B_KC, BN>(bs, wn * WTN + j * 8 + g, kk + 4, t);
             } else {
                 // the stage's last fragments are in registers: hand it back to the producer
                 __syncwarp();
@@ -178,15 +213,47 @@ gemm_f64_tma(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
         }
     }
 
+    if (SPLIT && csize > 1) {
+        // Split-K hand-over through distributed shared memory: ranks > 0 park their partial accumulators in their own
+        // (now idle) stage buffers, rank 0 pulls them over the cluster network in rank order and owns the epilogue.
+        constexpr int NT = CONSUMER_WARPS * 32;
+        __syncthreads();  // every DMMA warp of this CTA is done with the stage buffers
+        if (!producer && crank != 0) {
+#pragma unroll
+            for (int i = 0; i < MI; ++i)
+#pragma unroll
+                for (int j = 0; j < NJ; ++j) {
+                    tiles[((i * NJ + j) * 2 + 0) * NT + tid] = acc[i][j][0];
+                    tiles[((i * NJ + j) * 2 + 1) * NT + tid] = acc[i][j][1];
+                }
+        }
+        cluster_sync_all();
+        if (!producer && crank == 0) {
+            const uint32_t base = smem_u32(tiles);
+            for (uint32_t r = 1; r < (uint32_t)csize; ++r) {
+#pragma unroll
+                for (int i = 0; i < MI; ++i)
+#pragma unroll
+                    for (int j = 0; j < NJ; ++j) {
+                        acc[i][j][0] += ld_cluster_f64(base + (uint32_t)((((i * NJ + j) * 2 + 0) * NT + tid) * 8), r);
+                        acc[i][j][1] += ld_cluster_f64(base + (uint32_t)((((i * NJ + j) * 2 + 1) * NT + tid) * 8), r);
+                    }
+            }
+        }
+        cluster_sync_all();  // nobody's shared memory goes away before rank 0 has read it
+        if (crank != 0) return;
+    }
+    if (producer) return;
+
     // epilogue: thread owns rows i*8+g, column pairs j*8+2t; alpha/beta fused, beta == 0 never reads C
     const bool even_ld = (p.ldc & 1) == 0;
 #pragma unroll
     for (int i = 0; i < MI; ++i) {
-        const int64_t row = m0 + wm * 64 + i * 8 + g;
+        const int64_t row = m0 + wm * WTM + i * 8 + g;
         if (row >= p.m) continue;
 #pragma unroll
         for (int j = 0; j < NJ; ++j) {
-            const int64_t col = n0 + wn * 32 + j * 8 + 2 * t;
+            const int64_t col = n0 + wn * WTN + j * 8 + 2 * t;
             if (col >= p.n) continue;
             double *dst = p.c + row * p.ldc + col;
             double v0 = p.alpha * acc[i][j][0], v1 = p.alpha * acc[i][j][1];
@@ -229,7 +296,7 @@ EncodeTiledFn get_encode()
 }
 
 // rows x K operand with leading dimension ld; k_contig: element (r,k) at base[r*ld + k], else base[k*ld + r]
-bool make_map(CUtensorMap *map, const double *base, int64_t rows, int64_t k, int64_t ld, bool k_contig)
+bool make_map(CUtensorMap *map, const double *base, int64_t rows, int64_t k, int64_t ld, bool k_contig, int tile)
 {
     EncodeTiledFn enc = get_encode();
     if (!enc) return false;
@@ -237,10 +304,10 @@ bool make_map(CUtensorMap *map, const double *base, int64_t rows, int64_t k, int
     cuuint32_t box[3], estr[3] = {1, 1, 1};
     if (k_contig) {
         dims[0] = 4; dims[1] = (cuuint64_t)rows; dims[2] = (cuuint64_t)(k / 4);
-        box[0] = 4; box[1] = 128; box[2] = BK / 4;
+        box[0] = 4; box[1] = (cuuint32_t)tile; box[2] = BK / 4;
     } else {
         dims[0] = 4; dims[1] = (cuuint64_t)k; dims[2] = (cuuint64_t)(rows / 4);
-        box[0] = 4; box[1] = BK; box[2] = 128 / 4;
+        box[0] = 4; box[1] = BK; box[2] = (cuuint32_t)tile / 4;
     }
     strides[0] = (cuuint64_t)ld * sizeof(double);
     strides[1] = 4 * sizeof(double);
@@ -264,26 +331,68 @@ int gemm_f64_tma_launch(ndb_ctx *ctx, const double *a, int64_t lda, bool a_kc, c
     if (!a_kc && (m & 3)) return NDB_ERR_UNSUPPORTED;
     if (!b_kc && (n & 3)) return NDB_ERR_UNSUPPORTED;
     if ((lda & 1) || (ldb & 1) || ((uintptr_t)a & 15) || ((uintptr_t)b & 15)) return NDB_ERR_UNSUPPORTED;
+    // 128 x 128 tiles unless they would cover less than three quarters of the SMs
+    const int64_t big_tiles = ((m + 127) / 128) * ((n + 127) / 128);
+    int tile = big_tiles * 4 < (int64_t)ctx->sm_count * 3 ? 64 : 128;
+    if (getenv("NDB_GEMM_F64_TILE")) tile = atoi(getenv("NDB_GEMM_F64_TILE")) == 64 ? 64 : 128;
     CUtensorMap ma, mb;
-    if (!make_map(&ma, a, m, k, lda, a_kc) || !make_map(&mb, b, n, k, ldb, b_kc)) return NDB_ERR_UNSUPPORTED;
+    if (!make_map(&ma, a, m, k, lda, a_kc, tile) || !make_map(&mb, b, n, k, ldb, b_kc, tile)) return NDB_ERR_UNSUPPORTED;
     TmaArgs p;
     p.c = c; p.m = m; p.n = n; p.k = k; p.ldc = ldc;
     p.alpha = alpha; p.beta = beta;
-    p.tiles_m = (int)((m + BM - 1) / BM);
-    p.tiles_n = (int)((n + BN - 1) / BN);
-    const unsigned blocks = (unsigned)(p.tiles_m * p.tiles_n);
+    p.tiles_m = (int)((m + tile - 1) / tile);
+    p.tiles_n = (int)((n + tile - 1) / tile);
+    // small outputs: split K over a thread-block cluster (2/4/8 CTAs) until the grid covers ~2 CTAs per SM, keeping at
+    // least two k-tiles per CTA
+    const int64_t out_tiles = (int64_t)p.tiles_m * p.tiles_n;
+    const int64_t all_ktiles = (k + BK - 1) / BK;
+    int csize = 1;
+    if (tile == 64)
+        while (csize < 8 && out_tiles * csize * 2 <= (int64_t)ctx->sm_count * 2 && all_ktiles / (csize * 2) >= 2) csize *= 2;
+    if (getenv("NDB_GEMM_F64_SPLITK")) {
+        const int want = atoi(getenv("NDB_GEMM_F64_SPLITK"));
+        csize = (want == 2 || want == 4 || want == 8) && all_ktiles >= want ? want : 1;
+    }
+    p.csize = csize;
+    const unsigned blocks = (unsigned)(out_tiles * csize);
     static bool attr_done = false;
     if (!attr_done) {
-        NDB_CUDA(cudaFuncSetAttribute(gemm_f64_tma<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
-        NDB_CUDA(cudaFuncSetAttribute(gemm_f64_tma<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
-        NDB_CUDA(cudaFuncSetAttribute(gemm_f64_tma<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
-        NDB_CUDA(cudaFuncSetAttribute(gemm_f64_tma<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+#define NDB_F64_ATTR(A, B, T) \
+    NDB_CUDA(cudaFuncSetAttribute(gemm_f64_tma<A, B, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Shape<T>::SMEM_BYTES));
+        NDB_F64_ATTR(true, true, 128) NDB_F64_ATTR(true, false, 128) NDB_F64_ATTR(false, true, 128) NDB_F64_ATTR(false, false, 128)
+        NDB_F64_ATTR(true, true, 64) NDB_F64_ATTR(true, false, 64) NDB_F64_ATTR(false, true, 64) NDB_F64_ATTR(false, false, 64)
+#undef NDB_F64_ATTR
         attr_done = true;
     }
-    if (a_kc && b_kc) gemm_f64_tma<true, true><<<blocks, THREADS, SMEM_BYTES, ctx->stream>>>(ma, mb, p);
-    else if (a_kc) gemm_f64_tma<true, false><<<blocks, THREADS, SMEM_BYTES, ctx->stream>>>(ma, mb, p);
-    else if (b_kc) gemm_f64_tma<false, true><<<blocks, THREADS, SMEM_BYTES, ctx->stream>>>(ma, mb, p);
-    else gemm_f64_tma<false, false><<<blocks, THREADS, SMEM_BYTES, ctx->stream>>>(ma, mb, p);
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cudaLaunchAttribute attr[1];
+    cfg.gridDim = dim3(blocks, 1, 1);
+    cfg.stream = ctx->stream;
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)csize;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = csize > 1 ? 1 : 0;
+#define NDB_F64_LAUNCH(A, B, T)                          \
+    do {                                                 \
+        cfg.blockDim = dim3(Shape<T>::THREADS, 1, 1);    \
+        cfg.dynamicSmemBytes = Shape<T>::SMEM_BYTES;     \
+        NDB_CUDA(cudaLaunchKernelEx(&cfg, gemm_f64_tma<A, B, T>, ma, mb, p)); \
+    } while (0)
+    if (tile == 128) {
+        if (a_kc && b_kc) NDB_F64_LAUNCH(true, true, 128);
+        else if (a_kc) NDB_F64_LAUNCH(true, false, 128);
+        else if (b_kc) NDB_F64_LAUNCH(false, true, 128);
+        else NDB_F64_LAUNCH(false, false, 128);
+    } else {
+        if (a_kc && b_kc) NDB_F64_LAUNCH(true, true, 64);
+        else if (a_kc) NDB_F64_LAUNCH(true, false, 64);
+        else if (b_kc) NDB_F64_LAUNCH(false, true, 64);
+        else NDB_F64_LAUNCH(false, false, 64);
+    }
+#undef NDB_F64_LAUNCH
     NDB_CHECK_LAUNCH();
     return NDB_OK;
 }

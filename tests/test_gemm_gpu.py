@@ -268,6 +268,7 @@ def test_f64_tma_and_cpasync_kernels_agree_bitwise(nd, monkeypatch):
     """The TMA-fed and the cp.async-fed f64 kernels run the same DMMA sequence per output element, so they must agree to
     the bit on every layout combination, with tile overhang (m, n not multiples of 128) and a partial last k-tile."""
     rng = np.random.default_rng(11)
+    monkeypatch.setenv("NDB_GEMM_F64_SPLITK", "1")  # split-K regroups the k sum (covered to tolerance below)
     for (m, k, n) in [(256, 256, 256), (1000, 520, 776), (132, 36, 388)]:
         a = rng.standard_normal((m, k))
         b = rng.standard_normal((k, n))
@@ -290,3 +291,33 @@ def test_f64_tma_and_cpasync_kernels_agree_bitwise(nd, monkeypatch):
                     assert np.array_equal(outs[0], outs[1]), (m, k, n, af, bf, cf)
                     ref = -2.3 * (a @ b) + math.pi * c0
                     assert rel_norm(outs[0], ref) < 1e-12 * math.sqrt(k)
+
+
+def test_f64_small_outputs_split_k_over_clusters(nd, monkeypatch):
+    """Small outputs use 64x64 tiles and split K over a thread-block cluster (partials merged through distributed shared
+    memory in rank order): every cluster size gives the one-CTA result within rounding, and repeated runs are
+    bit-identical (fixed merge order)."""
+    rng = np.random.default_rng(12)
+    for (m, k, n) in [(256, 256, 256), (512, 512, 512), (192, 1024, 320), (100, 264, 60)]:
+        a = rng.standard_normal((m, k))
+        b = rng.standard_normal((k, n))
+        c0 = rng.standard_normal((m, n))
+        ref = -2.3 * (a @ b) + math.pi * c0
+        for bf in (False, True):
+            res = {}
+            for split in ("1", "2", "4", "8", None):
+                if split is None:
+                    monkeypatch.delenv("NDB_GEMM_F64_SPLITK", raising=False)
+                else:
+                    monkeypatch.setenv("NDB_GEMM_F64_SPLITK", split)
+                runs = []
+                for _ in range(2):
+                    da = nd.Array.from_numpy(a)
+                    db = nd.Array.from_numpy(np.asfortranarray(b) if bf else b)
+                    dc = nd.Array.from_numpy(c0)
+                    nd.general_mat_mul(-2.3, da, db, math.pi, dc)
+                    runs.append(dc.to_numpy())
+                assert np.array_equal(runs[0], runs[1]), (m, k, n, split)
+                res[split] = runs[0]
+                assert rel_norm(runs[0], ref) < 1e-12 * math.sqrt(k), (m, k, n, split)
+            monkeypatch.delenv("NDB_GEMM_F64_SPLITK", raising=False)
