@@ -307,6 +307,47 @@ gemm_tf32x3(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
 }
 
 // ---- host side ------------------------------------------------------------------------------------
+// Small problems are launch-bound: four Zip launches to pack A_hi/A_lo/B_hi/B_lo cost more than the GEMM itself
+// (256^3: 33 us in all, cuBLAS 13 us).  For operands of at most PACK_SMALL_ELEMS elements one launch packs both operands
+// and both halves from any signed strides (blockIdx.y selects the operand; reads follow the operand's unit-stride axis
+// when it has one, writes are k-major).  Same split as NDB_OP_TF32_HI/_LO in zip_kernels.cuh.
+constexpr int64_t PACK_SMALL_ELEMS = 1 << 18;  // 512 x 512: above that the Zip engine's vector kernels win (1024^3: 49.6 vs 53.6 us)
+
+struct PackSmallArgs {
+    const float *src[2];
+    int64_t rows[2], rs[2], cs[2];  // element (r, k) of operand o at src[o][r * rs[o] + k * cs[o]]
+    float *hi[2], *lo[2];
+    int64_t k, kp;
+};
+
+__global__ void __launch_bounds__(256) pack_tf32_small(PackSmallArgs a)
+{
+    const int o = blockIdx.y;
+    const int64_t rows = a.rows[o], total = rows * a.kp;
+    // walk the source along its denser axis so that neighbouring threads read neighbouring addresses
+    const bool k_fast = llabs(a.cs[o]) <= llabs(a.rs[o]);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        int64_t r, k;
+        if (k_fast) {
+            r = i / a.kp;
+            k = i - r * a.kp;
+        } else {
+            k = i / rows;
+            r = i - k * rows;
+        }
+        float h = 0.f, l = 0.f;
+        if (k < a.k) {
+            const float x = a.src[o][r * a.rs[o] + k * a.cs[o]];
+            uint32_t hb;
+            asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(x));
+            h = __uint_as_float(hb);
+            l = (fabsf(x) <= 3.4028234664e38f) ? x - h : 0.f;
+        }
+        a.hi[o][r * a.kp + k] = h;
+        a.lo[o][r * a.kp + k] = l;
+    }
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
                                   const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -418,7 +459,16 @@ int gemm_f32_launch(ndb_ctx *ctx, const GemmArgs &g0, float alpha, float beta)
     NDB_CUDA(cudaMallocAsync((void **)&ws, (2 * a_elems + 2 * b_elems) * sizeof(float), ctx->stream));
     float *a_hi = ws, *a_lo = ws + a_elems, *b_hi = ws + 2 * a_elems, *b_lo = ws + 2 * a_elems + b_elems;
     int st = NDB_OK;
-    {
+    if ((int64_t)a_elems <= PACK_SMALL_ELEMS && (int64_t)b_elems <= PACK_SMALL_ELEMS && !getenv("NDB_GEMM_F32_ZIP_PACK")) {
+        PackSmallArgs pa;
+        pa.src[0] = (const float *)g.a; pa.rows[0] = g.m; pa.rs[0] = g.rsa; pa.cs[0] = g.csa; pa.hi[0] = a_hi; pa.lo[0] = a_lo;
+        pa.src[1] = (const float *)g.b; pa.rows[1] = g.n; pa.rs[1] = g.csb; pa.cs[1] = g.rsb; pa.hi[1] = b_hi; pa.lo[1] = b_lo;
+        pa.k = g.k; pa.kp = kp;
+        const int64_t most = (int64_t)std::max(a_elems, b_elems);
+        const unsigned bx = (unsigned)std::min<int64_t>((most + 255) / 256, (int64_t)ctx->sm_count * 8);
+        pack_tf32_small<<<dim3(bx, 2, 1), 256, 0, ctx->stream>>>(pa);
+        NDB_CHECK_LAUNCH();
+    } else {
         // pack + split through the Zip engine: out[M][Kp] <- op(A),  out[N][Kp] <- op(B^T)
         const ndb_view va = view2(g.a, g.m, g.k, g.rsa, g.csa);
         const ndb_view vbt = view2(g.b, g.n, g.k, g.csb, g.rsb);
