@@ -44,7 +44,7 @@ def main():
     assert np.max(np.abs(par.var_axis0(sf, 1.0, dist).to_numpy() - f.var(axis=0, ddof=1))) <= tol * 8
     assert np.max(np.abs(par.var_axis0(sf, 0.0, dist, want_std=True).to_numpy() - f.std(axis=0))) <= tol * 8
     # the same reductions with the exchange done through peer memory (CUDA IPC windows over NVLink), no NCCL call
-    peers = par.PeerGroup(ctx, dist, slot_bytes=1 << 16)
+    peers = par.PeerGroup(ctx, dist, slot_bytes=1 << 20)
     for rep in range(3):  # repeated: the two slot sets and the arrival counter must keep working
         with np.errstate(over="ignore"):
             assert par.global_sum(sa, dist, peers) == a.sum(dtype=np.int64)
@@ -53,6 +53,25 @@ def main():
         assert np.max(np.abs(par.sum_axis0(sf, dist, peers).to_numpy() - f.sum(axis=0))) <= tol * 8
         assert np.max(np.abs(par.mean_axis0(sf, n0, dist, peers).to_numpy() - f.mean(axis=0))) <= tol
         assert np.max(np.abs(par.var_axis0(sf, 1.0, dist, peers=peers).to_numpy() - f.var(axis=0, ddof=1))) <= tol * 8
+        assert np.max(np.abs(par.var_axis0(sf, 1.0, dist, peers=peers, n_global=n0).to_numpy() - f.var(axis=0, ddof=1))) <= tol * 8
+        assert np.max(np.abs(par.var_axis0(sf, 0.0, dist, True, peers, n0).to_numpy() - f.std(axis=0))) <= tol * 8
+    # the fused one-launch path must actually be taken for these shapes (300 columns is not a multiple of the vector
+    # width times 32?  the library decides; a wide slab certainly qualifies) and agree with numpy
+    wide = rng.standard_normal((n0, 4096))
+    wl = par.shard_axis0(Array.from_numpy(wide, ctx), rank, world)
+    fused = par._fused_axis0(wl, Red.SUM, 0.0, wl.shape[0], peers)
+    assert fused is not None, "the fused sharded sum_axis path was refused for a [n, 4096] f64 slab"
+    assert np.max(np.abs(fused.to_numpy() - wide.sum(axis=0))) <= tol * 8
+    fv = par._fused_axis0(wl, Red.VAR, 1.0, n0, peers)
+    assert fv is not None, "fused var refused"
+    err = np.max(np.abs(fv.to_numpy() - wide.var(axis=0, ddof=1)))
+    assert err <= tol * 8, ("fused var", err, fv.to_numpy()[:4], wide.var(axis=0, ddof=1)[:4])
+    fm = par._fused_axis0(wl, Red.MEAN, 0.0, n0, peers)
+    assert fm is not None and np.max(np.abs(fm.to_numpy() - wide.mean(axis=0))) <= tol
+    wi = rng.integers(-2 ** 62, 2 ** 62, size=(n0, 2048), dtype=np.int64)
+    with np.errstate(over="ignore"):
+        fi = par._fused_axis0(par.shard_axis0(Array.from_numpy(wi, ctx), rank, world), Red.SUM, 0.0, n0, peers)
+        assert fi is not None and np.array_equal(fi.to_numpy(), wi.sum(axis=0, dtype=np.int64))
     # peer exchange and NCCL agree to the bit for integers and (same rank order) for this float case too
     g_peer = par.sum_axis0(sa, dist, peers).to_numpy()
     g_nccl = par.sum_axis0(sa, dist).to_numpy()

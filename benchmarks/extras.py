@@ -187,7 +187,7 @@ def run_extras(nd, ctx, torch, dist, rank, world, local, peak_gbs):
             import ctypes as C
             from ndarray_b200 import parallel as par
             from ndarray_b200.array import Red
-            peers = par.PeerGroup(ctx, dist, slot_bytes=1 << 18)
+            peers = par.PeerGroup(ctx, dist, slot_bytes=1 << 20)
             L = nd.lib()
 
             def c5_peer():
@@ -214,7 +214,16 @@ def run_extras(nd, ctx, torch, dist, rank, world, local, peak_gbs):
             # C3 sharded: sum_axis(Axis(0)) of a [2048, 16384] f64 slab per rank + exchange of the 128 KiB vector
             slab_t = torch.randn(2048, 16384, device=dev, dtype=torch.float64)
             slab = tarr(slab_t)
-            for label, fn in (("nccl", lambda: par.sum_axis0(slab, dist)), ("peer", lambda: par.sum_axis0(slab, dist, peers))):
+            def two_launch():
+                part = slab.sum_axis(0)
+                return peers.allreduce_(part)
+
+            n_glob = 2048 * world
+            assert par._fused_axis0(slab, Red.SUM, 0.0, n_glob, peers) is not None
+            for label, fn in (("nccl", lambda: par.sum_axis0(slab, dist)), ("peer", two_launch),
+                              ("peer_fused_one_launch", lambda: par._fused_axis0(slab, Red.SUM, 0.0, n_glob, peers)),
+                              ("var_nccl", lambda: par.var_axis0(slab, 1.0, dist)),
+                              ("var_peer_fused_one_launch", lambda: par._fused_axis0(slab, Red.VAR, 1.0, n_glob, peers))):
                 med_s, _ = _time(ctx, fn, 20, 3)
                 ts = torch.tensor([med_s], device=dev, dtype=torch.float64)
                 dist.all_reduce(ts, op=dist.ReduceOp.MAX)

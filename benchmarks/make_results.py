@@ -54,8 +54,15 @@ def main():
                 out.append(f"| {name} | {ex[k]['nccl_us']} µs | **{ex[k]['peer_memory_us']} µs** |")
         if "C3_sum_axis0_sharded_f64_nccl" in ex:
             a, b = ex["C3_sum_axis0_sharded_f64_nccl"], ex["C3_sum_axis0_sharded_f64_peer"]
+            f = ex.get("C3_sum_axis0_sharded_f64_peer_fused_one_launch")
             out.append(f"| sharded `sum_axis(Axis(0))`, 2048x16384 f64 per rank + exchange | {a['GB/s_aggregate']:.0f} GB/s aggregate ({a['ms'] * 1e3:.0f} µs) | "
-                       f"**{b['GB/s_aggregate']:.0f} GB/s aggregate** ({b['ms'] * 1e3:.0f} µs) |")
+                       f"**{b['GB/s_aggregate']:.0f} GB/s aggregate** ({b['ms'] * 1e3:.0f} µs) with reduce + exchange kernel"
+                       + (f"; {f['GB/s_aggregate']:.0f} GB/s ({f['ms'] * 1e3:.0f} µs) as ONE fused launch (`ndb_reduce_axis_peer`)" if f else "") + " |")
+        if "C3_sum_axis0_sharded_f64_var_nccl" in ex:
+            a, b = ex["C3_sum_axis0_sharded_f64_var_nccl"], ex["C3_sum_axis0_sharded_f64_var_peer_fused_one_launch"]
+            out.append(f"| sharded `var_axis(Axis(0), 1.0)`, same slab: Welford states of all ranks merged in rank order | {a['GB/s_aggregate']:.0f} GB/s aggregate "
+                       f"({a['ms'] * 1e3:.0f} µs: local kernel, three all-gathers, merge kernel) | **{b['GB/s_aggregate']:.0f} GB/s aggregate** "
+                       f"({b['ms'] * 1e3:.0f} µs, ONE launch per rank) |")
         out += ["", "Row-sharded `general_mat_mul` (A and C sharded along Axis(0), 8192 rows per rank; B broadcast from rank 0 with "
                     "`ncclBroadcast` INSIDE every timed step):", "", "| case | aggregate | per step |", "|---|---|---|"]
         for k, v in ex.items():

@@ -287,6 +287,13 @@ int ndb_peer_window_destroy(ndb_ctx *ctx);
 int ndb_peer_allreduce(ndb_ctx *ctx, int redop, int dtype, const void *local_dev, void *out_dev, int64_t n);
 /* out[r*n + i] = rank r's local[i]. */
 int ndb_peer_allgather(ndb_ctx *ctx, int dtype, const void *local_dev, void *out_dev, int64_t n);
+/* ndb_reduce_axis over ALL shards when `axis` is the sharded axis and a kept axis is the dense one (sum_axis(Axis(0)) of a
+ * C-order slab): ONE launch per rank - the block that completes a column tile locally exchanges its states (sums, or
+ * Welford (n, mean, M2) for var/std) with the other ranks through the windows, merges them in rank order and finalizes
+ * with the GLOBAL axis length n_global (mean divides by it, ddof is checked against it).  Returns NDB_ERR_UNSUPPORTED,
+ * without launching anything, when the layout, the tile count (> 2 per SM) or the slot size rule this path out; the rules
+ * depend on shapes only, so all ranks decide alike and the caller falls back to ndb_reduce_axis + ndb_peer_allreduce. */
+int ndb_reduce_axis_peer(ndb_ctx *ctx, int redop, int axis, const ndb_view *in, const ndb_view *out, double ddof, int64_t n_global);
 /* ndb_reduce_all_dev over ALL shards: the kernel that finishes this rank's reduction tree also performs the exchange. */
 int ndb_reduce_all_peer(ndb_ctx *ctx, int redop, const ndb_view *in, void *out_dev);
 

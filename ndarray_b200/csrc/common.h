@@ -83,6 +83,7 @@ struct ndb_ctx {
     void *peer_win[16] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     unsigned long long peer_expected = 0;  // arrivals my counter will have seen once every exchange issued so far is complete
     unsigned long long peer_calls = 0;
+    unsigned long long *peer_tile_epoch = nullptr;  // device: exchanges completed per tile counter (reduce.cu's fused axis reductions)
     unsigned *tickets = nullptr;    // NDB_TICKETS zeroed counters: 'last block finishes' hand-over in split reductions (self-resetting)
     // staging buffers for the host-pointer (end-to-end / cblas) entry points
     void *stage[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};

@@ -143,6 +143,8 @@ extern "C" int ndb_peer_window_create(ndb_ctx *ctx, int rank, int world, size_t 
     NDB_CUDA(cudaIpcGetMemHandle(&h, base));
     static_assert(sizeof(h) == 64, "ndb200.h promises 64-byte handles");
     memcpy(handle_out, &h, sizeof(h));
+    NDB_CUDA(cudaMalloc((void **)&ctx->peer_tile_epoch, PEER_MAX_TILES * sizeof(unsigned long long)));
+    NDB_CUDA(cudaMemset(ctx->peer_tile_epoch, 0, PEER_MAX_TILES * sizeof(unsigned long long)));
     ctx->peer_rank = rank;
     ctx->peer_world = world;
     ctx->peer_slot_bytes = slot_bytes;
@@ -185,6 +187,8 @@ extern "C" int ndb_peer_window_destroy(ndb_ctx *ctx)
         else cudaIpcCloseMemHandle(ctx->peer_win[r]);
         ctx->peer_win[r] = nullptr;
     }
+    if (ctx->peer_tile_epoch) cudaFree(ctx->peer_tile_epoch);
+    ctx->peer_tile_epoch = nullptr;
     ctx->peer_world = 0;
     ctx->peer_rank = -1;
     ctx->peer_attached = false;

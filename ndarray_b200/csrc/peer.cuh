@@ -13,7 +13,8 @@
 namespace ndb {
 
 constexpr int NDB_MAX_PEERS = 16;
-constexpr size_t PEER_HEADER = 256;  // bytes in front of the slots (the counter lives at offset 0)
+constexpr int PEER_MAX_TILES = 1000;  // per-tile arrival counters for reductions that exchange tile by tile (reduce.cu)
+constexpr size_t PEER_HEADER = 8192;  // bytes in front of the slots: counter 0 = whole-exchange arrivals, 1 + t = tile t
 
 struct PeerArgs {
     char *win[NDB_MAX_PEERS];      // window base of every rank, as mapped in THIS process
@@ -35,6 +36,24 @@ __device__ __forceinline__ void peer_arrive(const PeerArgs &p)
     __syncthreads();
     if ((int)threadIdx.x < p.world)
         atomicAdd_system(reinterpret_cast<unsigned long long *>(p.win[threadIdx.x]), 1ull);
+}
+
+// one thread spins until counter `index` of MY window reaches `target`
+__device__ __forceinline__ void peer_spin(const PeerArgs &p, int index, unsigned long long target)
+{
+    const unsigned long long *ctr = reinterpret_cast<const unsigned long long *>(p.win[p.rank]) + index;
+    unsigned long long seen, t0, now;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    for (;;) {
+        asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(ctr) : "memory");
+        if (seen >= target) break;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+        if (now - t0 > 20000000000ull) {  // 20 s: a peer never arrived; fail loudly instead of hanging the GPU
+            printf("ndb peer exchange: rank %d timed out at %llu of %llu arrivals (counter %d)\n", p.rank, seen, target, index);
+            __trap();
+        }
+        __nanosleep(200);
+    }
 }
 
 // called by all threads of a block; returns once every rank's contribution is visible in MY window

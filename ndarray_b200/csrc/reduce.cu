@@ -249,6 +249,9 @@ struct RedArgs {
     int splits;     // red_cols: blocks along the reduced axis
     void *partial;  // [splits][n_out] states
     unsigned *tickets;  // red_cols: one zeroed counter per column tile; non-null = the last split to finish merges (one launch)
+    int peer_on;                      // red_cols<PEER>: exchange every tile's state with the other ranks before finalizing
+    unsigned long long *tile_epoch;   // exchanges completed so far per tile counter (device, this rank)
+    PeerArgs peer;
 };
 
 __device__ __forceinline__ void kept_offsets(const Kept &k, int64_t lin, int64_t &in_off, int64_t &out_off,
@@ -375,7 +378,7 @@ __device__ __forceinline__ A merge_splits(const A *p, int splits, int64_t pitch)
 // ---- cols: a kept axis is unit-stride ------------------------------------------------------------
 // blockDim = (32, 8).  A block owns 32*W consecutive outputs along the last kept axis (in_stride 1) and
 // rows [split*chunk, ...) of the reduced axis; thread (tx, ty) strides rows ty, ty+8, ...
-template <typename T, int R, int FIN, int W>
+template <typename T, int R, int FIN, int W, bool PEER = false>
 __global__ void __launch_bounds__(256, R == R_WELFORD ? NDB_RED_COLS_MINB_W : 3) red_cols(RedArgs a)  // 3 CTAs/SM register budget (<= 85): f64 sum 6.52 -> 6.95 TB/s vs the default allocation
 {
     using V = Vec128<T>;
@@ -448,19 +451,23 @@ __global__ void __launch_bounds__(256, R == R_WELFORD ? NDB_RED_COLS_MINB_W : 3)
         __syncthreads();
         // 32*W columns, merged over ty in fixed order by the first 32*W threads
         const int t = ty * 32 + tx;
+        Acc<T, R> r;
+        r.reset();
+        const int64_t c = tile * (32 * W) + t;
+        const bool mine = t < 32 * W && c < ncol;
         if (t < 32 * W) {
-            Acc<T, R> r = smem[0][t];
+            r = smem[0][t];
 #pragma unroll
             for (int j = 1; j < 8; ++j) r.merge(smem[j][t]);
-            const int64_t c = tile * (32 * W) + t;
             if (c < ncol) {
                 if (a.splits == 1) {
-                    store_result<T, R, FIN>(a, r, out_off + c * a.k.out_stride[last], out2_off + c * a.k.out2_stride[last]);
+                    if constexpr (!PEER) store_result<T, R, FIN>(a, r, out_off + c * a.k.out_stride[last], out2_off + c * a.k.out2_stride[last]);
                 } else {
                     reinterpret_cast<Acc<T, R> *>(a.partial)[(int64_t)split * a.n_out + o * ncol + c] = r;
                 }
             }
         }
+        bool finisher = PEER && a.splits == 1;  // does this block hold the tile's complete local state in `r`?
         if (a.splits > 1 && a.tickets != nullptr) {
             // One launch instead of two: the block that takes the last ticket of this column tile merges all splits'
             // partial states IN SPLIT ORDER (so the result does not depend on which block came last) and stores.
@@ -471,13 +478,39 @@ __global__ void __launch_bounds__(256, R == R_WELFORD ? NDB_RED_COLS_MINB_W : 3)
             __syncthreads();
             if (ticket == (unsigned)a.splits - 1) {
                 __threadfence();
-                const int64_t c = tile * (32 * W) + t;
-                if (t < 32 * W && c < ncol) {
+                if (mine) {
                     const Acc<T, R> *p = reinterpret_cast<const Acc<T, R> *>(a.partial) + o * ncol + c;
-                    Acc<T, R> r = merge_splits(p, a.splits, a.n_out);
-                    store_result<T, R, FIN>(a, r, out_off + c * a.k.out_stride[last], out2_off + c * a.k.out2_stride[last]);
+                    r = merge_splits(p, a.splits, a.n_out);
+                    if constexpr (!PEER) store_result<T, R, FIN>(a, r, out_off + c * a.k.out_stride[last], out2_off + c * a.k.out2_stride[last]);
                 }
                 if (t == 0) a.tickets[vb] = 0;  // ready for the next launch
+                finisher = PEER;
+            }
+        }
+        if constexpr (PEER) {
+            // Sharded reduction, still one launch: the block that completed this tile locally stores its states into
+            // slot[rank] of EVERY rank's window (NVLink), bumps every rank's counter for this tile, waits until all
+            // ranks' states for the tile have landed here and merges them in rank order before finalizing.
+            if (finisher) {  // block-uniform
+                const int64_t col = o * ncol + c;
+                if (mine)
+                    for (int q = 0; q < a.peer.world; ++q) reinterpret_cast<Acc<T, R> *>(peer_slot(a.peer, q, a.peer.rank))[col] = r;
+                __threadfence_system();
+                __syncthreads();
+                if (t < a.peer.world)
+                    atomicAdd_system(reinterpret_cast<unsigned long long *>(a.peer.win[t]) + 1 + vb, 1ull);
+                if (t == 0) {
+                    const unsigned long long done = a.tile_epoch[vb];
+                    peer_spin(a.peer, 1 + (int)vb, (done + 1) * (unsigned long long)a.peer.world);
+                    a.tile_epoch[vb] = done + 1;
+                }
+                __syncthreads();
+                if (mine) {
+                    Acc<T, R> tot = ldcg_state(reinterpret_cast<const Acc<T, R> *>(peer_slot(a.peer, a.peer.rank, 0)) + col);
+                    for (int q = 1; q < a.peer.world; ++q)
+                        tot.merge(ldcg_state(reinterpret_cast<const Acc<T, R> *>(peer_slot(a.peer, a.peer.rank, q)) + col));
+                    store_result<T, R, FIN>(a, tot, out_off + c * a.k.out_stride[last], out2_off + c * a.k.out2_stride[last]);
+                }
             }
         }
         __syncthreads();
@@ -976,6 +1009,7 @@ static int reduce_axis_launch(ndb_ctx *ctx, RedArgs &a, const ZipPlan &z)
         if (a.k.dim[d] > 1) min_kept = std::min<int64_t>(min_kept, llabs(a.k.in_stride[d]));
     const int64_t as = llabs(a.s);
     const bool lanes = a.n_out == 1 || a.n == 1 || as <= min_kept;
+    if (a.peer_on && (lanes || !(a.k.in_stride[last] == 1 && a.k.dim[last] >= 32))) return NDB_ERR_UNSUPPORTED;
     if (lanes) {
         bool vec = a.s == 1 && a.n % vecn == 0 && ((uintptr_t)a.in % 16) == 0 && a.n >= 4 * vecn;
         for (int d = 0; d < a.k.n && vec; ++d) vec = a.k.dim[d] == 1 || a.k.in_stride[d] % vecn == 0;
@@ -1023,6 +1057,23 @@ static int reduce_axis_launch(ndb_ctx *ctx, RedArgs &a, const ZipPlan &z)
             if (total <= NDB_TICKETS && !getenv("NDB_RED_TWO_KERNELS")) a.tickets = ctx->tickets;
         }
         dim3 grid((unsigned)std::min<int64_t>(total, (int64_t)1 << 30), (unsigned)splits, 1), block(32, 8, 1);
+        if (a.peer_on) {
+            // fused exchange (see red_cols<PEER>): every tile's finishing block waits for the other ranks, so all of
+            // them must be resident together with the blocks still working -> at most two tiles per SM; the rules
+            // below depend on the shapes only, so every rank takes the same decision
+            if constexpr (FIN == FIN_WELFORD_RAW) {
+                return NDB_ERR_UNSUPPORTED;
+            } else {
+                if (!vec || total > std::min<int64_t>(PEER_MAX_TILES, (int64_t)ctx->sm_count * 2) || (splits > 1 && a.tickets == nullptr) ||
+                    (size_t)a.n_out * sizeof(Acc<T, R>) > ctx->peer_slot_bytes || !ctx->peer_tile_epoch)
+                    return NDB_ERR_UNSUPPORTED;
+                NDB_TRY(peer_begin(ctx, 0, (size_t)a.n_out * sizeof(Acc<T, R>), &a.peer));
+                a.tile_epoch = ctx->peer_tile_epoch;
+                red_cols<T, R, FIN, Vec128<T>::N, true><<<grid, block, 0, st>>>(a);
+                NDB_CHECK_LAUNCH();
+                return NDB_OK;
+            }
+        }
         if (vec) red_cols<T, R, FIN, Vec128<T>::N><<<grid, block, 0, st>>>(a);
         else red_cols<T, R, FIN, 1><<<grid, block, 0, st>>>(a);
         NDB_CHECK_LAUNCH();
@@ -1077,7 +1128,7 @@ static int fill_view(ndb_ctx *ctx, const ndb_view *out, double value)
 }
 
 static int reduce_axis_impl(ndb_ctx *ctx, int redop, int axis, const ndb_view *in, const ndb_view *out,
-                            const ndb_view *out2, double ddof)
+                            const ndb_view *out2, double ddof, bool peer = false, int64_t n_global = 0)
 {
     if (!ctx) {
         set_error("reduce_axis: null context (no CPU fallback exists)");
@@ -1101,16 +1152,18 @@ static int reduce_axis_impl(ndb_ctx *ctx, int redop, int axis, const ndb_view *i
     }
     base.ndim = in->ndim - 1;
     const int64_t n = in->dim[axis];
+    if (peer && (n == 0 || n_global < n)) return NDB_ERR_UNSUPPORTED;  // an empty shard cannot take the fused path
+    const int64_t n_stat = peer ? n_global : n;  // the length mean / var / std divide by: the whole axis, all shards
     const bool welford = redop == NDB_RED_VAR || redop == NDB_RED_STD || redop == -1;
     if (welford && !dtype_is_float(in->dtype)) {
         set_error("var_axis/std_axis need a float element type");
         return NDB_ERR_UNSUPPORTED;
     }
-    double nT = (double)n, dof = 0.0;
+    double nT = (double)n_stat, dof = 0.0;
     if (redop == NDB_RED_VAR || redop == NDB_RED_STD) {
         // assert!(!(ddof < zero || ddof > n)) in the element type; NaN passes (impl_numeric.rs:408-413)
         if (in->dtype == NDB_F32) {
-            const float d = (float)ddof, nf = (float)n;
+            const float d = (float)ddof, nf = (float)n_stat;
             if (d < 0.f || d > nf) {
                 set_error("`ddof` must not be less than zero or greater than the length of the axis");
                 return NDB_ERR_INVALID_ARG;
@@ -1118,11 +1171,11 @@ static int reduce_axis_impl(ndb_ctx *ctx, int redop, int axis, const ndb_view *i
             dof = (double)(nf - d);
             nT = (double)nf;
         } else {
-            if (ddof < 0.0 || ddof > (double)n) {
+            if (ddof < 0.0 || ddof > (double)n_stat) {
                 set_error("`ddof` must not be less than zero or greater than the length of the axis");
                 return NDB_ERR_INVALID_ARG;
             }
-            dof = (double)n - ddof;
+            dof = (double)n_stat - ddof;
         }
     }
     // the plan validates out/base shapes, drops unit axes, flips and merges jointly
@@ -1163,6 +1216,7 @@ static int reduce_axis_impl(ndb_ctx *ctx, int redop, int axis, const ndb_view *i
     a.nT = nT;
     a.dof = dof;
     a.splits = 1;
+    a.peer_on = peer ? 1 : 0;
     // a backwards reduced axis is walked forwards from its low end (legal: commutative up to tolerance)
     if (a.s < 0) {
         a.in += (n - 1) * a.s * (int64_t)dtype_size(in->dtype);
@@ -1287,6 +1341,20 @@ int ndb_reduce_axis(ndb_ctx *ctx, int redop, int axis, const ndb_view *in, const
         return NDB_ERR_UNSUPPORTED;
     }
     return reduce_axis_impl(ctx, redop, axis, in, out, nullptr, ddof);
+}
+
+int ndb_reduce_axis_peer(ndb_ctx *ctx, int redop, int axis, const ndb_view *in, const ndb_view *out, double ddof, int64_t n_global)
+{
+    clear_error();
+    if (redop < 0 || redop >= NDB_RED__COUNT) {
+        set_error("reduce_axis_peer: unknown redop %d", redop);
+        return NDB_ERR_UNSUPPORTED;
+    }
+    if (!ctx || ctx->peer_world <= 0 || !ctx->peer_attached) {
+        set_error("reduce_axis_peer: no peer window attached to this context");
+        return NDB_ERR_INVALID_ARG;
+    }
+    return reduce_axis_impl(ctx, redop, axis, in, out, nullptr, ddof, true, n_global);
 }
 
 int ndb_welford_axis(ndb_ctx *ctx, int axis, const ndb_view *in, const ndb_view *mean_out, const ndb_view *m2_out)

@@ -91,6 +91,19 @@ class PeerGroup:
         check(lib().ndb_peer_window_destroy(self.ctx.handle))
 
 
+def _fused_axis0(local: Array, redop: int, ddof: float, n_global: int, peers: "PeerGroup"):
+    """ndb_reduce_axis_peer along Axis(0): the whole sharded reduction (local column reduction, exchange of the per-tile
+    states through peer memory, rank-ordered merge, finalisation with the global length) in ONE launch.  Returns None
+    when the library rules the layout out (shape-derived, so every rank gets the same answer)."""
+    from . import _ffi
+    out = Array.uninit(local.shape[1:], local.dtype, ctx=local.ctx)
+    st = lib().ndb_reduce_axis_peer(local.ctx.handle, redop, 0, C.byref(local.v), C.byref(out.v), float(ddof), int(n_global))
+    if st == _ffi.ERR_UNSUPPORTED:
+        return None
+    check(st)
+    return out
+
+
 def _multi(dist) -> bool:
     return dist is not None and dist.is_initialized() and dist.get_world_size() > 1
 
@@ -113,6 +126,10 @@ def global_sum(local: Array, dist=None, peers: PeerGroup | None = None):
 def sum_axis0(local: Array, dist=None, peers: PeerGroup | None = None) -> Array:
     """sum_axis(Axis(0)) when axis 0 is the sharded axis: local partial vector, then all-reduce(sum) — one peer-memory
     exchange kernel with a PeerGroup, NCCL otherwise."""
+    if peers is not None and peers.world > 1 and local.shape[0] > 0:
+        fused = _fused_axis0(local, Red.SUM, 0.0, local.shape[0], peers)
+        if fused is not None:
+            return fused
     part = local.sum_axis(0)
     if peers is not None and peers.world > 1 and part.len() * part.dtype.itemsize <= peers.slot_bytes:
         return peers.allreduce_(part)
@@ -124,15 +141,25 @@ def sum_axis0(local: Array, dist=None, peers: PeerGroup | None = None) -> Array:
 
 def mean_axis0(local: Array, n_global: int, dist=None, peers: PeerGroup | None = None) -> Array:
     """mean_axis(Axis(0)): divide by the GLOBAL length after the all-reduce (impl_numeric.rs:342-355)."""
+    if peers is not None and peers.world > 1 and n_global >= peers.world and local.dtype.kind == "f":
+        fused = _fused_axis0(local, Red.MEAN, 0.0, n_global, peers)
+        if fused is not None:
+            return fused
     s = sum_axis0(local, dist, peers)
     s /= local.dtype.type(n_global)
     return s
 
 
-def var_axis0(local: Array, ddof: float, dist=None, want_std: bool = False, peers: PeerGroup | None = None) -> Array:
-    """var_axis(Axis(0), ddof): per-shard Welford state (n, mean, M2), all-gather, Chan merge in rank order."""
+def var_axis0(local: Array, ddof: float, dist=None, want_std: bool = False, peers: PeerGroup | None = None,
+              n_global: int | None = None) -> Array:
+    """var_axis(Axis(0), ddof): per-shard Welford state (n, mean, M2), all-gather, Chan merge in rank order.  With a
+    PeerGroup and the global axis length the whole thing is one launch (ndb_reduce_axis_peer)."""
     import torch
     shape = local.shape[1:]
+    if peers is not None and peers.world > 1 and n_global is not None and n_global >= peers.world:
+        fused = _fused_axis0(local, Red.STD if want_std else Red.VAR, ddof, n_global, peers)
+        if fused is not None:
+            return fused
     if peers is not None and peers.world > 1 and max(int(np.prod(shape)), 1) * local.dtype.itemsize <= peers.slot_bytes:
         mean, m2 = Array.uninit(shape, local.dtype, ctx=local.ctx), Array.uninit(shape, local.dtype, ctx=local.ctx)
         check(lib().ndb_welford_axis(local.ctx.handle, 0, C.byref(local.v), C.byref(mean.v), C.byref(m2.v)))
