@@ -449,6 +449,28 @@ struct TileShape {
 template <int NP>
 __device__ __forceinline__ void tile_coords(const TileArgs<NP> &a, int64_t vb, int64_t &tx, int64_t &ty, int64_t (&off)[NP])
 {
+#pragma unroll
+    for (int p = 0; p < NP; ++p) off[p] = 0;
+    if (a.total_tiles <= 0x7fffffff) {
+        // the usual case: 32-bit divisions (a 64-bit division is ~10x the instructions, and this runs once per tile)
+        uint32_t t = (uint32_t)vb;
+        const uint32_t f = (uint32_t)(a.y_fastest ? a.tiles_y : a.tiles_x), sl = (uint32_t)(a.y_fastest ? a.tiles_x : a.tiles_y);
+        const uint32_t fast = t % f;
+        t /= f;
+        const uint32_t slow = t % sl;
+        t /= sl;
+        tx = a.y_fastest ? slow : fast;
+        ty = a.y_fastest ? fast : slow;
+        for (int k = a.n_outer - 1; k >= 0; --k) {
+            const uint32_t d = (uint32_t)a.odim[k];
+            const uint32_t q = t / d;
+            const uint32_t idx = t - q * d;
+            t = q;
+#pragma unroll
+            for (int p = 0; p < NP; ++p) off[p] += (int64_t)idx * a.ostride[p][k];
+        }
+        return;
+    }
     int64_t t = vb;
     if (a.y_fastest) {
         ty = t % a.tiles_y;
@@ -461,8 +483,6 @@ __device__ __forceinline__ void tile_coords(const TileArgs<NP> &a, int64_t vb, i
         ty = t % a.tiles_y;
         t /= a.tiles_y;
     }
-#pragma unroll
-    for (int p = 0; p < NP; ++p) off[p] = 0;
     for (int k = a.n_outer - 1; k >= 0; --k) {
         const int64_t q = t / a.odim[k];
         const int64_t idx = t - q * a.odim[k];
