@@ -553,8 +553,10 @@ __global__ void __launch_bounds__(256) zip_tile(TileArgs<NIN + 1> a, T s0, T s1,
 // global loads (PASSES vectors per producer), then the staged ones go through shared memory.
 // STEP2: a staged producer may also step by +-2 along its dense axis (x.t().slice(s![..;-2, ..])): two vectors are
 // loaded and every other lane kept.
-template <typename T, int OP, int NIN, bool STEP2>
-__global__ void __launch_bounds__(256, STEP2 ? 2 : (NIN <= 1 ? 6 : (NIN <= 2 ? 4 : 2))) zip_tile_vec(TileArgs<NIN + 1> a, T s0, T s1, int *flag)
+// FULL = the tile lies entirely inside the array (every tile but the last row/column of tiles): bounds predicates fold away
+template <typename T, int OP, int NIN, bool STEP2, bool FULL>
+__device__ __forceinline__ void zip_tile_vec_body(const TileArgs<NIN + 1> &a, T s0, T s1, int *flag, unsigned char *tile_raw, int64_t tx,
+                                                  int64_t ty, const int64_t (&off)[NIN + 1])
 {
     using V = Vec128<T>;
     constexpr int N = V::N;
@@ -564,13 +566,10 @@ __global__ void __launch_bounds__(256, STEP2 ? 2 : (NIN <= 1 ? 6 : (NIN <= 2 ? 4
     constexpr int PASSES = TS / RPP;  // 4 (f32) / 2 (f64)
     constexpr int NI = NIN > 0 ? NIN : 1;
     constexpr int NP = NIN + 1;
-    extern __shared__ __align__(16) unsigned char tile_raw[];  // one padded TS x (TS+1) tile per staged producer
     T(*tile)[TS][TS + 1] = reinterpret_cast<T(*)[TS][TS + 1]>(tile_raw);
     const int vl = threadIdx.x % VPR;
     const int hi = threadIdx.x / VPR;
-    for (int64_t vb = blockIdx.x; vb < a.total_tiles; vb += gridDim.x) {
-        int64_t tx, ty, off[NP];
-        tile_coords<NP>(a, vb, tx, ty, off);
+    {
         const int64_t x0 = tx * TS, y0 = ty * TS;
         V ld[NI][PASSES];
         V ld2[STEP2 ? NI : 1][STEP2 ? PASSES : 1];  // second vector of a +-2-stepped staged producer
@@ -586,7 +585,7 @@ __global__ void __launch_bounds__(256, STEP2 ? 2 : (NIN <= 1 ? 6 : (NIN <= 2 ? 4
 #pragma unroll
                 for (int ps = 0; ps < PASSES; ++ps) {
                     const int64_t x = x0 + hi + ps * RPP;
-                    if (x < a.nx && y < a.ny) {
+                    if (FULL || (x < a.nx && y < a.ny)) {
                         ld[p - 1][ps] = *reinterpret_cast<const V *>(src + A + x * a.xs[p]);
                         if constexpr (STEP2) {
                             if (sy == 2) ld2[p - 1][ps] = *reinterpret_cast<const V *>(src + A + N + x * a.xs[p]);
@@ -598,7 +597,7 @@ __global__ void __launch_bounds__(256, STEP2 ? 2 : (NIN <= 1 ? 6 : (NIN <= 2 ? 4
 #pragma unroll
                 for (int ps = 0; ps < PASSES; ++ps) {
                     const int64_t y = y0 + hi + ps * RPP;
-                    if (x < a.nx && y < a.ny) ld[p - 1][ps] = *reinterpret_cast<const V *>(src + y * a.ys[p] + x);
+                    if (FULL || (x < a.nx && y < a.ny)) ld[p - 1][ps] = *reinterpret_cast<const V *>(src + y * a.ys[p] + x);
                 }
             }
         }
@@ -610,7 +609,7 @@ __global__ void __launch_bounds__(256, STEP2 ? 2 : (NIN <= 1 ? 6 : (NIN <= 2 ? 4
 #pragma unroll
                 for (int ps = 0; ps < PASSES; ++ps) {
                     const int lx = hi + ps * RPP;
-                    if (x0 + lx < a.nx && y0 + (int64_t)vl * N < a.ny) {
+                    if (FULL || (x0 + lx < a.nx && y0 + (int64_t)vl * N < a.ny)) {
                         const V &v0 = ld[p - 1][ps];
 #pragma unroll
                         for (int e = 0; e < N; ++e) {
@@ -637,7 +636,7 @@ __global__ void __launch_bounds__(256, STEP2 ? 2 : (NIN <= 1 ? 6 : (NIN <= 2 ? 4
             for (int ps = 0; ps < PASSES; ++ps) {
                 const int ly = hi + ps * RPP;
                 const int64_t y = y0 + ly;
-                if (x < a.nx && y < a.ny) {
+                if (FULL || (x < a.nx && y < a.ny)) {
                     V o;
 #pragma unroll
                     for (int e = 0; e < N; ++e) {
@@ -654,6 +653,20 @@ __global__ void __launch_bounds__(256, STEP2 ? 2 : (NIN <= 1 ? 6 : (NIN <= 2 ? 4
             }
         }
         __syncthreads();
+    }
+}
+
+template <typename T, int OP, int NIN, bool STEP2>
+__global__ void __launch_bounds__(256, STEP2 ? 2 : (NIN <= 1 ? 6 : (NIN <= 2 ? 4 : 2))) zip_tile_vec(TileArgs<NIN + 1> a, T s0, T s1, int *flag)
+{
+    constexpr int TS = TileShape<T>::TS;
+    extern __shared__ __align__(16) unsigned char tile_raw[];  // one padded TS x (TS+1) tile per staged producer
+    const int64_t full_x = a.nx / TS, full_y = a.ny / TS;
+    for (int64_t vb = blockIdx.x; vb < a.total_tiles; vb += gridDim.x) {
+        int64_t tx, ty, off[NIN + 1];
+        tile_coords<NIN + 1>(a, vb, tx, ty, off);
+        if (tx < full_x && ty < full_y) zip_tile_vec_body<T, OP, NIN, STEP2, true>(a, s0, s1, flag, tile_raw, tx, ty, off);
+        else zip_tile_vec_body<T, OP, NIN, STEP2, false>(a, s0, s1, flag, tile_raw, tx, ty, off);
     }
 }
 
