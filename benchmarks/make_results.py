@@ -38,11 +38,11 @@ def main():
         d = load(f"r01_bench_n{n}.json")
         if d:
             out.append(f"| {n} | {d['value']:.0f} | {d['value'] / n1['value']:.2f} | {d['e2e']['value']:.0f} |")
-    d8 = load("r01_bench_n8.json")
+    d8 = load("r01_bench_n8_extras.json") or load("r01_bench_n8.json")  # the run WITH extras (headline lines above are --no-extras reruns)
     if d8 and "extra" in d8 and "C5_zip+global_sum_f32" in d8["extra"]:
         ex = d8["extra"]
         c5 = ex["C5_zip+global_sum_f32"]
-        out += ["", "## Multi-GPU exchange steps (8 GPUs, `extra` of `profiles/r01_bench_n8.json`)", "",
+        out += ["", "## Multi-GPU exchange steps (8 GPUs, `extra` of `profiles/r01_bench_n8_extras.json`)", "",
                 "| case | NCCL (`torch.distributed` on the ctx stream) | peer memory over NVLink (`csrc/peer.cu`) |", "|---|---|---|"]
         if "C5_zip+global_sum_f32_peer_fused" in ex:
             pf = ex["C5_zip+global_sum_f32_peer_fused"]
