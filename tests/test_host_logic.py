@@ -70,6 +70,22 @@ def test_compute_fails_loudly_without_gpu():
     a = mk(4096, np.float32, (4,), (1,))
     parts = (View * 2)(a, a)
     assert nd.lib().ndb_zip(None, 0, None, 2, parts) != 0  # null context: no fallback
+    # every other compute entry point refuses a null context the same way (there is no CPU path to fall into)
+    L = nd.lib()
+    out = np.zeros(4, np.float32)
+    hp = C.c_void_p(out.ctypes.data)
+    assert L.ndb_reduce_all(None, 0, C.byref(a), hp) != 0
+    assert L.ndb_reduce_all_dev(None, 0, C.byref(a), hp) != 0
+    assert L.ndb_reduce_all_peer(None, 0, C.byref(a), hp) != 0
+    assert L.ndb_reduce_axis(None, 0, 0, C.byref(a), C.byref(a), 0.0) != 0
+    assert L.ndb_reduce_axis_peer(None, 0, 0, C.byref(a), C.byref(a), 0.0, 4) != 0
+    assert L.ndb_accumulate_axis(None, 2, 0, C.byref(a)) != 0
+    assert L.ndb_cast(None, C.byref(a), C.byref(a)) != 0
+    assert L.ndb_dot(None, C.byref(a), C.byref(a), hp) != 0
+    assert L.ndb_peer_allreduce(None, 0, 0, hp, hp, 4) != 0
+    assert L.ndb_peer_allgather(None, 0, hp, hp, 4) != 0
+    assert L.ndb_peer_window_create(None, 0, 1, 1 << 10, hp) != 0
+    assert L.ndb_peer_window_attach(None, hp) != 0
 
 
 @pytest.mark.parametrize("spec", [(1, 3, -1), (1, None, -2), (0, 4, -2), (0, None, 2), (-3, -1, 1), (2, 2, 1), (0, 0, -1),
