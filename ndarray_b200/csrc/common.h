@@ -89,11 +89,19 @@ struct ndb_ctx {
     void *stage[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     size_t stage_bytes[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     cudaStream_t copy_in = nullptr, copy_out = nullptr;
+    // pinned bounce buffers for PAGEABLE host memory (the CBLAS boundary hands in ndarray's Vec storage)
+    void *bounce[2] = {nullptr, nullptr};
+    cudaEvent_t bounce_ev[2] = {nullptr, nullptr};
 };
 
 namespace ndb {
 int ensure_workspace(ndb_ctx *ctx, size_t bytes);
 int ensure_stage(ndb_ctx *ctx, int slot, size_t bytes);
+// pageable host <-> device through two pinned bounce buffers: a few host threads copy chunk i+1 while the DMA engine
+// moves chunk i (cudaMemcpy from pageable memory runs at ~12 GB/s on these boxes, this pipeline at the threads' memcpy rate).
+// Ordered after / before work on ctx->stream; returns after the last chunk has been ISSUED (h2d) or has LANDED (d2h).
+int staged_h2d(ndb_ctx *ctx, void *dst_dev, const void *src_host, size_t bytes);
+int staged_d2h(ndb_ctx *ctx, void *dst_host, const void *src_dev, size_t bytes);
 struct PeerArgs;
 int peer_begin(ndb_ctx *ctx, int blocks, size_t bytes, PeerArgs *out);  // peer.cu
 struct DeviceGuard {

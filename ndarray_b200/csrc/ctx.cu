@@ -1,6 +1,11 @@
 // Context, memory, events and error plumbing of libndb200.
 #include <stdarg.h>
 
+#include <algorithm>
+#include <cstdlib>
+#include <thread>
+#include <vector>
+
 #include "common.h"
 
 namespace ndb {
@@ -114,6 +119,91 @@ int ensure_workspace(ndb_ctx *ctx, size_t bytes)
     return NDB_OK;
 }
 
+namespace {
+
+constexpr size_t BOUNCE_BYTES = size_t(16) << 20;
+
+int ensure_bounce(ndb_ctx *ctx)
+{
+    for (int i = 0; i < 2; ++i) {
+        if (!ctx->bounce[i]) NDB_CUDA(cudaHostAlloc(&ctx->bounce[i], BOUNCE_BYTES, cudaHostAllocDefault));
+        if (!ctx->bounce_ev[i]) NDB_CUDA(cudaEventCreateWithFlags(&ctx->bounce_ev[i], cudaEventDisableTiming));
+    }
+    return NDB_OK;
+}
+
+// memcpy split over a few threads (one thread moves ~10 GB/s; the DMA engine wants ~50)
+void parallel_memcpy(void *dst, const void *src, size_t bytes)
+{
+    unsigned hw = std::thread::hardware_concurrency();
+    int nt = (int)std::min<unsigned>(8, std::max<unsigned>(1, hw / 2));
+    if (getenv("NDB_COPY_THREADS")) nt = std::max(1, atoi(getenv("NDB_COPY_THREADS")));
+    if (bytes < (size_t(1) << 20) || nt == 1) {
+        memcpy(dst, src, bytes);
+        return;
+    }
+    const size_t per = ((bytes + nt - 1) / nt + 4095) & ~size_t(4095);
+    std::vector<std::thread> th;
+    for (int t = 1; t < nt; ++t) {
+        const size_t lo = per * t;
+        if (lo >= bytes) break;
+        const size_t len = std::min(per, bytes - lo);
+        th.emplace_back([=] { memcpy((char *)dst + lo, (const char *)src + lo, len); });
+    }
+    memcpy(dst, src, std::min(per, bytes));
+    for (auto &x : th) x.join();
+}
+
+}  // namespace
+
+int staged_h2d(ndb_ctx *ctx, void *dst_dev, const void *src_host, size_t bytes)
+{
+    if (bytes < (size_t(4) << 20) || getenv("NDB_NO_BOUNCE")) {
+        NDB_CUDA(cudaMemcpyAsync(dst_dev, src_host, bytes, cudaMemcpyHostToDevice, ctx->stream));
+        return NDB_OK;
+    }
+    NDB_TRY(ensure_bounce(ctx));
+    size_t done = 0;
+    for (int i = 0; done < bytes; ++i) {
+        const int b = i & 1;
+        const size_t len = std::min(BOUNCE_BYTES, bytes - done);
+        if (i >= 2) NDB_CUDA(cudaEventSynchronize(ctx->bounce_ev[b]));  // the DMA that last read this buffer is done
+        parallel_memcpy(ctx->bounce[b], (const char *)src_host + done, len);
+        NDB_CUDA(cudaMemcpyAsync((char *)dst_dev + done, ctx->bounce[b], len, cudaMemcpyHostToDevice, ctx->stream));
+        NDB_CUDA(cudaEventRecord(ctx->bounce_ev[b], ctx->stream));
+        done += len;
+    }
+    // the bounce buffers are reused by the next call: wait until the DMA engine has drained them
+    NDB_CUDA(cudaEventSynchronize(ctx->bounce_ev[0]));
+    NDB_CUDA(cudaEventSynchronize(ctx->bounce_ev[1]));
+    return NDB_OK;
+}
+
+int staged_d2h(ndb_ctx *ctx, void *dst_host, const void *src_dev, size_t bytes)
+{
+    if (bytes < (size_t(4) << 20) || getenv("NDB_NO_BOUNCE")) {
+        NDB_CUDA(cudaMemcpyAsync(dst_host, src_dev, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+        NDB_CUDA(cudaStreamSynchronize(ctx->stream));
+        return NDB_OK;
+    }
+    NDB_TRY(ensure_bounce(ctx));
+    const size_t chunks = (bytes + BOUNCE_BYTES - 1) / BOUNCE_BYTES;
+    auto issue = [&](size_t i) -> cudaError_t {
+        const size_t off = i * BOUNCE_BYTES, len = std::min(BOUNCE_BYTES, bytes - off);
+        cudaError_t e = cudaMemcpyAsync(ctx->bounce[i & 1], (const char *)src_dev + off, len, cudaMemcpyDeviceToHost, ctx->stream);
+        if (e == cudaSuccess) e = cudaEventRecord(ctx->bounce_ev[i & 1], ctx->stream);
+        return e;
+    };
+    NDB_CUDA(issue(0));
+    for (size_t i = 0; i < chunks; ++i) {
+        if (i + 1 < chunks) NDB_CUDA(issue(i + 1));  // next chunk's DMA overlaps this chunk's host copy
+        NDB_CUDA(cudaEventSynchronize(ctx->bounce_ev[i & 1]));
+        const size_t off = i * BOUNCE_BYTES, len = std::min(BOUNCE_BYTES, bytes - off);
+        parallel_memcpy((char *)dst_host + off, ctx->bounce[i & 1], len);
+    }
+    return NDB_OK;
+}
+
 int ensure_stage(ndb_ctx *ctx, int slot, size_t bytes)
 {
     if (ctx->stage_bytes[slot] >= bytes) return NDB_OK;
@@ -208,6 +298,10 @@ int ndb_ctx_destroy(ndb_ctx *ctx)
     if (ctx->host_flag) cudaFreeHost(ctx->host_flag);
     if (ctx->host_scalar) cudaFreeHost(ctx->host_scalar);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+    for (int i = 0; i < 2; ++i) {
+        if (ctx->bounce[i]) cudaFreeHost(ctx->bounce[i]);
+        if (ctx->bounce_ev[i]) cudaEventDestroy(ctx->bounce_ev[i]);
+    }
     if (ctx->copy_in) cudaStreamDestroy(ctx->copy_in);
     if (ctx->copy_out) cudaStreamDestroy(ctx->copy_out);
     delete ctx;

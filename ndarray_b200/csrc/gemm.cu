@@ -443,12 +443,12 @@ static void cblas_gemm_impl(int dtype, int layout, int transa, int transb, int m
     bool ok = ensure_stage(ctx, 0, std::max<size_t>(16, A.span * sizeof(T))) == NDB_OK &&
               ensure_stage(ctx, 1, std::max<size_t>(16, B.span * sizeof(T))) == NDB_OK &&
               ensure_stage(ctx, 2, std::max<size_t>(16, Cm.span * sizeof(T))) == NDB_OK;
-    if (ok && A.span) ok = cudaMemcpyAsync(ctx->stage[0], a, A.span * sizeof(T), cudaMemcpyHostToDevice, ctx->stream) == cudaSuccess;
-    if (ok && B.span) ok = cudaMemcpyAsync(ctx->stage[1], b, B.span * sizeof(T), cudaMemcpyHostToDevice, ctx->stream) == cudaSuccess;
+    if (ok && A.span) ok = staged_h2d(ctx, ctx->stage[0], a, A.span * sizeof(T)) == NDB_OK;
+    if (ok && B.span) ok = staged_h2d(ctx, ctx->stage[1], b, B.span * sizeof(T)) == NDB_OK;
     // C travels up even for beta == 0 when it has padding (ldc > minor), so the padding survives the trip back
     const bool c_dense = (layout == NdbCblasRowMajor ? ldc == n : ldc == m);
     if (ok && (beta != T(0) || !c_dense))
-        ok = cudaMemcpyAsync(ctx->stage[2], c, Cm.span * sizeof(T), cudaMemcpyHostToDevice, ctx->stream) == cudaSuccess;
+        ok = staged_h2d(ctx, ctx->stage[2], c, Cm.span * sizeof(T)) == NDB_OK;
     ndb_view va, vb, vc;
     memset(&va, 0, sizeof(va));
     memset(&vb, 0, sizeof(vb));
@@ -457,7 +457,7 @@ static void cblas_gemm_impl(int dtype, int layout, int transa, int transb, int m
     vb.ptr = ctx->stage[1]; vb.ndim = 2; vb.dtype = dtype; vb.dim[0] = k; vb.dim[1] = n; vb.stride[0] = B.rs; vb.stride[1] = B.cs;
     vc.ptr = ctx->stage[2]; vc.ndim = 2; vc.dtype = dtype; vc.dim[0] = m; vc.dim[1] = n; vc.stride[0] = Cm.rs; vc.stride[1] = Cm.cs;
     if (ok) ok = gemm_impl(ctx, &alpha, &va, &vb, &beta, &vc) == NDB_OK;
-    if (ok) ok = cudaMemcpyAsync(c, ctx->stage[2], Cm.span * sizeof(T), cudaMemcpyDeviceToHost, ctx->stream) == cudaSuccess;
+    if (ok) ok = staged_d2h(ctx, c, ctx->stage[2], Cm.span * sizeof(T)) == NDB_OK;
     if (ok) ok = cudaStreamSynchronize(ctx->stream) == cudaSuccess;
     if (!ok) {
         fprintf(stderr, "libndb200: cblas gemm failed: %s\n", ndb_last_error());
@@ -483,7 +483,7 @@ static void cblas_gemv_impl(int dtype, int layout, int trans, int m, int n, T al
     const size_t syb = ((size_t)(ylen - 1) * ay + 1) * sizeof(T);
     bool ok = ensure_stage(ctx, 0, std::max<size_t>(16, A.span * sizeof(T))) == NDB_OK && ensure_stage(ctx, 1, sxb) == NDB_OK &&
               ensure_stage(ctx, 2, syb) == NDB_OK;
-    if (ok && A.span) ok = cudaMemcpyAsync(ctx->stage[0], a, A.span * sizeof(T), cudaMemcpyHostToDevice, ctx->stream) == cudaSuccess;
+    if (ok && A.span) ok = staged_h2d(ctx, ctx->stage[0], a, A.span * sizeof(T)) == NDB_OK;
     if (ok && xlen > 0) ok = cudaMemcpyAsync(ctx->stage[1], x, sxb, cudaMemcpyHostToDevice, ctx->stream) == cudaSuccess;
     if (ok && (beta != T(0) || ay != 1)) ok = cudaMemcpyAsync(ctx->stage[2], y, syb, cudaMemcpyHostToDevice, ctx->stream) == cudaSuccess;
     ndb_view va, vx, vy;
