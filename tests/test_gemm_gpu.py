@@ -321,3 +321,21 @@ def test_f64_small_outputs_split_k_over_clusters(nd, monkeypatch):
                 res[split] = runs[0]
                 assert rel_norm(runs[0], ref) < 1e-12 * math.sqrt(k), (m, k, n, split)
             monkeypatch.delenv("NDB_GEMM_F64_SPLITK", raising=False)
+
+
+def test_cblas_large_operands_bounce_pipeline(nd):
+    """Operands above 4 MiB travel through the pinned bounce-buffer pipeline (several 16 MiB chunks each way, pageable
+    numpy memory like ndarray's Vec): results and the ldc padding must survive the trip."""
+    L = nd.lib()
+    L.cblas_dgemm.restype = None
+    L.cblas_dgemm.argtypes = [C.c_int] * 6 + [C.c_double, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_double, C.c_void_p, C.c_int]
+    rng = np.random.default_rng(21)
+    m, n, k = 2304, 2048, 1536
+    a = rng.standard_normal((m, k))               # 27 MiB
+    b = rng.standard_normal((k, n))               # 24 MiB
+    c = rng.standard_normal((m, n + 8))           # 36 MiB, ldc = n + 8
+    c0 = c.copy()
+    L.cblas_dgemm(101, 111, 111, m, n, k, 1.5, a.ctypes.data, k, b.ctypes.data, n, -0.5, c.ctypes.data, n + 8)
+    ref = 1.5 * (a @ b) - 0.5 * c0[:, :n]
+    assert rel_norm(c[:, :n], ref) < 1e-12 * math.sqrt(k)
+    assert np.array_equal(c[:, n:], c0[:, n:])
