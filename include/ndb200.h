@@ -294,6 +294,11 @@ int ndb_peer_allgather(ndb_ctx *ctx, int dtype, const void *local_dev, void *out
  * without launching anything, when the layout, the tile count (> 2 per SM) or the slot size rule this path out; the rules
  * depend on shapes only, so all ranks decide alike and the caller falls back to ndb_reduce_axis + ndb_peer_allreduce. */
 int ndb_reduce_axis_peer(ndb_ctx *ctx, int redop, int axis, const ndb_view *in, const ndb_view *out, double ddof, int64_t n_global);
+/* Would ndb_reduce_axis_peer take the fused path for these arguments on THIS rank?  NDB_OK / NDB_ERR_UNSUPPORTED, launches
+ * nothing.  A caller that cannot rule out rank-dependent layouts (a misaligned shard on one rank) agrees on the answer
+ * across ranks once per shape (logical AND) before using the fused call, because a rank that falls back while the others
+ * wait in the kernel would only be caught by the 20 s watchdog. */
+int ndb_reduce_axis_peer_ok(ndb_ctx *ctx, int redop, int axis, const ndb_view *in, const ndb_view *out, double ddof, int64_t n_global);
 /* ndb_reduce_all_dev over ALL shards: the kernel that finishes this rank's reduction tree also performs the exchange. */
 int ndb_reduce_all_peer(ndb_ctx *ctx, int redop, const ndb_view *in, void *out_dev);
 

@@ -120,6 +120,7 @@ def lib():
         "ndb_peer_allgather": (i32, [vp, i32, vp, vp, C.c_int64]),
         "ndb_reduce_all_peer": (i32, [vp, i32, PV, vp]),
         "ndb_reduce_axis_peer": (i32, [vp, i32, i32, PV, PV, C.c_double, C.c_int64]),
+        "ndb_reduce_axis_peer_ok": (i32, [vp, i32, i32, PV, PV, C.c_double, C.c_int64]),
         "ndb_accumulate_axis": (i32, [vp, i32, i32, PV]),
         "ndb_dot": (i32, [vp, PV, PV, vp]),
         "ndb_gemm": (i32, [vp, vp, PV, PV, vp, PV]),

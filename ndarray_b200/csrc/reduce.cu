@@ -1067,6 +1067,7 @@ static int reduce_axis_launch(ndb_ctx *ctx, RedArgs &a, const ZipPlan &z)
                 if (!vec || total > std::min<int64_t>(PEER_MAX_TILES, (int64_t)ctx->sm_count * 2) || (splits > 1 && a.tickets == nullptr) ||
                     (size_t)a.n_out * sizeof(Acc<T, R>) > ctx->peer_slot_bytes || !ctx->peer_tile_epoch)
                     return NDB_ERR_UNSUPPORTED;
+                if (a.peer_on == 2) return NDB_OK;  // eligibility query only (ndb_reduce_axis_peer_ok): nothing is launched
                 NDB_TRY(peer_begin(ctx, 0, (size_t)a.n_out * sizeof(Acc<T, R>), &a.peer));
                 a.tile_epoch = ctx->peer_tile_epoch;
                 red_cols<T, R, FIN, Vec128<T>::N, true><<<grid, block, 0, st>>>(a);
@@ -1128,7 +1129,7 @@ static int fill_view(ndb_ctx *ctx, const ndb_view *out, double value)
 }
 
 static int reduce_axis_impl(ndb_ctx *ctx, int redop, int axis, const ndb_view *in, const ndb_view *out,
-                            const ndb_view *out2, double ddof, bool peer = false, int64_t n_global = 0)
+                            const ndb_view *out2, double ddof, int peer = 0, int64_t n_global = 0)
 {
     if (!ctx) {
         set_error("reduce_axis: null context (no CPU fallback exists)");
@@ -1216,7 +1217,7 @@ static int reduce_axis_impl(ndb_ctx *ctx, int redop, int axis, const ndb_view *i
     a.nT = nT;
     a.dof = dof;
     a.splits = 1;
-    a.peer_on = peer ? 1 : 0;
+    a.peer_on = peer;
     // a backwards reduced axis is walked forwards from its low end (legal: commutative up to tolerance)
     if (a.s < 0) {
         a.in += (n - 1) * a.s * (int64_t)dtype_size(in->dtype);
@@ -1354,7 +1355,14 @@ int ndb_reduce_axis_peer(ndb_ctx *ctx, int redop, int axis, const ndb_view *in, 
         set_error("reduce_axis_peer: no peer window attached to this context");
         return NDB_ERR_INVALID_ARG;
     }
-    return reduce_axis_impl(ctx, redop, axis, in, out, nullptr, ddof, true, n_global);
+    return reduce_axis_impl(ctx, redop, axis, in, out, nullptr, ddof, 1, n_global);
+}
+
+int ndb_reduce_axis_peer_ok(ndb_ctx *ctx, int redop, int axis, const ndb_view *in, const ndb_view *out, double ddof, int64_t n_global)
+{
+    clear_error();
+    if (redop < 0 || redop >= NDB_RED__COUNT || !ctx || ctx->peer_world <= 0 || !ctx->peer_attached) return NDB_ERR_UNSUPPORTED;
+    return reduce_axis_impl(ctx, redop, axis, in, out, nullptr, ddof, 2, n_global);
 }
 
 int ndb_welford_axis(ndb_ctx *ctx, int axis, const ndb_view *in, const ndb_view *mean_out, const ndb_view *m2_out)

@@ -61,6 +61,8 @@ class PeerGroup:
 
     def __init__(self, ctx, dist, slot_bytes: int = 1 << 20):
         self.ctx, self.rank, self.world = ctx, dist.get_rank(), dist.get_world_size()
+        self._dist = dist
+        self._fused_ok = {}  # (shape, strides, dtype, redop) -> all ranks can take ndb_reduce_axis_peer
         handle = (C.c_ubyte * 64)()
         check(lib().ndb_peer_window_create(ctx.handle, self.rank, self.world, slot_bytes, handle))
         handles = [None] * self.world
@@ -97,9 +99,21 @@ def _fused_axis0(local: Array, redop: int, ddof: float, n_global: int, peers: "P
     when the library rules the layout out (shape-derived, so every rank gets the same answer)."""
     from . import _ffi
     out = Array.uninit(local.shape[1:], local.dtype, ctx=local.ctx)
+    # agree ONCE per (shape, strides, dtype, op) that every rank takes the fused path: a rank that fell back while the
+    # others wait inside the kernel would only be caught by the watchdog
+    key = (tuple(local.shape[1:]), tuple(local.strides), str(local.dtype), int(redop))
+    agreed = peers._fused_ok.get(key)
+    if agreed is None:
+        mine = lib().ndb_reduce_axis_peer_ok(local.ctx.handle, redop, 0, C.byref(local.v), C.byref(out.v), float(ddof), int(n_global)) == 0
+        votes = [None] * peers.world
+        peers._dist.all_gather_object(votes, bool(mine))
+        agreed = all(votes)
+        peers._fused_ok[key] = agreed
+    if not agreed:
+        return None
     st = lib().ndb_reduce_axis_peer(local.ctx.handle, redop, 0, C.byref(local.v), C.byref(out.v), float(ddof), int(n_global))
     if st == _ffi.ERR_UNSUPPORTED:
-        return None
+        raise _ffi.NdbError(st, "fused sharded reduction refused after all ranks had agreed on it")
     check(st)
     return out
 

@@ -90,6 +90,7 @@ extern "C" {
     pub fn ndb_peer_allreduce(ctx: *mut ndb_ctx, redop: c_int, dtype: c_int, local_dev: *const c_void, out_dev: *mut c_void, n: i64) -> c_int;
     pub fn ndb_peer_allgather(ctx: *mut ndb_ctx, dtype: c_int, local_dev: *const c_void, out_dev: *mut c_void, n: i64) -> c_int;
     pub fn ndb_reduce_axis_peer(ctx: *mut ndb_ctx, redop: c_int, axis: c_int, input: *const ndb_view, out: *const ndb_view, ddof: c_double, n_global: i64) -> c_int;
+    pub fn ndb_reduce_axis_peer_ok(ctx: *mut ndb_ctx, redop: c_int, axis: c_int, input: *const ndb_view, out: *const ndb_view, ddof: c_double, n_global: i64) -> c_int;
     pub fn ndb_reduce_all_peer(ctx: *mut ndb_ctx, redop: c_int, input: *const ndb_view, out_dev: *mut c_void) -> c_int;
     pub fn ndb_accumulate_axis(ctx: *mut ndb_ctx, op: c_int, axis: c_int, v: *const ndb_view) -> c_int;
     // ndarray's own CBLAS boundary (src/linalg/impl_linalg.rs:466-491, :116-122); normally bound through cblas-sys
