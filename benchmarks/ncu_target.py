@@ -1,6 +1,6 @@
 """One small workload per invocation, for `ncu --set full` captures (kept short: ncu replays every kernel ~40x).
 
-  python benchmarks/ncu_target.py zip|reduce|gemm64|gemm32
+  python benchmarks/ncu_target.py zip|combined|reduce|gemm64|gemm32
 """
 import sys
 from pathlib import Path
@@ -27,6 +27,17 @@ def main():
             Zip.from_(out.slice(s_[: n // 2, :, :])).and_(x.slice(s_[::-2, :, :])).and_(y.slice(s_[::2, :, :])).for_each("a=b+c")
             Zip.from_(out).and_(x).and_broadcast(row).for_each("a=b*c")
             Zip.from_(out).and_(x.slice(s_[:, :, ::-1])).and_(y).for_each("a=b+c")
+    elif which == "combined":
+        n = 512
+        x = Array.from_numpy(rng.random((n, n, n), dtype=np.float32))
+        y = Array.from_numpy(rng.random((n, n, n), dtype=np.float32))
+        row = Array.from_numpy(rng.random(n, dtype=np.float32))
+        out = Array.uninit((n, n, n), np.float32)
+        o_half = out.slice(s_[: n // 2, :, :])
+        rowb = row.broadcast((n // 2, n, n))
+        xts, ys = x.t().slice(s_[::-2, :, :]), y.slice(s_[::2, :, :])
+        for _ in range(3):
+            Zip.from_(o_half).and_(ys).and_(rowb).and_(xts).for_each("a=b*c+d")
     elif which == "reduce":
         n = 16384
         f = Array.from_numpy(rng.standard_normal((n, n)))
