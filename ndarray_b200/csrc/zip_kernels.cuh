@@ -441,6 +441,12 @@ struct TileArgs {
     int y_fastest;  // block order: 1 = consecutive blocks walk Y tiles first
 };
 
+#ifndef NDB_TILE_MINB_STEP2
+#define NDB_TILE_MINB_STEP2 2
+#endif
+#ifndef NDB_TILE_MINB3
+#define NDB_TILE_MINB3 2
+#endif
 #ifndef NDB_TILE_MINB2
 #define NDB_TILE_MINB2 4  // CTAs/SM the binary-op tile kernel is compiled for (64 registers)
 #endif
@@ -661,7 +667,7 @@ __device__ __forceinline__ void zip_tile_vec_body(const TileArgs<NIN + 1> &a, T 
 }
 
 template <typename T, int OP, int NIN, bool STEP2>
-__global__ void __launch_bounds__(256, STEP2 ? 2 : (NIN <= 1 ? 6 : (NIN <= 2 ? NDB_TILE_MINB2 : 2))) zip_tile_vec(TileArgs<NIN + 1> a, T s0, T s1, int *flag)
+__global__ void __launch_bounds__(256, STEP2 ? NDB_TILE_MINB_STEP2 : (NIN <= 1 ? 6 : (NIN <= 2 ? NDB_TILE_MINB2 : NDB_TILE_MINB3))) zip_tile_vec(TileArgs<NIN + 1> a, T s0, T s1, int *flag)
 {
     constexpr int TS = TileShape<T>::TS;
     extern __shared__ __align__(16) unsigned char tile_raw[];  // one padded TS x (TS+1) tile per staged producer
