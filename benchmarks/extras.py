@@ -187,52 +187,61 @@ def run_extras(nd, ctx, torch, dist, rank, world, local, peak_gbs):
             import ctypes as C
             from ndarray_b200 import parallel as par
             from ndarray_b200.array import Red
-            peers = par.PeerGroup(ctx, dist, slot_bytes=1 << 20)
             L = nd.lib()
+            try:
+                peers = par.PeerGroup(ctx, dist, slot_bytes=1 << 20)  # raises on ALL ranks or on none
+            except Exception as e:  # noqa: BLE001
+                peers = None
+                out["peer_windows"] = {"error": repr(e)}
 
-            def c5_peer():
-                Zip.from_(a).and_(b).and_(c).for_each("a=b*c+a")
-                L.ndb_reduce_all_peer(ctx.handle, Red.SUM, C.byref(a.v), C.c_void_p(accv.v.ptr))
+            def peer_section():
+                def c5_peer():
+                    Zip.from_(a).and_(b).and_(c).for_each("a=b*c+a")
+                    L.ndb_reduce_all_peer(ctx.handle, Red.SUM, C.byref(a.v), C.c_void_p(accv.v.ptr))
 
-            med, best = _time(ctx, c5_peer, 10, 2)
-            t = torch.tensor([med], device=dev, dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            out["C5_zip+global_sum_f32_peer_fused"] = {"GB/s_aggregate": round(gbs(nbytes, float(t.item())), 1), "ms": round(float(t.item()), 3),
-                                                       "collective": "none: the sum's finishing kernel exchanges the scalar through peer memory"}
-            # exchange latency alone: one element and the C3 sum_axis(Axis(0)) vector (16384 f64 = 128 KiB)
-            vec_t = torch.zeros(16384, device=dev, dtype=torch.float64)
-            vec = tarr(vec_t)
-            for label, arr, tt in (("1elt", accv, acc), ("128KiB", vec, vec_t)):
-                def nccl(tt=tt):
-                    with torch.cuda.stream(stream):
-                        dist.all_reduce(tt)
-                med_n, _ = _time(ctx, nccl, 50, 5)
-                med_p, _ = _time(ctx, lambda arr=arr: peers.allreduce_(arr), 50, 5)
-                tn = torch.tensor([med_n, med_p], device=dev, dtype=torch.float64)
-                dist.all_reduce(tn, op=dist.ReduceOp.MAX)
-                out[f"allreduce_latency_{label}"] = {"nccl_us": round(float(tn[0].item()) * 1e3, 1), "peer_memory_us": round(float(tn[1].item()) * 1e3, 1)}
-            # C3 sharded: sum_axis(Axis(0)) of a [2048, 16384] f64 slab per rank + exchange of the 128 KiB vector
-            slab_t = torch.randn(2048, 16384, device=dev, dtype=torch.float64)
-            slab = tarr(slab_t)
-            def two_launch():
-                part = slab.sum_axis(0)
-                return peers.allreduce_(part)
+                med, best = _time(ctx, c5_peer, 10, 2)
+                t = torch.tensor([med], device=dev, dtype=torch.float64)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                out["C5_zip+global_sum_f32_peer_fused"] = {"GB/s_aggregate": round(gbs(nbytes, float(t.item())), 1), "ms": round(float(t.item()), 3),
+                                                           "collective": "none: the sum's finishing kernel exchanges the scalar through peer memory"}
+                # exchange latency alone: one element and the C3 sum_axis(Axis(0)) vector (16384 f64 = 128 KiB)
+                vec_t = torch.zeros(16384, device=dev, dtype=torch.float64)
+                vec = tarr(vec_t)
+                for label, arr, tt in (("1elt", accv, acc), ("128KiB", vec, vec_t)):
+                    def nccl(tt=tt):
+                        with torch.cuda.stream(stream):
+                            dist.all_reduce(tt)
+                    med_n, _ = _time(ctx, nccl, 50, 5)
+                    med_p, _ = _time(ctx, lambda arr=arr: peers.allreduce_(arr), 50, 5)
+                    tn = torch.tensor([med_n, med_p], device=dev, dtype=torch.float64)
+                    dist.all_reduce(tn, op=dist.ReduceOp.MAX)
+                    out[f"allreduce_latency_{label}"] = {"nccl_us": round(float(tn[0].item()) * 1e3, 1), "peer_memory_us": round(float(tn[1].item()) * 1e3, 1)}
+                # C3 sharded: sum_axis(Axis(0)) of a [2048, 16384] f64 slab per rank + exchange of the 128 KiB vector
+                slab_t = torch.randn(2048, 16384, device=dev, dtype=torch.float64)
+                slab = tarr(slab_t)
+                def two_launch():
+                    part = slab.sum_axis(0)
+                    return peers.allreduce_(part)
 
-            n_glob = 2048 * world
-            assert par._fused_axis0(slab, Red.SUM, 0.0, n_glob, peers) is not None
-            for label, fn in (("nccl", lambda: par.sum_axis0(slab, dist)), ("peer", two_launch),
-                              ("peer_fused_one_launch", lambda: par._fused_axis0(slab, Red.SUM, 0.0, n_glob, peers)),
-                              ("var_nccl", lambda: par.var_axis0(slab, 1.0, dist)),
-                              ("var_peer_fused_one_launch", lambda: par._fused_axis0(slab, Red.VAR, 1.0, n_glob, peers))):
-                med_s, _ = _time(ctx, fn, 20, 3)
-                ts = torch.tensor([med_s], device=dev, dtype=torch.float64)
-                dist.all_reduce(ts, op=dist.ReduceOp.MAX)
-                out[f"C3_sum_axis0_sharded_f64_{label}"] = {"GB/s_aggregate": round(gbs(world * (8 * 2048 * 16384 + 8 * 16384), float(ts.item())), 1),
-                                                           "ms": round(float(ts.item()), 4)}
-            ctx.sync()
-            dist.barrier()
-            peers.close()
-            del slab, slab_t, vec, vec_t
+                n_glob = 2048 * world
+                fused_ok = par._fused_axis0(slab, Red.SUM, 0.0, n_glob, peers) is not None  # agreed across ranks
+                cases = [("nccl", lambda: par.sum_axis0(slab, dist)), ("peer", two_launch), ("var_nccl", lambda: par.var_axis0(slab, 1.0, dist))]
+                if fused_ok:
+                    cases += [("peer_fused_one_launch", lambda: par._fused_axis0(slab, Red.SUM, 0.0, n_glob, peers)),
+                              ("var_peer_fused_one_launch", lambda: par._fused_axis0(slab, Red.VAR, 1.0, n_glob, peers))]
+                for label, fn in cases:
+                    med_s, _ = _time(ctx, fn, 20, 3)
+                    ts = torch.tensor([med_s], device=dev, dtype=torch.float64)
+                    dist.all_reduce(ts, op=dist.ReduceOp.MAX)
+                    out[f"C3_sum_axis0_sharded_f64_{label}"] = {"GB/s_aggregate": round(gbs(world * (8 * 2048 * 16384 + 8 * 16384), float(ts.item())), 1),
+                                                               "ms": round(float(ts.item()), 4)}
+                ctx.sync()
+                dist.barrier()
+                peers.close()
+                del slab, slab_t, vec, vec_t
+
+            if peers is not None:
+                peer_section()
         del a, b, c, ts
         torch.cuda.empty_cache()
     # ---- C4 at N GPUs: A and C row-sharded (8192 rows per rank, weak), B broadcast from rank 0 EVERY step ----------

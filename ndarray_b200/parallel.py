@@ -63,13 +63,29 @@ class PeerGroup:
         self.ctx, self.rank, self.world = ctx, dist.get_rank(), dist.get_world_size()
         self._dist = dist
         self._fused_ok = {}  # (shape, strides, dtype, redop) -> all ranks can take ndb_reduce_axis_peer
+        # Collective-safe construction: a failure on ONE rank (IPC not permitted, out of memory) must not leave the others
+        # waiting in a collective, so every step's outcome is exchanged and all ranks raise together.
         handle = (C.c_ubyte * 64)()
-        check(lib().ndb_peer_window_create(ctx.handle, self.rank, self.world, slot_bytes, handle))
-        handles = [None] * self.world
-        dist.all_gather_object(handles, bytes(handle))
-        blob = (C.c_ubyte * (64 * self.world)).from_buffer_copy(b"".join(handles))
-        check(lib().ndb_peer_window_attach(ctx.handle, blob))
-        dist.barrier()  # nobody stores into a window before everybody has mapped it
+        err = None
+        try:
+            check(lib().ndb_peer_window_create(ctx.handle, self.rank, self.world, slot_bytes, handle))
+        except Exception as e:  # noqa: BLE001
+            err = repr(e)
+        gathered = [None] * self.world
+        dist.all_gather_object(gathered, (err, bytes(handle)))
+        if any(g[0] for g in gathered):
+            lib().ndb_peer_window_destroy(ctx.handle)
+            raise RuntimeError(f"peer window creation failed on some rank: {[g[0] for g in gathered]}")
+        blob = (C.c_ubyte * (64 * self.world)).from_buffer_copy(b"".join(g[1] for g in gathered))
+        try:
+            check(lib().ndb_peer_window_attach(ctx.handle, blob))
+        except Exception as e:  # noqa: BLE001
+            err = repr(e)
+        errs = [None] * self.world
+        dist.all_gather_object(errs, err)  # doubles as the barrier: nobody stores into a window before all have mapped it
+        if any(errs):
+            lib().ndb_peer_window_destroy(ctx.handle)
+            raise RuntimeError(f"peer window attach failed on some rank: {errs}")
         self.slot_bytes = slot_bytes
 
     def allreduce_(self, arr: Array, redop: int = Red.SUM) -> Array:
