@@ -175,3 +175,97 @@ pub fn dot<A: Elem + Default>(x: &DeviceArray<A, Ix1>, y: &DeviceArray<A, Ix1>) 
     check(unsafe { ffi::ndb_dot(x.buf.ctx.0, &x.view(), &y.view(), &mut out as *mut A as *mut c_void) });
     out
 }
+
+// ---- the rest of SURVEY §8f: predicates / fold over a Zip, casts, scans, matrix-vector ----------------------------
+
+/// Comparison predicates for `Zip::all` / `Zip::any` (src/zip/mod.rs:674-696); closures cannot cross the FFI.
+pub enum Pred { Eq = 25, Ne = 26, Lt = 27, Le = 28, Gt = 29, Ge = 30 }
+
+impl<A: Elem> Zip<A> {
+    /// `Zip::from(&a).and(&b).all(|&a, &b| a < b)`: the first two producers are compared; vacuously true when empty.
+    pub fn all(self, pred: Pred) -> bool {
+        let mut r = 0i32;
+        check(unsafe { ffi::ndb_zip_all(self.ctx, pred as i32, std::ptr::null(), self.parts.len() as i32, self.parts.as_ptr(), &mut r) });
+        r != 0
+    }
+    pub fn any(self, pred: Pred) -> bool {
+        let mut r = 0i32;
+        check(unsafe { ffi::ndb_zip_any(self.ctx, pred as i32, std::ptr::null(), self.parts.len() as i32, self.parts.as_ptr(), &mut r) });
+        r != 0
+    }
+    /// `Zip::fold(0, |acc, &a, &b| acc + a * b)` for the additive folds (op = Mul / Add / Sub of the two producers).
+    pub fn fold_sum(self, op: Op) -> A where A: Default {
+        let code = match op { Op::Mul => 4, Op::Add => 2, Op::Sub => 3, _ => panic!("fold_sum: op must be Mul, Add or Sub") };
+        let mut out = A::default();
+        check(unsafe { ffi::ndb_zip_fold_sum(self.ctx, code, std::ptr::null(), self.parts.len() as i32, self.parts.as_ptr(), &mut out as *mut A as *mut c_void) });
+        out
+    }
+}
+
+impl<A: Elem, D: Dimension> DeviceArray<A, D> {
+    /// `a.mapv(|x| x as B)` (Rust `as` semantics: saturating float -> int, NaN -> 0), src/impl_methods.rs:2934.
+    pub fn mapv_cast<B: Elem>(&self) -> DeviceArray<B, D> {
+        let out = DeviceArray::<B, D>::uninit(&self.buf.ctx, self.dim.clone());
+        check(unsafe { ffi::ndb_cast(self.buf.ctx.0, &out.view(), &self.view()) });
+        out
+    }
+    /// `accumulate_axis_inplace(axis, |&prev, cur| *cur = *cur + prev)` / `... * prev` (src/impl_methods.rs:3243): one scan launch.
+    pub fn accumulate_axis_inplace(&mut self, axis: Axis, op: Op) {
+        let code = match op { Op::Add | Op::AddAssign => 2, Op::Mul | Op::MulAssign => 4, _ => panic!("accumulate: op must be Add or Mul") };
+        check(unsafe { ffi::ndb_accumulate_axis(self.buf.ctx.0, code, axis.index() as i32, &self.view()) });
+    }
+    /// whole-array `var(ddof)` / `std(ddof)` (src/numeric/impl_numeric.rs:180-249)
+    pub fn var(&self, ddof: f64) -> A where A: Default {
+        let mut out = A::default();
+        check(unsafe { ffi::ndb_var(self.buf.ctx.0, &self.view(), ddof, 0, &mut out as *mut A as *mut c_void) });
+        out
+    }
+}
+
+/// `general_mat_vec_mul(alpha, &a, &x, beta, &mut y)` (src/linalg/impl_linalg.rs:657).
+pub fn general_mat_vec_mul<A: Elem>(alpha: A, a: &DeviceArray<A, Ix2>, x: &DeviceArray<A, Ix1>, beta: A, y: &mut DeviceArray<A, Ix1>) {
+    check(unsafe { ffi::ndb_gemv(y.buf.ctx.0, &alpha as *const A as *const c_void, &a.view(), &x.view(), &beta as *const A as *const c_void, &y.view()) });
+}
+
+// ---- multi-GPU: one Context per GPU (one process per GPU), arrays sharded along Axis(0) ------------------------------
+
+/// Balanced, contiguous, rank-ordered partition of an axis of length `n` (what `Zip::split` does recursively on one host).
+pub fn shard_bounds(n: usize, rank: usize, world: usize) -> (usize, usize) { (n * rank / world, n * (rank + 1) / world) }
+
+/// Peer windows over NVLink (include/ndb200.h "multi-GPU exchange"): created once per context; `exchange_handles` is any
+/// host-side all-gather of 64-byte blobs the application already has (MPI, a socket, a shared file).
+pub struct PeerGroup { ctx: Arc<Context>, pub rank: usize, pub world: usize }
+impl PeerGroup {
+    pub fn new(ctx: &Arc<Context>, rank: usize, world: usize, slot_bytes: usize, exchange_handles: impl FnOnce([u8; 64]) -> Vec<[u8; 64]>) -> Self {
+        let mut h = [0u8; 64];
+        check(unsafe { ffi::ndb_peer_window_create(ctx.0, rank as i32, world as i32, slot_bytes, h.as_mut_ptr() as *mut c_void) });
+        let all = exchange_handles(h);
+        assert_eq!(all.len(), world);
+        check(unsafe { ffi::ndb_peer_window_attach(ctx.0, all.as_ptr() as *const c_void) });
+        PeerGroup { ctx: ctx.clone(), rank, world }
+    }
+    /// `sum()` over all shards: the kernel that finishes this rank's reduction also exchanges the scalar (no second launch).
+    pub fn global_sum<A: Elem + Default, D: Dimension>(&self, shard: &DeviceArray<A, D>) -> A {
+        let out = DeviceArray::<A, ndarray::Ix0>::uninit(&self.ctx, ());
+        check(unsafe { ffi::ndb_reduce_all_peer(self.ctx.0, 0, &shard.view(), out.ptr as *mut c_void) });
+        let mut host = A::default();
+        check(unsafe { ffi::ndb_d2h(self.ctx.0, &mut host as *mut A as *mut c_void, out.ptr as *const c_void, std::mem::size_of::<A>()) });
+        check(unsafe { ffi::ndb_sync(self.ctx.0) });
+        host
+    }
+    /// `sum_axis` / `mean_axis` / `var_axis` / `std_axis(Axis(0))` of a row-sharded array: one fused launch per rank when
+    /// the layout allows (all ranks must have agreed on that once, `ndb_reduce_axis_peer_ok`), else reduce + exchange.
+    pub fn reduce_axis0<A: Elem, D: Dimension + RemoveAxis>(&self, redop: i32, shard: &DeviceArray<A, D>, ddof: f64, n_global: usize, fused: bool) -> DeviceArray<A, D::Smaller> {
+        let out = DeviceArray::<A, D::Smaller>::uninit(&self.ctx, shard.dim.remove_axis(Axis(0)));
+        if fused {
+            check(unsafe { ffi::ndb_reduce_axis_peer(self.ctx.0, redop, 0, &shard.view(), &out.view(), ddof, n_global as i64) });
+        } else {
+            assert!(redop <= 3, "mean/var over shards need the fused path or ndb_welford_axis + ndb_peer_allgather + ndb_welford_merge");
+            check(unsafe { ffi::ndb_reduce_axis(self.ctx.0, redop, 0, &shard.view(), &out.view(), 0.0) });
+            let n: usize = out.dim.size();
+            check(unsafe { ffi::ndb_peer_allreduce(self.ctx.0, redop, A::DTYPE, out.ptr as *const c_void, out.ptr as *mut c_void, n as i64) });
+        }
+        out
+    }
+}
+impl Drop for PeerGroup { fn drop(&mut self) { unsafe { ffi::ndb_peer_window_destroy(self.ctx.0); } } }
