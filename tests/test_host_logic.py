@@ -291,3 +291,27 @@ def test_collapse_axis():
     assert nd.lib().ndb_view_collapse_axis(C.byref(v), 0, 2) == 0
     assert (v.ptr, v.dim[0], v.dim[1]) == (1000 + 2 * 4 * 8, 1, 4)
     assert nd.lib().ndb_view_collapse_axis(C.byref(v), 1, 4) == _ffi.ERR_OOB
+
+
+def test_planner_combined_views_and_config5():
+    """Config 2 (iv): all three views in one Zip -> the tile kernel with a stride -2 staged producer; config 5: 2^32
+    elements stay one flat run with 64-bit extents; nine producers (tests/azip.rs:481) plan as one flat Zip."""
+    A = 1 << 20
+    n = 512
+    out = mk(A, np.float32, (n // 2, n, n), c_strides((n // 2, n, n)))
+    ys = mk(A, np.float32, (n // 2, n, n), (2 * n * n, n, 1))
+    rowb = mk(A, np.float32, (n // 2, n, n), (0, 0, 1))
+    # x.t() has strides (1, n, n*n); [::-2] on axis 0 -> stride -2 from the last element of the axis
+    xts = mk(A + (n - 1) * 4, np.float32, (n // 2, n, n), (-2, n, n * n))
+    st, pl = plan(nd.Op.MUL_ADD, out, ys, rowb, xts)
+    assert st == 0 and pl.kernel == 5 and pl.staged_mask == 0b1000
+    k = pl.tile_axis
+    assert pl.stride[3][k] == -2 and pl.stride[3][pl.ndim - 1] == n * n
+    big = mk(A, np.float32, (65536, 65536), (65536, 1))
+    st, pl = plan(nd.Op.MUL_ADD, big, big, big, big)
+    assert st == 0 and pl.kernel == 1 and pl.ndim == 1 and pl.dim[0] == 1 << 32
+    v = mk(A, np.int64, (7, 11), (11, 1))
+    st, pl = plan(17, *([v] * 9))  # ADD_N: out + 8 inputs
+    assert st == 0 and pl.kernel in (1, 2) and pl.dim[0] == 77
+    st, pl = plan(17, *([v] * 10))
+    assert st != 0  # more than 9 producers: ndarray's Zip stops at 9 too
