@@ -86,13 +86,66 @@ __global__ void __launch_bounds__(256) scan_lanes(ScanArgs a)
     }
 }
 
+// scan_lanes with 128-bit accesses: a thread scans one vector locally, the warp scans the 32 vector totals with shuffles,
+// so a 32*N-element step costs one shuffle scan instead of N of them (unit-stride, 16-byte aligned lanes).
+template <typename T, bool MUL>
+__global__ void __launch_bounds__(256) scan_lanes_vec(ScanArgs a)
+{
+    using V = Vec128<T>;
+    constexpr int N = V::N;
+    const int lane_id = threadIdx.x & 31;
+    const int64_t lane = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (lane >= a.n_lanes) return;
+    T *p = reinterpret_cast<T *>(a.base) + lane_offset(a, lane);
+    const T ident = MUL ? T(1) : T(0);
+    T carry = ident;
+    for (int64_t i0 = 0; i0 < a.n; i0 += 32 * N) {
+        const int64_t i = i0 + (int64_t)lane_id * N;
+        const bool whole = i + N <= a.n;
+        V v;
+        if (whole) {
+            v = *reinterpret_cast<const V *>(p + i);
+        } else {
+#pragma unroll
+            for (int e = 0; e < N; ++e) v.v[e] = (i + e < a.n) ? p[i + e] : ident;
+        }
+#pragma unroll
+        for (int e = 1; e < N; ++e) v.v[e] = comb<T, MUL>(v.v[e - 1], v.v[e]);
+        T inc = v.v[N - 1];
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const T up = __shfl_up_sync(0xffffffffu, inc, d);
+            if (lane_id >= d) inc = comb<T, MUL>(up, inc);
+        }
+        T excl = __shfl_up_sync(0xffffffffu, inc, 1);
+        if (lane_id == 0) excl = ident;
+        const T off = comb<T, MUL>(carry, excl);
+#pragma unroll
+        for (int e = 0; e < N; ++e) v.v[e] = comb<T, MUL>(off, v.v[e]);
+        if (whole) {
+            *reinterpret_cast<V *>(p + i) = v;
+        } else {
+#pragma unroll
+            for (int e = 0; e < N; ++e)
+                if (i + e < a.n) p[i + e] = v.v[e];
+        }
+        carry = comb<T, MUL>(carry, __shfl_sync(0xffffffffu, inc, 31));
+    }
+}
+
 template <typename T>
 int scan_dispatch(ndb_ctx *ctx, int op, const ScanArgs &a, bool lanes)
 {
     const bool mul = op == NDB_OP_MUL;
     if (lanes) {
         const unsigned blocks = (unsigned)((a.n_lanes + 7) / 8);
-        if (mul) scan_lanes<T, true><<<blocks, 256, 0, ctx->stream>>>(a);
+        constexpr int64_t VN = 16 / sizeof(T);
+        bool vec = a.s == 1 && ((uintptr_t)a.base % 16) == 0 && a.n >= 2 * VN && !getenv("NDB_SCAN_SCALAR");
+        for (int d = 0; d < a.n_kept && vec; ++d) vec = a.kdim[d] == 1 || a.kstride[d] % VN == 0;
+        if (vec) {
+            if (mul) scan_lanes_vec<T, true><<<blocks, 256, 0, ctx->stream>>>(a);
+            else scan_lanes_vec<T, false><<<blocks, 256, 0, ctx->stream>>>(a);
+        } else if (mul) scan_lanes<T, true><<<blocks, 256, 0, ctx->stream>>>(a);
         else scan_lanes<T, false><<<blocks, 256, 0, ctx->stream>>>(a);
     } else {
         const unsigned blocks = (unsigned)((a.n_lanes + 255) / 256);

@@ -388,3 +388,23 @@ def test_multi_gpu_protocol_under_torchrun():
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
                         "--master-port", "29577", str(root / "benchmarks" / "dist_check.py")], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and "dist_check ok on 2 GPUs" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.int32, np.float64])
+def test_accumulate_axis_vector_scan_with_ragged_tail(nd, dtype):
+    """The 128-bit warp scan (dense, 16-byte aligned lanes) on lanes whose length is not a multiple of the vector width:
+    rows of 136 elements sliced to 130, so every lane ends in a partial vector and the pad columns must stay untouched."""
+    from ndarray_b200 import Array, Op, s_
+    rng = np.random.default_rng(23)
+    base = (rng.integers(-3, 4, size=(8, 12, 136)) if np.dtype(dtype).kind == "i" else 1.0 + 0.01 * rng.standard_normal((8, 12, 136))).astype(dtype)
+    for op, ref in ((Op.ADD, np.cumsum), (Op.MUL, np.cumprod)):
+        d = Array.from_numpy(base)
+        d.slice(s_[:, :, :130]).accumulate_axis_inplace(2, op)
+        got = d.to_numpy()
+        assert np.array_equal(got[:, :, 130:], base[:, :, 130:])
+        want = ref(base[:, :, :130].astype(np.float64) if np.dtype(dtype).kind == "f" else base[:, :, :130], axis=2)
+        if np.dtype(dtype).kind == "i":
+            assert np.array_equal(got[:, :, :130], want.astype(dtype))
+        else:
+            tol = (1e-5 if dtype == np.float32 else 1e-12) * np.sqrt(130)
+            assert np.max(np.abs(got[:, :, :130] - want) / np.abs(want)) <= tol
