@@ -6,6 +6,8 @@
 //               neighbouring addresses, every step is coalesced.
 //   scan_lanes  the scanned axis is the dense one: a warp owns a lane and scans it 32 elements at a time with shuffles
 //               plus a running carry (coalesced; the association differs, so floats agree to rounding, integers exactly).
+#include <algorithm>
+
 #include "zip_kernels.cuh"
 #include "zip_plan.h"
 
@@ -86,6 +88,58 @@ __global__ void __launch_bounds__(256) scan_lanes(ScanArgs a)
     }
 }
 
+// ---- few lanes, long strided axis: chunk the scanned axis ---------------------------------------------------------
+// scan_cols gives one thread per lane; 8192 lanes of 8192 elements are 32 blocks on 148 SMs (0.86 TB/s).  Three small
+// kernels instead: per (chunk, lane) totals; an exclusive scan of the totals along the chunks (one thread per lane);
+// the local scans again with their carry-in.  The data is read twice, but by ~300 K threads.
+template <typename T, bool MUL>
+__global__ void __launch_bounds__(256) scan_chunk_totals(ScanArgs a, T *totals, int chunks, int64_t chunk_len)
+{
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= a.n_lanes * chunks) return;
+    const int64_t lane = idx % a.n_lanes, chunk = idx / a.n_lanes;  // neighbouring threads -> neighbouring lanes
+    const T *p = reinterpret_cast<const T *>(a.base) + lane_offset(a, lane);
+    const int64_t c0 = chunk * chunk_len, c1 = c0 + chunk_len < a.n ? c0 + chunk_len : a.n;
+    T acc = p[c0 * a.s];
+    for (int64_t i = c0 + 1; i < c1; ++i) acc = comb<T, MUL>(acc, p[i * a.s]);
+    totals[idx] = acc;
+}
+
+template <typename T, bool MUL>
+__global__ void __launch_bounds__(256) scan_chunk_carries(T *totals, int64_t n_lanes, int chunks)
+{
+    const int64_t lane = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (lane >= n_lanes) return;
+    T running = totals[lane];  // carry into chunk 1 = total of chunk 0; chunk 0 itself takes no carry
+    for (int c = 1; c < chunks; ++c) {
+        const T t = totals[(int64_t)c * n_lanes + lane];
+        totals[(int64_t)c * n_lanes + lane] = running;
+        running = comb<T, MUL>(running, t);
+    }
+}
+
+template <typename T, bool MUL>
+__global__ void __launch_bounds__(256) scan_chunk_apply(ScanArgs a, const T *carries, int chunks, int64_t chunk_len)
+{
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= a.n_lanes * chunks) return;
+    const int64_t lane = idx % a.n_lanes, chunk = idx / a.n_lanes;
+    T *p = reinterpret_cast<T *>(a.base) + lane_offset(a, lane);
+    const int64_t c0 = chunk * chunk_len, c1 = c0 + chunk_len < a.n ? c0 + chunk_len : a.n;
+    int64_t i = c0;
+    T acc;
+    if (chunk == 0) {
+        acc = p[0];  // the first element is left as it is (no identity is folded in: -0.0 stays -0.0)
+        i = 1;
+    } else {
+        acc = carries[idx];
+    }
+    for (; i < c1; ++i) {
+        acc = comb<T, MUL>(acc, p[i * a.s]);
+        p[i * a.s] = acc;
+    }
+}
+
 // scan_lanes with 128-bit accesses: a thread scans one vector locally, the warp scans the 32 vector totals with shuffles,
 // so a 32*N-element step costs one shuffle scan instead of N of them (unit-stride, 16-byte aligned lanes).
 template <typename T, bool MUL>
@@ -147,6 +201,25 @@ int scan_dispatch(ndb_ctx *ctx, int op, const ScanArgs &a, bool lanes)
             else scan_lanes_vec<T, false><<<blocks, 256, 0, ctx->stream>>>(a);
         } else if (mul) scan_lanes<T, true><<<blocks, 256, 0, ctx->stream>>>(a);
         else scan_lanes<T, false><<<blocks, 256, 0, ctx->stream>>>(a);
+    } else if (a.n >= 512 && a.n_lanes < (int64_t)ctx->sm_count * 512 && !getenv("NDB_SCAN_NO_CHUNKS")) {
+        const int64_t target = (int64_t)ctx->sm_count * 2048;  // threads that fill the machine
+        int chunks = (int)std::min<int64_t>((target + a.n_lanes - 1) / a.n_lanes, a.n / 64);
+        chunks = std::max(2, std::min(chunks, 4096));
+        const int64_t chunk_len = (a.n + chunks - 1) / chunks;
+        chunks = (int)((a.n + chunk_len - 1) / chunk_len);  // no empty chunk
+        NDB_TRY(ensure_workspace(ctx, (size_t)chunks * (size_t)a.n_lanes * sizeof(T)));
+        T *totals = reinterpret_cast<T *>(ctx->workspace);
+        const unsigned blocks = (unsigned)((a.n_lanes * chunks + 255) / 256);
+        const unsigned lane_blocks = (unsigned)((a.n_lanes + 255) / 256);
+        if (mul) {
+            scan_chunk_totals<T, true><<<blocks, 256, 0, ctx->stream>>>(a, totals, chunks, chunk_len);
+            scan_chunk_carries<T, true><<<lane_blocks, 256, 0, ctx->stream>>>(totals, a.n_lanes, chunks);
+            scan_chunk_apply<T, true><<<blocks, 256, 0, ctx->stream>>>(a, totals, chunks, chunk_len);
+        } else {
+            scan_chunk_totals<T, false><<<blocks, 256, 0, ctx->stream>>>(a, totals, chunks, chunk_len);
+            scan_chunk_carries<T, false><<<lane_blocks, 256, 0, ctx->stream>>>(totals, a.n_lanes, chunks);
+            scan_chunk_apply<T, false><<<blocks, 256, 0, ctx->stream>>>(a, totals, chunks, chunk_len);
+        }
     } else {
         const unsigned blocks = (unsigned)((a.n_lanes + 255) / 256);
         if (mul) scan_cols<T, true><<<blocks, 256, 0, ctx->stream>>>(a);

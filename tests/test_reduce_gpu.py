@@ -408,3 +408,39 @@ def test_accumulate_axis_vector_scan_with_ragged_tail(nd, dtype):
         else:
             tol = (1e-5 if dtype == np.float32 else 1e-12) * np.sqrt(130)
             assert np.max(np.abs(got[:, :, :130] - want) / np.abs(want)) <= tol
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32, np.int64])
+def test_accumulate_long_strided_axis_is_chunked(nd, dtype):
+    """Few lanes and a long strided axis (cumsum down the rows of a [4096, 96] matrix) take the chunked scan: per-chunk
+    totals, carries, local scans.  Integers exactly; floats within the reduction tolerance; a -0.0 first element keeps
+    its sign; a transposed view and a stepped axis use the same path."""
+    from ndarray_b200 import Array, Op, s_
+    rng = np.random.default_rng(29)
+    kind = np.dtype(dtype).kind
+    h = (rng.integers(-3, 4, size=(4096, 96)) if kind == "i" else 1.0 + 0.001 * rng.standard_normal((4096, 96))).astype(dtype)
+    if kind == "f":
+        h[0, :4] = -0.0
+    for op, ref in ((Op.ADD, np.cumsum), (Op.MUL, np.cumprod)):
+        d = Array.from_numpy(h)
+        d.accumulate_axis_inplace(0, op)
+        got = d.to_numpy()
+        want = ref(h.astype(np.float64) if kind == "f" else h, axis=0)
+        if kind == "i":
+            assert np.array_equal(got, want.astype(dtype))
+        else:
+            tol = (1e-5 if dtype == np.float32 else 1e-12) * np.sqrt(4096)
+            assert np.max(np.abs(got.astype(np.float64) - want) / np.maximum(np.abs(want), 1e-30)) <= tol
+            if op == Op.ADD:
+                assert np.all(np.signbit(got[0, :4]))
+    # stepped rows of a transposed view: lanes along axis 1 of h.T[:, ::3]
+    d = Array.from_numpy(h)
+    d.t().slice(s_[:, ::3]).accumulate_axis_inplace(1, Op.ADD)
+    got = d.to_numpy()
+    want = h.copy()
+    want[::3, :] = np.cumsum(h[::3, :].astype(np.float64) if kind == "f" else h[::3, :], axis=0).astype(dtype)
+    if kind == "i":
+        assert np.array_equal(got, want)
+    else:
+        g64, w64 = got.astype(np.float64), want.astype(np.float64)
+        assert np.max(np.abs(g64 - w64) / np.maximum(np.abs(w64), 1e-30)) <= (1e-5 if dtype == np.float32 else 1e-12) * np.sqrt(1366)
