@@ -1,18 +1,21 @@
 #!/usr/bin/env python
 """bench.py — headline measurement of the ndarray hot path on B200.
 
-Workload (`config.workload`): BASELINE.json configs[1] — f32 512x512x512 non-contiguous views through Zip:
-  (i)   out = x.t() + y                                   transposed operand   (1 610 612 736 algorithmic bytes)
-  (ii)  half = x.slice(s![..;-2,..,..]) + y.slice(s![..;2,..,..])  negative step (805 306 368 B)
-  (iii) out = x * row.broadcast((512,512,512))            stride-0 operand     (1 073 743 872 B)
-One step = the three Zips once.  metric = algorithmic bytes moved per second (GB/s): every distinct
-element read or written counts once.  Arrays are 512 MiB each, far beyond the 126 MB L2.
+Workload (`config.workload`): BASELINE.json configs[4], the one config with an exchange in it — f32 [65536, 65536]
+(2^32 elements, 16 GiB per array) `Zip::from(&mut a).and(&b).and(&c).for_each(|a, &b, &c| *a = b * c + *a)` followed by the
+global `a.sum()`.  The total size is FIXED (strong scaling): with N ranks each owns 65536/N rows (Zip::split's partition,
+reference src/zip/mod.rs:811-815, src/impl_raw_views.rs:113-135; the parallel sum is the reference's
+`axis_iter(Axis(0)).into_par_iter().map(|x| x.sum()).sum()`, tests/par_rayon.rs:12-24).  The elementwise part needs no
+communication; the sum ends in a one-element exchange that is INSIDE the timed step: by default fused into the kernel that
+finishes the local reduction tree (peer windows over NVLink, csrc/peer.cu), with NCCL's all-reduce timed as the A/B.
+N = 1 runs the whole 2^32 problem on one GPU (48 GiB resident).
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--no-extras]
+One step = the Zip once + the global sum once.  metric = algorithmic bytes per second:
+4 streams x 4 B x 2^32 (elementwise) + 4 B x 2^32 (sum) = 85 899 345 920 B per step, whatever N is.
 
-N > 1 (launched under torchrun): each rank runs the same step on its own shard (weak scaling; Zip needs no
-exchange), times are max-reduced over ranks, rank 0 prints the line.  `--impl reference` times the CPU
-restatement of ndarray (oracle/, all host threads) on the same config.
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--no-extras] [--no-cpu] [--rows R]
+
+`--impl reference` times the CPU restatement of ndarray (oracle/, all host cores) on a bounded sample of the same workload.
 """
 from __future__ import annotations
 
@@ -21,7 +24,6 @@ import ctypes as C
 import json
 import os
 import statistics
-import subprocess
 import sys
 import threading
 import time
@@ -32,14 +34,29 @@ import numpy as np
 ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 
-N3 = 512
-BYTES_I = 3 * N3 ** 3 * 4
-BYTES_II = 3 * (N3 // 2) * N3 * N3 * 4
-BYTES_III = 2 * N3 ** 3 * 4 + N3 * 4
-STEP_BYTES = BYTES_I + BYTES_II + BYTES_III
-METRIC = "zip_views_hbm_gbps"
+ROWS = 65536
+COLS = 65536
+SEED_A, SEED_B, SEED_C = 0x5EED0001, 0x5EED0002, 0x5EED0003
+METRIC = "zip_global_sum_hbm_gbps"
 UNIT = "GB/s"
-WORKLOAD = "C2: f32 512^3 Zip over views — x.t()+y, s![..;-2]+s![..;2], x*row.broadcast"
+OP_MUL_ADD, RED_SUM = 7, 0
+F32_TOL = 1e-5  # north star: float reductions agree within 1e-5 (f32) x sqrt(n), relative to the mean magnitude
+
+
+def workload_name(rows):
+    return (f"C5: f32 [{rows}, {COLS}] a = b*c + a (Zip, in place) + global a.sum(), rows sharded over the ranks, "
+            "one-element exchange inside the step")
+
+
+def step_bytes(rows):
+    return 20 * rows * COLS
+
+
+def config_dict(rows):
+    """Identical in both arms (ours and --impl reference) so the driver can match them."""
+    return {"workload": workload_name(rows), "shape": [rows, COLS], "bytes_per_step": step_bytes(rows),
+            "sharding": "Axis(0) split_at, rows/N per rank, total size fixed (strong scaling)",
+            "l2": "every array is 16 GiB/N >= 2 GiB per rank, far beyond the 126 MB L2: no flush needed"}
 
 
 def peaks():
@@ -51,8 +68,7 @@ def peaks():
 
 
 class ClockSampler:
-    """SM clock and throttle reasons sampled through NVML DURING the timed region (a polling thread, ~1 kHz;
-    nvidia-smi's 100 ms loop would miss a region that lasts tens of milliseconds)."""
+    """SM clock and throttle reasons sampled through NVML DURING the timed region (a polling thread, ~1 kHz)."""
 
     def __init__(self, device: int):
         self.device = device
@@ -64,8 +80,7 @@ class ClockSampler:
         self.err = None
 
     def _run(self, nv, h):
-        bits = {"hw_slowdown": nv.nvmlClocksEventReasonHwSlowdown if hasattr(nv, "nvmlClocksEventReasonHwSlowdown") else 0x8,
-                "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
+        bits = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
         while not self.stop_flag.is_set():
             try:
                 self.samples.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
@@ -103,93 +118,115 @@ class ClockSampler:
         return out
 
 
-# -------------------------------------------------------------------------------------------------
-def host_inputs(n, seed):
-    rng = np.random.default_rng(seed)
-    x = rng.random((n, n, n), dtype=np.float32) * 2 - 1
-    y = rng.random((n, n, n), dtype=np.float32) * 2 - 1
-    row = rng.random(n, dtype=np.float32) * 2 - 1
-    return x, y, row
+# ---- CPU arm: the oracle port of ndarray on the host cores ---------------------------------------------------------
+class CpuSample:
+    """A bounded sample of the workload on the host: f32 [rows, 65536] a = b*c + a with ndarray's Zip traversal split
+    over the host threads like rayon's par_for_each, then the parallel row-sum idiom of tests/par_rayon.rs:19."""
+
+    def __init__(self, rows, threads):
+        from oracle import oracle as orc
+        orc.build()
+        self.orc, self.rows, self.threads = orc, rows, threads
+        self.a, self.b, self.c = (np.empty((rows, COLS), np.float32) for _ in range(3))
+        for arr, seed in ((self.a, SEED_A), (self.b, SEED_B), (self.c, SEED_C)):
+            orc.counter_fill(arr, seed, 0, threads)
+        self.total = None
+
+    def step(self):
+        assert self.orc.zip_(OP_MUL_ADD, self.a, [self.b, self.c, self.a], threads=self.threads) == 0
+        self.total = self.orc.par_row_sum(self.a, self.threads)
+
+    def describe(self, passes, dt):
+        return (f"f32 [{self.rows}, {COLS}] (1/{ROWS // self.rows} of the workload) a=b*c+a + parallel row-sum, {passes} passes in "
+                f"{dt:.1f} s, oracle/ndarray_oracle.cpp (port of ndarray's Zip traversal and unrolled_fold) with OpenMP over Zip::split's axis")
 
 
-def step_bytes(n):
-    return 3 * n ** 3 * 4 + 3 * (n // 2) * n * n * 4 + 2 * n ** 3 * 4 + n * 4
+def all_host_cpus():
+    try:
+        return set(range(os.cpu_count() or 1))
+    except Exception:
+        return None
+
+
+def with_all_cores(fn):
+    """Run fn with this process allowed on every host CPU (ranks are otherwise pinned near their GPU)."""
+    try:
+        saved = os.sched_getaffinity(0)
+        try:
+            os.sched_setaffinity(0, all_host_cpus())
+        except Exception:
+            pass
+    except AttributeError:
+        saved = None
+    try:
+        return fn()
+    finally:
+        if saved is not None:
+            try:
+                os.sched_setaffinity(0, saved)
+            except Exception:
+                pass
 
 
 def run_reference(args, rank, world):
-    """The reference arm: ndarray's algorithm on the host cores (the oracle port; ndarray itself is Rust and
-    the image has no rustc/cargo — DESIGN.md)."""
+    """The reference arm: ndarray's algorithm on the host cores (the oracle port; ndarray itself is Rust and the image has
+    no rustc/cargo — DESIGN.md).  Under torchrun only rank 0 runs; the thread count comes from the CPUs the process may
+    run on, not from OMP_NUM_THREADS (torchrun exports 1)."""
     if rank != 0:
         return
-    from oracle import oracle as orc
-    orc.build()
-    threads = orc.max_threads()
-    OP_ADD, OP_MUL = 2, 4
-    # size the sample so one step takes a few seconds at most
-    n = N3
-    xs, ys, rs = host_inputs(128, 1)
-    o = np.empty_like(xs)
-    t0 = time.perf_counter()
-    orc.zip_(OP_ADD, o, [xs.transpose(2, 1, 0), ys], threads=threads)
-    t_small = time.perf_counter() - t0
-    est = t_small * (N3 / 128) ** 3 * 2.2  # three cases ~ 2.2x the transposed one
-    total_steps = args.steps + args.warmup
-    while n > 128 and est * (n / N3) ** 3 * total_steps > 150.0:
-        n //= 2
-    x, y, row = host_inputs(n, 2)
-    out = np.empty((n, n, n), np.float32)
-    half = np.empty((n // 2, n, n), np.float32)
-    rowb = np.broadcast_to(row, (n, n, n))
 
-    def step():
-        assert orc.zip_(OP_ADD, out, [x.transpose(2, 1, 0), y], threads=threads) == 0
-        assert orc.zip_(OP_ADD, half, [x[::-1][::2], y[::2]], threads=threads) == 0
-        assert orc.zip_(OP_MUL, out, [x, rowb], threads=threads) == 0
+    def run():
+        from oracle import oracle as orc
+        orc.build()
+        threads = orc.max_threads()
+        total_steps = args.steps + args.warmup
+        # calibrate on 512 rows, then size the sample so the whole run stays near two minutes
+        probe = CpuSample(512, threads)
+        probe.step()
+        t0 = time.perf_counter()
+        probe.step()
+        per_row = (time.perf_counter() - t0) / 512
+        rows = 8192
+        while rows > 512 and per_row * rows * total_steps > 120.0:
+            rows //= 2
+        del probe
+        s = CpuSample(rows, threads)
+        for _ in range(args.warmup):
+            s.step()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            s.step()
+        dt = time.perf_counter() - t0
+        val = step_bytes(rows) * args.steps / dt / 1e9
+        line = {
+            "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config_dict(args.rows),
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port", "sample": s.describe(args.steps, dt)},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0,
+        }
+        print(json.dumps(line), flush=True)
 
-    for _ in range(args.warmup):
-        step()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        step()
-    dt = time.perf_counter() - t0
-    val = step_bytes(n) * args.steps / dt / 1e9
-    sample = f"f32 {n}^3 (same three Zips), {args.steps} steps, oracle port of ndarray's Zip traversal, OpenMP static split along Zip::split's axis"
-    line = {
-        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "sample_n": n},
-        "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
-        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "gpu_launches": 0,
-    }
-    print(json.dumps(line), flush=True)
+    with_all_cores(run)
 
 
-def cpu_baseline_sample(budget_s=20.0):
-    from oracle import oracle as orc
-    orc.build()
-    threads = orc.max_threads()
-    n = N3  # the bench workload itself (512^3), fewer passes: a smaller cube would sit in the CPU's last-level cache
-    x, y, row = host_inputs(n, 3)
-    out = np.empty((n, n, n), np.float32)
-    half = np.empty((n // 2, n, n), np.float32)
-    rowb = np.broadcast_to(row, (n, n, n))
+def cpu_baseline_sample(budget_s=16.0):
+    def run():
+        from oracle import oracle as orc
+        orc.build()
+        threads = orc.max_threads()
+        s = CpuSample(8192, threads)  # one 8-GPU shard: 2 GiB per array, well beyond the CPU's last-level cache
+        s.step()
+        t0 = time.perf_counter()
+        reps = 0
+        while reps < 3 or (time.perf_counter() - t0 < budget_s and reps < 100):
+            s.step()
+            reps += 1
+        dt = time.perf_counter() - t0
+        return {"value": step_bytes(8192) * reps / dt / 1e9, "unit": UNIT, "cores": threads, "kind": "port", "sample": s.describe(reps, dt)}
 
-    def step():
-        orc.zip_(2, out, [x.transpose(2, 1, 0), y], threads=threads)
-        orc.zip_(2, half, [x[::-1][::2], y[::2]], threads=threads)
-        orc.zip_(4, out, [x, rowb], threads=threads)
-
-    step()
-    t0 = time.perf_counter()
-    reps = 0
-    while reps < 3 or (time.perf_counter() - t0 < budget_s / 2 and reps < 60):
-        step()
-        reps += 1
-    dt = time.perf_counter() - t0
-    return {"value": step_bytes(n) * reps / dt / 1e9, "unit": UNIT, "cores": threads, "kind": "port",
-            "sample": f"f32 {n}^3 views (same three Zips), {reps} passes in {dt:.1f} s, oracle/ndarray_oracle.cpp with OpenMP"}
+    return with_all_cores(run)
 
 
 def bind_to_gpu_numa_node(local: int) -> None:
@@ -216,11 +253,14 @@ def bind_to_gpu_numa_node(local: int) -> None:
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours")
+    ap.add_argument("--rows", type=int, default=ROWS, help="rows of the [rows, 65536] problem (default: the full 2^32 elements)")
+    ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"], help="how the global sum crosses the GPUs in the headline")
     ap.add_argument("--no-extras", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     rank = int(os.environ.get("RANK", "0"))
@@ -233,8 +273,9 @@ def main():
 
     import torch
     import ndarray_b200 as nd
-    from ndarray_b200 import Array, Zip, s_, Op, Axis
+    from ndarray_b200 import Array, Zip, parallel as par
     from ndarray_b200._ffi import View, lib, check
+    from ndarray_b200.array import Red
 
     bind_to_gpu_numa_node(local)  # pinned staging buffers should live on the socket the GPU hangs off
     dist = None
@@ -245,6 +286,10 @@ def main():
     os.environ.setdefault("NDB_DEVICE", str(local))
     ctx = nd.Context(local)
     L = lib()
+    dev = torch.device("cuda", local)
+    rows_total = args.rows
+    n_total = rows_total * COLS
+    STEP_BYTES = step_bytes(rows_total)
 
     def barrier():
         if dist is not None:
@@ -252,140 +297,206 @@ def main():
         torch.cuda.synchronize(local)
         ctx.sync()
 
-    # ---- inputs resident in HBM ---------------------------------------------------------------
-    n = N3
-    xh, yh, rowh = host_inputs(n, 100 + rank)
-    x, y, row = Array.from_numpy(xh, ctx), Array.from_numpy(yh, ctx), Array.from_numpy(rowh, ctx)
-    out = Array.uninit((n, n, n), np.float32, ctx=ctx)
-    half = out.slice(s_[: n // 2, :, :])
-    xt, xs, ys_, rowb = x.t(), x.slice(s_[::-2, :, :]), y.slice(s_[::2, :, :]), row.broadcast((n, n, n))
-    z1 = Zip.from_(out).and_(xt).and_(y)
-    z2 = Zip.from_(half).and_(xs).and_(ys_)
-    z3 = Zip.from_(out).and_(x).and_(rowb)
-    kernels = [nd.KERNEL_NAMES[z.plan(op).kernel] for z, op in ((z1, Op.ADD), (z2, Op.ADD), (z3, Op.MUL))]
+    def max_over_ranks(x):
+        if dist is None:
+            return float(x)
+        t = torch.tensor([x], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
 
-    def step():
-        z1.for_each("a=b+c")
-        z2.for_each("a=b+c")
-        z3.for_each("a=b*c")
+    # ---- this rank's rows, resident in HBM, filled from the index-addressable generator ---------------
+    lo, hi = par.shard_bounds(rows_total, rank, world)
+    rows = hi - lo
+    a, b, c = (Array.uninit((rows, COLS), np.float32, ctx=ctx) for _ in range(3))
+    acc = Array.zeros((), np.float32, ctx=ctx)
 
+    def fill():
+        for arr, seed in ((a, SEED_A), (b, SEED_B), (c, SEED_C)):
+            check(L.ndb_fill_counter_rng(ctx.handle, C.byref(arr.v), seed, lo * COLS))
+
+    peers, peer_err = None, None
+    if world > 1:
+        try:
+            peers = par.PeerGroup(ctx, dist, slot_bytes=1 << 20)  # raises on ALL ranks or on none
+        except Exception as e:  # noqa: BLE001
+            peer_err = repr(e)
+    exchange = "none (1 rank)" if world == 1 else ("peer" if (peers is not None and args.exchange == "peer") else "nccl")
+    stream = torch.cuda.ExternalStream(ctx.stream_ptr(), device=dev)
+    acc_t = par._torch_view(acc)
+    z = Zip.from_(a).and_(b).and_(c)
+
+    def sum_step(mode):
+        if mode == "peer":
+            check(L.ndb_reduce_all_peer(ctx.handle, Red.SUM, C.byref(a.v), C.c_void_p(acc.v.ptr)))
+        else:
+            check(L.ndb_reduce_all_dev(ctx.handle, Red.SUM, C.byref(a.v), C.c_void_p(acc.v.ptr)))
+            if mode == "nccl":
+                with torch.cuda.stream(stream):
+                    dist.all_reduce(acc_t)
+
+    def step(mode=exchange):
+        z.for_each("a=b*c+a")
+        sum_step(mode)
+
+    # ---- parity, from fresh data, before anything is timed ------------------------------------------------
+    from oracle import oracle as orc  # the checker (test infrastructure), never on the timed path
+    orc.build()
+
+    def oracle_rows(sample_rows):
+        """a' = b*c + a for the given GLOBAL row numbers, recomputed on the host by the oracle's Zip."""
+        out = {}
+        for r in sample_rows:
+            ra, rb, rc = (orc.counter_fill(np.empty(COLS, np.float32), s, r * COLS) for s in (SEED_A, SEED_B, SEED_C))
+            assert orc.zip_(OP_MUL_ADD, ra, [rb, rc, ra]) == 0
+            out[r] = ra
+        return out
+
+    sample = sorted({lo, hi - 1, lo + (rows * 5) // 13, lo + (rows * 11) // 17}) if rows > 0 else []
+    want_rows = oracle_rows(sample)
+    fill()
+    step()
+    got_sum = float(acc.to_numpy()[()])
+    rows_ok = all(np.array_equal(a.index_axis(0, r - lo).to_numpy(), want_rows[r]) for r in sample)
+    parity = {"elementwise_rows_checked_per_rank": len(sample), "elementwise": "bit-exact"}
+    if world > 1:
+        # the other exchange must give the same total up to the order of N additions
+        fill()
+        step("nccl" if exchange == "peer" else ("peer" if peers is not None else "nccl"))
+        other_sum = float(acc.to_numpy()[()])
+        flags = [None] * world
+        dist.all_gather_object(flags, bool(rows_ok))
+        rows_ok = all(flags)
+        parity["sum_other_exchange"] = other_sum
+    if not rows_ok:
+        parity["elementwise"] = "MISMATCH"
+    if rank == 0:
+        ref_sum, ref_abs, ref_nd = with_all_cores(lambda: orc.c5_sums(SEED_A, SEED_B, SEED_C, 0, n_total, orc.max_threads(), world == 1))
+        tol = F32_TOL * np.sqrt(n_total) * (ref_abs / n_total)
+        parity.update({"sum": got_sum, "sum_f64_oracle": ref_sum, "sum_abs_err": abs(got_sum - ref_sum), "sum_tolerance": tol,
+                       "sum_tolerance_rule": "1e-5 * sqrt(n) * mean|x| (north star: f32 reductions to 1e-5 relative, scaled by sqrt(n))",
+                       "sum_ok": bool(abs(got_sum - ref_sum) <= tol)})
+        if ref_nd is not None:
+            parity["ndarray_order_f32_sum"] = float(ref_nd)
+            parity["ndarray_order_f32_sum_abs_err"] = abs(float(ref_nd) - ref_sum)
+        if world > 1:
+            parity["sum_other_exchange_ok"] = bool(abs(parity["sum_other_exchange"] - ref_sum) <= tol)
+    dist_parity = "n/a (1 rank)"
+    if world > 1:
+        from benchmarks.dist_check import run_checks
+        n_checks, fails = run_checks(ctx, dist, rank, world, gemm=True, peers=peers)
+        dist_parity = "ok" if not fails else "FAILED: " + "; ".join(fails[:5])
+        parity["dist_checks"] = n_checks
+    parity_ok = rows_ok and (rank != 0 or (parity.get("sum_ok") and parity.get("sum_other_exchange_ok", True))) and not dist_parity.startswith("FAILED")
+
+    # ---- the timed region ------------------------------------------------------------------------------
+    fill()
     for _ in range(args.warmup):
         step()
     barrier()
-    # timed region: events on the stream the kernels are launched on; per-kernel events ride along
-    evs = [[ctx.event() for _ in range(4)] for _ in range(args.steps)]
+    evs = [[ctx.event() for _ in range(3)] for _ in range(args.steps)]
     clocks = ClockSampler(local)
     clocks.start()
     launches0 = L.ndb_launch_count()
     barrier()
     for k in range(args.steps):
         ctx.record(evs[k][0])
-        z1.for_each("a=b+c")
+        z.for_each("a=b*c+a")
         ctx.record(evs[k][1])
-        z2.for_each("a=b+c")
+        sum_step(exchange)
         ctx.record(evs[k][2])
-        z3.for_each("a=b*c")
-        ctx.record(evs[k][3])
     barrier()
     launches = L.ndb_launch_count() - launches0
     clk = clocks.stop()
-    total_ms = ctx.elapsed_ms(evs[0][0], evs[-1][3])
-    per_kernel_ms = [statistics.mean(ctx.elapsed_ms(evs[k][j], evs[k][j + 1]) for k in range(args.steps)) for j in range(3)]
-    if dist is not None:
-        t = torch.tensor([total_ms], device=f"cuda:{local}", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        total_ms = float(t.item())
-    value = STEP_BYTES * args.steps * world / (total_ms * 1e-3) / 1e9
+    total_ms = max_over_ranks(ctx.elapsed_ms(evs[0][0], evs[-1][2]))
+    zip_ms = statistics.mean(ctx.elapsed_ms(e[0], e[1]) for e in evs)
+    sum_ms = statistics.mean(ctx.elapsed_ms(e[1], e[2]) for e in evs)
+    zip_ms_max, sum_ms_max = max_over_ranks(zip_ms), max_over_ranks(sum_ms)
+    value = STEP_BYTES * args.steps / (total_ms * 1e-3) / 1e9
 
-    # ---- roofline of the dominant kernel ----------------------------------------------------------
+    # ---- what limits scaling: the A/B exchange, and the exchange alone ---------------------------------
+    breakdown = {"zip_ms": zip_ms_max, "sum_with_exchange_ms": sum_ms_max, "exchange": exchange,
+                 "ideal_ms_per_step_at_measured_peak": STEP_BYTES / world / (peaks()[0] * 1e9) * 1e3}
+    if peer_err:
+        breakdown["peer_windows_error"] = peer_err
+    if world > 1:
+        ab_steps = min(args.steps, 20)
+        for mode in ["nccl"] + (["peer"] if peers is not None else []):
+            for _ in range(3):
+                step(mode)
+            barrier()
+            e0, e1 = ctx.event(), ctx.event()
+            ctx.record(e0)
+            for _ in range(ab_steps):
+                step(mode)
+            ctx.record(e1)
+            barrier()
+            breakdown[f"ms_per_step_{mode}_exchange"] = max_over_ranks(ctx.elapsed_ms(e0, e1)) / ab_steps
+
+        def lat(fn, iters=100):
+            for _ in range(10):
+                fn()
+            barrier()
+            e0, e1 = ctx.event(), ctx.event()
+            ctx.record(e0)
+            for _ in range(iters):
+                fn()
+            ctx.record(e1)
+            barrier()
+            return max_over_ranks(ctx.elapsed_ms(e0, e1)) / iters * 1e3
+
+        def nccl_one():
+            with torch.cuda.stream(stream):
+                dist.all_reduce(acc_t)
+
+        breakdown["exchange_alone_us_nccl_1elt"] = lat(nccl_one)
+        if peers is not None:
+            breakdown["exchange_alone_us_peer_1elt"] = lat(lambda: peers.allreduce_(acc))
+        # local reduction without any exchange, for the difference
+        breakdown["sum_local_only_ms"] = lat(lambda: sum_step("local"), 20) / 1e3
+
+    # ---- roofline of the dominant kernel -------------------------------------------------------------
     peak, peak_src = peaks()
-    case_bytes = [BYTES_I, BYTES_II, BYTES_III]
-    dom = int(np.argmax(per_kernel_ms))
-    achieved = case_bytes[dom] / (per_kernel_ms[dom] * 1e-3) / 1e9
+    zip_bytes = 16 * rows * COLS
+    sum_bytes = 4 * rows * COLS
+    achieved = zip_bytes / (zip_ms * 1e-3) / 1e9
     traffic = None
     tf = ROOT / "profiles" / "traffic.json"
     if tf.exists():
         try:
-            traffic = json.loads(tf.read_text()).get(["zip_tile", "zip_rows", "zip_rows"][dom])
+            t = json.loads(tf.read_text()).get("zip_flat_c5_per_element_bytes")
+            traffic = t * rows * COLS if t else None
         except Exception:
             traffic = None
-    roofline = {"bound": "hbm", "kernel": ["zip_tile<f32,ADD> (x.t()+y)", "zip_rows<f32,ADD,VEC> (s![..;-2])",
-                                           "zip_rows<f32,MUL,VEC> (broadcast row)"][dom],
-                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                "peak_source": peak_src,
-                "per_case": {nm: {"ms": per_kernel_ms[j], "GB/s": case_bytes[j] / (per_kernel_ms[j] * 1e-3) / 1e9,
-                                  "kernel_class": kernels[j]}
-                             for j, nm in enumerate(["transposed", "neg_step", "broadcast_row"])}}
-
-    # ---- end to end through the host-buffer C-ABI call ---------------------------------------------
-    def pinned(arr):
-        p = C.c_void_p()
-        check(L.ndb_host_alloc(arr.nbytes, C.byref(p)))
-        buf = np.ctypeslib.as_array((C.c_byte * arr.nbytes).from_address(p.value)).view(arr.dtype).reshape(arr.shape)
-        buf[...] = arr
-        return buf
-
-    hx, hy, hrow = pinned(xh), pinned(yh), pinned(rowh)
-    hout = pinned(np.zeros((n, n, n), np.float32))
-
-    def hview(a, shape=None, strides=None, offset=0):
-        v = View()
-        shape = a.shape if shape is None else shape
-        strides = [s // 4 for s in a.strides] if strides is None else strides
-        v.ptr = a.ctypes.data + offset * 4
-        v.ndim = len(shape)
-        v.dtype = 0
-        for i, (d, s) in enumerate(zip(shape, strides)):
-            v.dim[i] = d
-            v.stride[i] = s
-        return v
-
-    nn = n * n
-    e2e_parts = [
-        (Op.ADD, (View * 3)(hview(hout), hview(hx, (n, n, n), (1, n, nn)), hview(hy))),
-        (Op.ADD, (View * 3)(hview(hout, (n // 2, n, n)), hview(hx, (n // 2, n, n), (-2 * nn, n, 1), (n - 1) * nn),
-                            hview(hy, (n // 2, n, n), (2 * nn, n, 1)))),
-        (Op.MUL, (View * 3)(hview(hout), hview(hx), hview(hrow, (n, n, n), (0, 0, 1)))),
-    ]
-    h2d = (2 * n ** 3 * 4) + (2 * (n // 2) * nn * 4) + (n ** 3 * 4 + n * 4)
-    d2h = n ** 3 * 4 + (n // 2) * nn * 4 + n ** 3 * 4
-
-    def e2e_step():
-        for op, parts in e2e_parts:
-            check(L.ndb_zip_host(ctx.handle, op, None, 3, parts))
-
-    e2e_steps = max(2, min(args.steps, 5))
-    e2e_step()
-    barrier()
-    es, ee = ctx.event(), ctx.event()
-    ctx.record(es)
-    for _ in range(e2e_steps):
-        e2e_step()
-    ctx.record(ee)
-    barrier()
-    e2e_ms = ctx.elapsed_ms(es, ee)
-    if dist is not None:
-        t = torch.tensor([e2e_ms], device=f"cuda:{local}", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_ms = float(t.item())
-    e2e_val = STEP_BYTES * e2e_steps * world / (e2e_ms * 1e-3) / 1e9
-    # the e2e result must equal the device result for case (iii), which ran last on both paths
-    e2e_ok = bool(np.array_equal(hout[5], out.index_axis(0, 5).to_numpy()))
+    roofline = {"bound": "hbm", "kernel": "zip_flat_vec<f32, MUL_ADD> (a = b*c + a over this rank's rows)", "achieved": achieved, "peak": peak,
+                "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": zip_bytes, "ms_per_launch": zip_ms,
+                "other_kernels": {"red_all_flat<f32, SUM> + finish (+ exchange)": {"ms": sum_ms, "GB/s": sum_bytes / (sum_ms * 1e-3) / 1e9,
+                                                                                  "frac": sum_bytes / (sum_ms * 1e-3) / 1e9 / peak}}}
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "shape": [n, n, n], "bytes_per_step": STEP_BYTES, "per_gpu_shard": "one 512^3 problem per rank",
-                   "l2": "inputs 512 MiB each >> 126 MB L2, no flush needed", "kernel_classes": kernels},
-        "clocks": clk, "gpu_launches": int(launches),
-        "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
-                "ms_per_step": e2e_ms / e2e_steps, "api": "ndb_zip_host (pinned host buffers, chunked H2D/kernel/D2H overlap)",
-                "matches_device_path": e2e_ok},
-        "roofline": roofline,
+        "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic", "config": config_dict(rows_total),
+        "clocks": clk, "gpu_launches": int(launches), "dist_parity": dist_parity, "parity": parity, "parity_ok": bool(parity_ok),
+        "roofline": roofline, "scaling_breakdown": breakdown,
     }
-    if rank == 0 and world == 1 and not args.no_cpu:
+
+    # ---- end to end through the host-buffer C-ABI call -----------------------------------------------------
+    if not args.no_e2e:
+        try:
+            line["e2e"] = run_e2e(ctx, L, torch, dist, dev, a, b, c, fill, rows, lo, world, rank, STEP_BYTES, n_total, want_rows, sample,
+                                  parity, barrier, max_over_ranks, View, check)
+        except Exception as e:  # noqa: BLE001
+            line["e2e"] = {"error": repr(e)}
+    del a, b, c, z
+    if peers is not None:
+        ctx.sync()
+        dist.barrier()
+        peers.close()
+    if rank == 0 and not args.no_cpu:
         line["cpu_baseline"] = cpu_baseline_sample()
+    if dist is not None:
+        dist.barrier()
     if not args.no_extras:
         try:
             from benchmarks.extras import run_extras
@@ -396,6 +507,75 @@ def main():
         print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()
+
+
+def run_e2e(ctx, L, torch, dist, dev, a, b, c, fill, rows, lo, world, rank, STEP_BYTES, n_total, want_rows, sample, parity, barrier,
+            max_over_ranks, View, check):
+    """The same step through ndb_zip_host_fold: HOST buffers in, a' and the sum back in host memory; every step moves
+    this rank's a, b, c over PCIe to the GPU and a' back (chunked, copies in both directions overlapped with the kernels)."""
+    shard_bytes = rows * COLS * 4
+
+    def pinned():
+        p = C.c_void_p()
+        check(L.ndb_host_alloc(max(shard_bytes, 16), C.byref(p)))
+        return p
+
+    t0 = time.perf_counter()
+    hp = [pinned() for _ in range(3)]
+    alloc_s = time.perf_counter() - t0
+    fill()
+    for p, arr in zip(hp, (a, b, c)):
+        check(L.ndb_d2h(ctx.handle, p, C.c_void_p(arr.v.ptr), shard_bytes))
+    ctx.sync()
+
+    def hview(p):
+        v = View()
+        v.ptr = p.value
+        v.ndim, v.dtype = 2, 0
+        v.dim[0], v.dim[1] = rows, COLS
+        v.stride[0], v.stride[1] = COLS, 1
+        return v
+
+    parts = (View * 4)(hview(hp[0]), hview(hp[1]), hview(hp[2]), hview(hp[0]))
+    res = C.c_float()
+    tot = torch.zeros(1, device=dev, dtype=torch.float32)
+
+    def e2e_step():
+        check(L.ndb_zip_host_fold(ctx.handle, OP_MUL_ADD, None, 4, parts, RED_SUM, C.byref(res)))
+        if dist is not None:
+            tot.fill_(res.value)
+            dist.all_reduce(tot)
+            return float(tot.item())
+        return float(res.value)
+
+    barrier()
+    got = e2e_step()  # warm-up from fresh data: also the parity check of this path
+    host_a = np.ctypeslib.as_array((C.c_float * (rows * COLS)).from_address(hp[0].value)).reshape(rows, COLS) if rows else None
+    rows_ok = all(np.array_equal(host_a[r - lo], want_rows[r]) for r in sample)
+    if dist is not None:
+        flags = [None] * world
+        dist.all_gather_object(flags, bool(rows_ok))
+        rows_ok = all(flags)
+    sum_ok = None
+    if rank == 0 and "sum_f64_oracle" in parity:
+        sum_ok = bool(abs(got - parity["sum_f64_oracle"]) <= parity["sum_tolerance"])
+    e2e_steps = 2
+    barrier()
+    es, ee = ctx.event(), ctx.event()
+    ctx.record(es)
+    for _ in range(e2e_steps):
+        e2e_step()
+    ctx.record(ee)
+    barrier()
+    e2e_ms = max_over_ranks(ctx.elapsed_ms(es, ee))
+    for p in hp:
+        L.ndb_host_free(p)
+    return {"value": STEP_BYTES * e2e_steps / (e2e_ms * 1e-3) / 1e9, "unit": UNIT,
+            "h2d_bytes_per_step": 3 * n_total * 4, "d2h_bytes_per_step": n_total * 4 + 4 * world, "bytes_are": "whole job (all ranks)",
+            "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps,
+            "api": "ndb_zip_host_fold(MUL_ADD, (a; b, c, a), SUM) on pinned host buffers: chunked H2D / kernel / D2H overlap, per-slab sums on the device"
+                   + ("" if dist is None else ", then an all-reduce of the per-rank scalars"),
+            "rows_match_oracle": bool(rows_ok), "sum_within_tolerance": sum_ok, "sum": got, "pinned_alloc_s": alloc_s}
 
 
 if __name__ == "__main__":

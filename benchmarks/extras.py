@@ -3,7 +3,7 @@
 C1  f32 4096^2 contiguous  a = b*c + a  and sum_axis (buffers rotated so the 64 MiB arrays do not sit in L2)
 C3  16384^2 f64 sum/mean/var_axis and i64 sum_axis / fold_axis(min), both axes
 C4  general_mat_mul f64 / f32 at 8192^3 (C- and F-order operands)
-C5  (N > 1) per-rank f32 elementwise + global sum() finished by an NCCL all-reduce
+C3  (N > 1) strong-scaled sharded sum_axis/var_axis(Axis(0)): NCCL vs peer windows vs the fused one-launch kernel
 C4  (N > 1) row-sharded general_mat_mul with B broadcast over NCCL, one shot and pipelined in 8 row blocks
 All timed with CUDA events on the context stream after warm-up; algorithmic bytes per SURVEY.md §8d.
 """
@@ -161,88 +161,58 @@ def run_extras(nd, ctx, torch, dist, rank, world, local, peak_gbs):
             out["C4_comparator_cublas_1xtf32_8192^3"] = {"TFLOP/s": round(flops / (e0.elapsed_time(e1) / 3 * 1e-3) / 1e12, 2)}
         del ta, tb, tc
     torch.cuda.empty_cache()
-    # ---- C5: sharded elementwise + global sum with an all-reduce ----------------------------------------
-    if dist is not None:
-        rows = 65536 // 8  # per-rank shard of the [65536, 65536] f32 problem at 8 GPUs; weak-scaled below that
-        ts = [torch.rand(rows, 65536, device=dev) * 2 - 1 for _ in range(3)]
-        a, b, c = (tarr(t) for t in ts)
-        acc = torch.zeros(1, device=dev, dtype=torch.float32)
-        accv = tarr(acc, shape=())
+    # ---- sharded axis reductions (C3 slabs) and the exchange alone; config 5 itself is bench.py's headline ------------
+    if dist is not None and world > 1:
+        import ctypes as C
+        from ndarray_b200 import parallel as par
+        from ndarray_b200.array import Red
         stream = torch.cuda.ExternalStream(ctx.stream_ptr(), device=dev)
+        try:
+            peers = par.PeerGroup(ctx, dist, slot_bytes=1 << 20)  # raises on ALL ranks or on none
+        except Exception as e:  # noqa: BLE001
+            peers = None
+            out["peer_windows"] = {"error": repr(e)}
 
-        def c5():
-            Zip.from_(a).and_(b).and_(c).for_each("a=b*c+a")
-            a.sum_to_device(accv)
-            with torch.cuda.stream(stream):
-                dist.all_reduce(acc)
+        def peer_section():
+            # exchange latency alone for the C3 sum_axis(Axis(0)) vector (16384 f64 = 128 KiB)
+            vec_t = torch.zeros(16384, device=dev, dtype=torch.float64)
+            vec = tarr(vec_t)
 
-        med, best = _time(ctx, c5, 10, 2)
-        t = torch.tensor([med], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        nbytes = (4 * 4 + 4) * rows * 65536 * world
-        out["C5_zip+global_sum_f32"] = {"GB/s_aggregate": round(gbs(nbytes, float(t.item())), 1), "ms": round(float(t.item()), 3),
-                                        "per_rank_elems": rows * 65536, "collective": "ncclAllReduce(sum, 1 elt) on the ctx stream"}
-        if world > 1:
-            # the same step with the exchange fused into the reduction's finishing kernel (peer windows over NVLink)
-            import ctypes as C
-            from ndarray_b200 import parallel as par
-            from ndarray_b200.array import Red
-            L = nd.lib()
-            try:
-                peers = par.PeerGroup(ctx, dist, slot_bytes=1 << 20)  # raises on ALL ranks or on none
-            except Exception as e:  # noqa: BLE001
-                peers = None
-                out["peer_windows"] = {"error": repr(e)}
+            def nccl():
+                with torch.cuda.stream(stream):
+                    dist.all_reduce(vec_t)
+            med_n, _ = _time(ctx, nccl, 50, 5)
+            med_p, _ = _time(ctx, lambda: peers.allreduce_(vec), 50, 5)
+            tn = torch.tensor([med_n, med_p], device=dev, dtype=torch.float64)
+            dist.all_reduce(tn, op=dist.ReduceOp.MAX)
+            out["allreduce_latency_128KiB"] = {"nccl_us": round(float(tn[0].item()) * 1e3, 1), "peer_memory_us": round(float(tn[1].item()) * 1e3, 1)}
+            # C3 sharded, STRONG-scaled: sum_axis(Axis(0)) of this rank's [16384/N, 16384] f64 slab + exchange of the 128 KiB vector
+            n = 16384
+            rows = n // world
+            slab_t = torch.randn(rows, n, device=dev, dtype=torch.float64)
+            slab = tarr(slab_t)
 
-            def peer_section():
-                def c5_peer():
-                    Zip.from_(a).and_(b).and_(c).for_each("a=b*c+a")
-                    L.ndb_reduce_all_peer(ctx.handle, Red.SUM, C.byref(a.v), C.c_void_p(accv.v.ptr))
+            def two_launch():
+                part = slab.sum_axis(0)
+                return peers.allreduce_(part)
 
-                med, best = _time(ctx, c5_peer, 10, 2)
-                t = torch.tensor([med], device=dev, dtype=torch.float64)
-                dist.all_reduce(t, op=dist.ReduceOp.MAX)
-                out["C5_zip+global_sum_f32_peer_fused"] = {"GB/s_aggregate": round(gbs(nbytes, float(t.item())), 1), "ms": round(float(t.item()), 3),
-                                                           "collective": "none: the sum's finishing kernel exchanges the scalar through peer memory"}
-                # exchange latency alone: one element and the C3 sum_axis(Axis(0)) vector (16384 f64 = 128 KiB)
-                vec_t = torch.zeros(16384, device=dev, dtype=torch.float64)
-                vec = tarr(vec_t)
-                for label, arr, tt in (("1elt", accv, acc), ("128KiB", vec, vec_t)):
-                    def nccl(tt=tt):
-                        with torch.cuda.stream(stream):
-                            dist.all_reduce(tt)
-                    med_n, _ = _time(ctx, nccl, 50, 5)
-                    med_p, _ = _time(ctx, lambda arr=arr: peers.allreduce_(arr), 50, 5)
-                    tn = torch.tensor([med_n, med_p], device=dev, dtype=torch.float64)
-                    dist.all_reduce(tn, op=dist.ReduceOp.MAX)
-                    out[f"allreduce_latency_{label}"] = {"nccl_us": round(float(tn[0].item()) * 1e3, 1), "peer_memory_us": round(float(tn[1].item()) * 1e3, 1)}
-                # C3 sharded: sum_axis(Axis(0)) of a [2048, 16384] f64 slab per rank + exchange of the 128 KiB vector
-                slab_t = torch.randn(2048, 16384, device=dev, dtype=torch.float64)
-                slab = tarr(slab_t)
-                def two_launch():
-                    part = slab.sum_axis(0)
-                    return peers.allreduce_(part)
+            fused_ok = par._fused_axis0(slab, Red.SUM, 0.0, n, peers) is not None  # same answer on every rank
+            cases = [("nccl", lambda: par.sum_axis0(slab, dist)), ("peer", two_launch), ("var_nccl", lambda: par.var_axis0(slab, 1.0, dist))]
+            if fused_ok:
+                cases += [("peer_fused_one_launch", lambda: par._fused_axis0(slab, Red.SUM, 0.0, n, peers)),
+                          ("var_peer_fused_one_launch", lambda: par._fused_axis0(slab, Red.VAR, 1.0, n, peers))]
+            for label, fn in cases:
+                med_s, _ = _time(ctx, fn, 20, 3)
+                ts = torch.tensor([med_s], device=dev, dtype=torch.float64)
+                dist.all_reduce(ts, op=dist.ReduceOp.MAX)
+                out[f"C3_sum_axis0_sharded_f64_{label}"] = {"GB/s_aggregate": round(gbs(8 * n * n + 8 * n, float(ts.item())), 1),
+                                                           "ms": round(float(ts.item()), 4), "scaling": "strong: 16384^2 f64 over all ranks"}
+            ctx.sync()
+            dist.barrier()
+            peers.close()
 
-                n_glob = 2048 * world
-                fused_ok = par._fused_axis0(slab, Red.SUM, 0.0, n_glob, peers) is not None  # agreed across ranks
-                cases = [("nccl", lambda: par.sum_axis0(slab, dist)), ("peer", two_launch), ("var_nccl", lambda: par.var_axis0(slab, 1.0, dist))]
-                if fused_ok:
-                    cases += [("peer_fused_one_launch", lambda: par._fused_axis0(slab, Red.SUM, 0.0, n_glob, peers)),
-                              ("var_peer_fused_one_launch", lambda: par._fused_axis0(slab, Red.VAR, 1.0, n_glob, peers))]
-                for label, fn in cases:
-                    med_s, _ = _time(ctx, fn, 20, 3)
-                    ts = torch.tensor([med_s], device=dev, dtype=torch.float64)
-                    dist.all_reduce(ts, op=dist.ReduceOp.MAX)
-                    out[f"C3_sum_axis0_sharded_f64_{label}"] = {"GB/s_aggregate": round(gbs(world * (8 * 2048 * 16384 + 8 * 16384), float(ts.item())), 1),
-                                                               "ms": round(float(ts.item()), 4)}
-                ctx.sync()
-                dist.barrier()
-                peers.close()
-                del slab, slab_t, vec, vec_t
-
-            if peers is not None:
-                peer_section()
-        del a, b, c, ts
+        if peers is not None:
+            peer_section()
         torch.cuda.empty_cache()
     # ---- C4 at N GPUs: A and C row-sharded (8192 rows per rank, weak), B broadcast from rank 0 EVERY step ----------
     if dist is not None and world > 1:

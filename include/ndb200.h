@@ -251,6 +251,12 @@ int ndb_zip_any(ndb_ctx *ctx, int op, const void *scalars, int n_inputs, const n
 /* Zip::fold / par_fold with an additive accumulator (src/zip/mod.rs:622, parallel/impl_par_methods.rs:173):
  * sum over all element tuples of op(inputs...), result (element type) to host. */
 int ndb_zip_fold_sum(ndb_ctx *ctx, int op, const void *scalars, int n_inputs, const ndb_view *inputs, void *out_host);
+/* Zip::fold with any ASSOCIATIVE accumulator (src/zip/mod.rs:622-655): out = redop(init, redop over all element tuples of
+ * op(inputs...)), redop in {SUM, PROD, MIN, MAX}; `init` (element type, host) may be NULL = the identity.  An empty shape
+ * returns `init` like Rust's fold (NDB_ERR_EMPTY for MIN/MAX without one).  Closures that are not associative cannot be
+ * evaluated as a tree and are out of scope (fold_axis has the same restriction). */
+int ndb_zip_fold(ndb_ctx *ctx, int op, const void *scalars, int n_inputs, const ndb_view *inputs, int redop, const void *init,
+                 void *out_host);
 /* Zip::map_collect's output-order rule (src/zip/mod.rs:278-281,764-789): returns 1 if the fresh
  * output must be F-order, 0 for C-order, given the INPUT producers only. */
 int ndb_zip_prefer_f(int n_inputs, const ndb_view *inputs);
@@ -290,14 +296,17 @@ int ndb_peer_allgather(ndb_ctx *ctx, int dtype, const void *local_dev, void *out
 /* ndb_reduce_axis over ALL shards when `axis` is the sharded axis and a kept axis is the dense one (sum_axis(Axis(0)) of a
  * C-order slab): ONE launch per rank - the block that completes a column tile locally exchanges its states (sums, or
  * Welford (n, mean, M2) for var/std) with the other ranks through the windows, merges them in rank order and finalizes
- * with the GLOBAL axis length n_global (mean divides by it, ddof is checked against it).  Returns NDB_ERR_UNSUPPORTED,
- * without launching anything, when the layout, the tile count (> 2 per SM) or the slot size rule this path out; the rules
- * depend on shapes only, so all ranks decide alike and the caller falls back to ndb_reduce_axis + ndb_peer_allreduce. */
+ * with the GLOBAL axis length n_global (mean divides by it, ddof is checked against it).
+ * Contract: every rank passes its slab of ONE global array - same kept shape, strides, dtype and op; the row count may
+ * differ and may be 0.  Returns NDB_ERR_UNSUPPORTED, without launching anything, when the layout, the tile count or the slot
+ * size rule this path out.  That rule reads only values the contract makes identical on every rank (kept shape, strides,
+ * dtype, op, n_global, slot size, occupancy x SM count): a shard that starts off a 16-byte boundary or holds a single row
+ * changes how the rank loads its rows, not whether it takes part, so all ranks decide alike and the caller falls back to
+ * ndb_reduce_axis + ndb_peer_allreduce together.  The launch is cooperative (every block co-resident or the launch fails),
+ * so a block waiting for its peers can never keep the blocks it waits for off the machine. */
 int ndb_reduce_axis_peer(ndb_ctx *ctx, int redop, int axis, const ndb_view *in, const ndb_view *out, double ddof, int64_t n_global);
-/* Would ndb_reduce_axis_peer take the fused path for these arguments on THIS rank?  NDB_OK / NDB_ERR_UNSUPPORTED, launches
- * nothing.  A caller that cannot rule out rank-dependent layouts (a misaligned shard on one rank) agrees on the answer
- * across ranks once per shape (logical AND) before using the fused call, because a rank that falls back while the others
- * wait in the kernel would only be caught by the 20 s watchdog. */
+/* Would ndb_reduce_axis_peer take the fused path for these arguments?  NDB_OK / NDB_ERR_UNSUPPORTED, launches nothing; the
+ * answer is the same on every rank under the contract above. */
 int ndb_reduce_axis_peer_ok(ndb_ctx *ctx, int redop, int axis, const ndb_view *in, const ndb_view *out, double ddof, int64_t n_global);
 /* ndb_reduce_all_dev over ALL shards: the kernel that finishes this rank's reduction tree also performs the exchange. */
 int ndb_reduce_all_peer(ndb_ctx *ctx, int redop, const ndb_view *in, void *out_dev);
@@ -341,6 +350,18 @@ double cblas_ddot(int n, const double *x, int incx, const double *y, int incy);
  * inputs are copied H2D, the op runs, the output is copied D2H, chunked along the outermost
  * axis so copies in both directions overlap the kernel.  Synchronous. */
 int ndb_zip_host(ndb_ctx *ctx, int op, const void *scalars, int n_parts, const ndb_view *parts);
+/* The same Zip followed by a fold of the values it wrote (Zip::fold with an associative accumulator, src/zip/mod.rs:622):
+ * each slab is reduced on the device while it is still resident, the per-slab scalars are combined in slab order and
+ * the result (element type) lands in `out_host`.  redop in {SUM, PROD, MIN, MAX}.  BASELINE config 5 end to end is
+ * ndb_zip_host_fold(MUL_ADD, (a; b, c, a), SUM): a = b*c + a and a.sum() in one pass over PCIe. */
+int ndb_zip_host_fold(ndb_ctx *ctx, int op, const void *scalars, int n_parts, const ndb_view *parts, int redop, void *out_host);
+
+/* ---- synthetic data for harnesses ----------------------------------------------------------------------------------
+ * Counter-based generator: element i of the stream is a pure function of (seed, i) (splitmix64 output i, top bits mapped to
+ * [-1, 1) for floats, raw bits for integers), so shards of one logical array can be filled independently on any number
+ * of GPUs and reproduced bit for bit on the CPU (oracle: orc_counter_fill).  `out` must be standard-layout and 16-byte
+ * aligned; out[j] (C-order flat index j) = value(seed, first_index + j).  Not part of ndarray's path. */
+int ndb_fill_counter_rng(ndb_ctx *ctx, const ndb_view *out, uint64_t seed, uint64_t first_index);
 
 #ifdef __cplusplus
 }

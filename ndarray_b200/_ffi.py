@@ -104,9 +104,12 @@ def lib():
         "ndb_zip_plan": (i32, [i32, i32, PV, C.POINTER(ZipPlan)]),
         "ndb_zip_prefer_f": (i32, [i32, PV]),
         "ndb_zip_host": (i32, [vp, i32, vp, i32, PV]),
+        "ndb_zip_host_fold": (i32, [vp, i32, vp, i32, PV, i32, vp]),
+        "ndb_fill_counter_rng": (i32, [vp, PV, u64, u64]),
         "ndb_zip_all": (i32, [vp, i32, vp, i32, PV, C.POINTER(i32)]),
         "ndb_zip_any": (i32, [vp, i32, vp, i32, PV, C.POINTER(i32)]),
         "ndb_zip_fold_sum": (i32, [vp, i32, vp, i32, PV, vp]),
+        "ndb_zip_fold": (i32, [vp, i32, vp, i32, PV, i32, vp, vp]),
         "ndb_var": (i32, [vp, PV, dbl, i32, vp]),
         "ndb_reduce_all": (i32, [vp, i32, PV, vp]),
         "ndb_reduce_all_dev": (i32, [vp, i32, PV, vp]),

@@ -831,6 +831,22 @@ class Zip:
 
     par_fold_sum = fold_sum
 
+    def fold(self, init, op: int, fold: str = "sum", scalars=()):
+        """Zip::fold(init, |acc, ...| acc <fold> op(...)) for an associative accumulator (src/zip/mod.rs:622):
+        fold in {"sum", "prod", "min", "max"}.  An empty Zip returns `init`."""
+        redop = {"sum": Red.SUM, "prod": Red.PROD, "min": Red.MIN, "max": Red.MAX}[fold]
+        n = len(self.parts)
+        dt = self.parts[0].dtype
+        views = (View * n)(*[p.v for p in self.parts])
+        sc = np.asarray(scalars, dtype=dt) if len(scalars) else None
+        ini = np.asarray(init, dtype=dt) if init is not None else None
+        out = np.zeros((), dtype=dt)
+        check(lib().ndb_zip_fold(self._ctx().handle, op, C.c_void_p(sc.ctypes.data) if sc is not None else None, n, views, redop,
+                                 C.c_void_p(ini.ctypes.data) if ini is not None else None, C.c_void_p(out.ctypes.data)))
+        return out[()]
+
+    par_fold = fold
+
     @staticmethod
     def indexed(p: "Array") -> "Zip":
         """Zip::indexed (src/zip/mod.rs:237): the index along each axis rides along as extra producers (broadcast

@@ -86,8 +86,8 @@ struct ndb_ctx {
     unsigned long long *peer_tile_epoch = nullptr;  // device: exchanges completed per tile counter (reduce.cu's fused axis reductions)
     unsigned *tickets = nullptr;    // NDB_TICKETS zeroed counters: 'last block finishes' hand-over in split reductions (self-resetting)
     // staging buffers for the host-pointer (end-to-end / cblas) entry points
-    void *stage[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-    size_t stage_bytes[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    void *stage[NDB_MAX_PARTS] = {};  // one per Zip producer (ndb_zip_host mirrors up to NDB_MAX_PARTS spans)
+    size_t stage_bytes[NDB_MAX_PARTS] = {};
     cudaStream_t copy_in = nullptr, copy_out = nullptr;
     // pinned bounce buffers for PAGEABLE host memory (the CBLAS boundary hands in ndarray's Vec storage)
     void *bounce[2] = {nullptr, nullptr};

@@ -206,6 +206,11 @@ int staged_d2h(ndb_ctx *ctx, void *dst_host, const void *src_dev, size_t bytes)
 
 int ensure_stage(ndb_ctx *ctx, int slot, size_t bytes)
 {
+    static_assert(sizeof(ctx->stage) / sizeof(ctx->stage[0]) == NDB_MAX_PARTS, "one staging slot per Zip producer");
+    if (slot < 0 || slot >= NDB_MAX_PARTS) {
+        set_error("ensure_stage: slot %d outside 0..%d", slot, NDB_MAX_PARTS - 1);
+        return NDB_ERR_INVALID_ARG;
+    }
     if (ctx->stage_bytes[slot] >= bytes) return NDB_OK;
     NDB_CUDA(cudaDeviceSynchronize());
     if (ctx->stage[slot]) NDB_CUDA(cudaFree(ctx->stage[slot]));
@@ -291,7 +296,7 @@ int ndb_ctx_destroy(ndb_ctx *ctx)
     DeviceGuard g(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     if (ctx->workspace) cudaFree(ctx->workspace);
-    for (int i = 0; i < 8; ++i)
+    for (int i = 0; i < NDB_MAX_PARTS; ++i)
         if (ctx->stage[i]) cudaFree(ctx->stage[i]);
     if (ctx->tickets) cudaFree(ctx->tickets);
     if (ctx->dev_flag) cudaFree(ctx->dev_flag);

@@ -419,10 +419,12 @@ int launch(ndb_ctx *ctx, const GemmArgs &g, float alpha, float beta, const float
     p.group_m = getenv("NDB_GEMM_GROUP_M") ? std::max(1, atoi(getenv("NDB_GEMM_GROUP_M"))) : 12;
     p.debug = getenv("NDB_GEMM_DEBUG") ? atoi(getenv("NDB_GEMM_DEBUG")) : 0;
     p.chunk_kb = getenv("NDB_GEMM_CHUNK_KB") ? std::max(1, atoi(getenv("NDB_GEMM_CHUNK_KB"))) : 8;
-    static bool attr_done = false;
-    if (!attr_done) {
+    // the opt-in is per DEVICE (a process may hold one context per GPU); setting it twice from racing threads is harmless
+    static std::atomic<uint64_t> attr_done{0};
+    const uint64_t dev_bit = 1ull << (ctx->device & 63);
+    if (!(attr_done.load(std::memory_order_acquire) & dev_bit)) {
         NDB_CUDA(cudaFuncSetAttribute(gemm_tf32x3<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg<BN>::SMEM_BYTES));
-        attr_done = true;
+        attr_done.fetch_or(dev_bit, std::memory_order_release);
     }
     const unsigned blocks = (unsigned)(p.tiles_m * p.tiles_n);
     gemm_tf32x3<BN><<<blocks, THREADS, Cfg<BN>::SMEM_BYTES, ctx->stream>>>(ma_hi, ma_lo, mb_hi, mb_lo, p);

@@ -353,13 +353,15 @@ int launch_dense(ndb_ctx *ctx, const GemmArgs &g, double alpha, double beta)
         if (st != NDB_ERR_UNSUPPORTED) return st;
     }
     const unsigned blocks = (unsigned)(p.tiles_m * p.tiles_n);
-    static bool attr_done = false;
-    if (!attr_done) {
+    // the opt-in is per DEVICE (a process may hold one context per GPU); setting it twice from racing threads is harmless
+    static std::atomic<uint64_t> attr_done{0};
+    const uint64_t dev_bit = 1ull << (ctx->device & 63);
+    if (!(attr_done.load(std::memory_order_acquire) & dev_bit)) {
         NDB_CUDA(cudaFuncSetAttribute(gemm_f64_dmma<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
         NDB_CUDA(cudaFuncSetAttribute(gemm_f64_dmma<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
         NDB_CUDA(cudaFuncSetAttribute(gemm_f64_dmma<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
         NDB_CUDA(cudaFuncSetAttribute(gemm_f64_dmma<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
-        attr_done = true;
+        attr_done.fetch_or(dev_bit, std::memory_order_release);
     }
     if (a_kc && b_kc) gemm_f64_dmma<true, true><<<blocks, THREADS, SMEM_BYTES, ctx->stream>>>(p);
     else if (a_kc) gemm_f64_dmma<true, false><<<blocks, THREADS, SMEM_BYTES, ctx->stream>>>(p);

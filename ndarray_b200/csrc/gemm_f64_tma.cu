@@ -355,14 +355,16 @@ int gemm_f64_tma_launch(ndb_ctx *ctx, const double *a, int64_t lda, bool a_kc, c
     }
     p.csize = csize;
     const unsigned blocks = (unsigned)(out_tiles * csize);
-    static bool attr_done = false;
-    if (!attr_done) {
+    // the opt-in is per DEVICE (a process may hold one context per GPU); setting it twice from racing threads is harmless
+    static std::atomic<uint64_t> attr_done{0};
+    const uint64_t dev_bit = 1ull << (ctx->device & 63);
+    if (!(attr_done.load(std::memory_order_acquire) & dev_bit)) {
 #define NDB_F64_ATTR(A, B, T) \
     NDB_CUDA(cudaFuncSetAttribute(gemm_f64_tma<A, B, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Shape<T>::SMEM_BYTES));
         NDB_F64_ATTR(true, true, 128) NDB_F64_ATTR(true, false, 128) NDB_F64_ATTR(false, true, 128) NDB_F64_ATTR(false, false, 128)
         NDB_F64_ATTR(true, true, 64) NDB_F64_ATTR(true, false, 64) NDB_F64_ATTR(false, true, 64) NDB_F64_ATTR(false, false, 64)
 #undef NDB_F64_ATTR
-        attr_done = true;
+        attr_done.fetch_or(dev_bit, std::memory_order_release);
     }
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));

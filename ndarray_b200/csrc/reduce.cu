@@ -153,8 +153,23 @@ struct Acc {
             s.m2 = s.m2 + bm2 + delta * delta * (s.n * w);
             s.n = n;
         } else {
+            // pairwise tree over the batch, then ONE add into the running state: the sequential chain a thread carries is
+            // K times shorter, so is its rounding-error random walk (2^32-element f32 sum: ~0.16 -> ~0.04 absolute), and the
+            // K values combine with log2(K) dependent operations instead of K
+            T t[K];
 #pragma unroll
-            for (int i = 0; i < K; ++i) add(x[i]);
+            for (int i = 0; i < K; ++i) t[i] = x[i];
+#pragma unroll
+            for (int w = K; w > 1; w = (w + 1) / 2) {
+#pragma unroll
+                for (int i = 0; i < w / 2; ++i) {
+                    typename Rd::State m = t[2 * i];
+                    Rd::add(m, t[2 * i + 1]);
+                    t[i] = m;
+                }
+                if (w & 1) t[w / 2] = t[w - 1];
+            }
+            add(t[0]);
         }
     }
     __device__ __forceinline__ void merge(const Acc &o)
@@ -250,6 +265,7 @@ struct RedArgs {
     void *partial;  // [splits][n_out] states
     unsigned *tickets;  // red_cols: one zeroed counter per column tile; non-null = the last split to finish merges (one launch)
     int peer_on;                      // red_cols<PEER>: exchange every tile's state with the other ranks before finalizing
+    int peer_scalar;                  // red_cols<PEER>: this rank's base pointer is not 16-byte aligned -> same tile geometry, scalar loads
     unsigned long long *tile_epoch;   // exchanges completed so far per tile counter (device, this rank)
     PeerArgs peer;
 };
@@ -419,6 +435,16 @@ __global__ void __launch_bounds__(256, R == R_WELFORD ? NDB_RED_COLS_MINB_W : 3)
             int64_t r = r0 + ty;
             constexpr int U = (R == R_WELFORD) ? NDB_RED_COLS_WU : 8;  // rows in flight per thread
             if constexpr (W > 1) {
+                if constexpr (PEER) {
+                    // The tile geometry of the fused sharded reduction must be the same on every rank, so a rank whose
+                    // shard happens to start off a 16-byte boundary keeps W columns per thread and loads them one by one.
+                    if (a.peer_scalar) {
+                        for (; r < r1; r += 8) {
+#pragma unroll
+                            for (int e = 0; e < W; ++e) acc[e].add(src[r * a.s + e]);
+                        }
+                    }
+                }
                 for (; r + 8 * (U - 1) < r1; r += 8 * U) {
                     V v[U];
 #pragma unroll
@@ -576,19 +602,19 @@ __global__ void __launch_bounds__(256) red_all_flat(AllArgs a)
     int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
     for (; i + 3 * stride < nv; i += 4 * stride) {
         V v0 = vsrc[i], v1 = vsrc[i + stride], v2 = vsrc[i + 2 * stride], v3 = vsrc[i + 3 * stride];
+        T x[4 * N];
 #pragma unroll
-        for (int e = 0; e < N; ++e) acc.add(v0.v[e]);
-#pragma unroll
-        for (int e = 0; e < N; ++e) acc.add(v1.v[e]);
-#pragma unroll
-        for (int e = 0; e < N; ++e) acc.add(v2.v[e]);
-#pragma unroll
-        for (int e = 0; e < N; ++e) acc.add(v3.v[e]);
+        for (int e = 0; e < N; ++e) {
+            x[e] = v0.v[e];
+            x[N + e] = v1.v[e];
+            x[2 * N + e] = v2.v[e];
+            x[3 * N + e] = v3.v[e];
+        }
+        acc.template add_batch<4 * N>(x);
     }
     for (; i < nv; i += stride) {
         V v0 = vsrc[i];
-#pragma unroll
-        for (int e = 0; e < N; ++e) acc.add(v0.v[e]);
+        acc.template add_batch<N>(v0.v);
     }
     if (blockIdx.x == 0) {  // ragged head and tail
         const int64_t tail0 = head + nv * N;
@@ -1008,7 +1034,9 @@ static int reduce_axis_launch(ndb_ctx *ctx, RedArgs &a, const ZipPlan &z)
     for (int d = 0; d < a.k.n; ++d)
         if (a.k.dim[d] > 1) min_kept = std::min<int64_t>(min_kept, llabs(a.k.in_stride[d]));
     const int64_t as = llabs(a.s);
-    const bool lanes = a.n_out == 1 || a.n == 1 || as <= min_kept;
+    // peer mode: the choice must not depend on this rank's row count (a rank holding one row, or none, still has to take
+    // part in the exchange with the same tile geometry as the others)
+    const bool lanes = a.n_out == 1 || (!a.peer_on && a.n == 1) || as <= min_kept;
     if (a.peer_on && (lanes || !(a.k.in_stride[last] == 1 && a.k.dim[last] >= 32))) return NDB_ERR_UNSUPPORTED;
     if (lanes) {
         bool vec = a.s == 1 && a.n % vecn == 0 && ((uintptr_t)a.in % 16) == 0 && a.n >= 4 * vecn;
@@ -1034,8 +1062,10 @@ static int reduce_axis_launch(ndb_ctx *ctx, RedArgs &a, const ZipPlan &z)
     }
     if (a.k.in_stride[last] == 1 && a.k.dim[last] >= 32) {
         const int64_t ncol = a.k.dim[last];
-        bool vec = ncol % vecn == 0 && ((uintptr_t)a.in % 16) == 0 && a.s % vecn == 0;
+        const bool aligned = ((uintptr_t)a.in % 16) == 0;
+        bool vec = ncol % vecn == 0 && (aligned || a.peer_on) && a.s % vecn == 0;  // peer: alignment is rank-local, see peer_scalar
         for (int d = 0; d < last && vec; ++d) vec = a.k.in_stride[d] % vecn == 0;
+        a.peer_scalar = a.peer_on && !aligned;
         const int w = vec ? (int)vecn : 1;
         const int64_t tiles = (ncol + 32 * w - 1) / (32 * w);
         const int64_t total = tiles * (a.n_out / ncol);
@@ -1058,19 +1088,35 @@ static int reduce_axis_launch(ndb_ctx *ctx, RedArgs &a, const ZipPlan &z)
         }
         dim3 grid((unsigned)std::min<int64_t>(total, (int64_t)1 << 30), (unsigned)splits, 1), block(32, 8, 1);
         if (a.peer_on) {
-            // fused exchange (see red_cols<PEER>): every tile's finishing block waits for the other ranks, so all of
-            // them must be resident together with the blocks still working -> at most two tiles per SM; the rules
-            // below depend on the shapes only, so every rank takes the same decision
+            // Fused exchange (see red_cols<PEER>): every tile's finishing block waits for the other ranks' finishers, so
+            // the whole grid is launched COOPERATIVELY - the driver either makes every block co-resident or refuses the
+            // launch - and is sized from the kernel's real occupancy.  A waiting block can therefore never keep a block it
+            // (transitively) waits for off the machine, and the watchdog in peer_spin only fires if a peer process died.
+            // Everything that decides eligibility (tile count, occupancy x SM count, slot size) is the same on every
+            // rank for identically shaped shards; the split count is rank-local and free to differ.
             if constexpr (FIN == FIN_WELFORD_RAW) {
                 return NDB_ERR_UNSUPPORTED;
             } else {
-                if (!vec || total > std::min<int64_t>(PEER_MAX_TILES, (int64_t)ctx->sm_count * 2) || (splits > 1 && a.tickets == nullptr) ||
+                auto kern = red_cols<T, R, FIN, Vec128<T>::N, true>;
+                static std::atomic<int> occ_cache{0};
+                int occ = occ_cache.load(std::memory_order_relaxed);
+                if (occ == 0) {
+                    NDB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 256, 0));
+                    occ_cache.store(occ, std::memory_order_relaxed);
+                }
+                const int64_t capacity = (int64_t)occ * ctx->sm_count;
+                if (!vec || total > std::min<int64_t>(PEER_MAX_TILES, capacity) || total > NDB_TICKETS ||
                     (size_t)a.n_out * sizeof(Acc<T, R>) > ctx->peer_slot_bytes || !ctx->peer_tile_epoch)
                     return NDB_ERR_UNSUPPORTED;
                 if (a.peer_on == 2) return NDB_OK;  // eligibility query only (ndb_reduce_axis_peer_ok): nothing is launched
+                splits = (int)std::max<int64_t>(1, std::min<int64_t>(splits, capacity / total));
+                a.splits = splits;
+                a.tickets = splits > 1 ? ctx->tickets : nullptr;
+                grid.y = (unsigned)splits;
                 NDB_TRY(peer_begin(ctx, 0, (size_t)a.n_out * sizeof(Acc<T, R>), &a.peer));
                 a.tile_epoch = ctx->peer_tile_epoch;
-                red_cols<T, R, FIN, Vec128<T>::N, true><<<grid, block, 0, st>>>(a);
+                void *kargs[1] = {(void *)&a};
+                NDB_CUDA(cudaLaunchCooperativeKernel((const void *)kern, grid, block, kargs, 0, st));
                 NDB_CHECK_LAUNCH();
                 return NDB_OK;
             }
@@ -1153,7 +1199,8 @@ static int reduce_axis_impl(ndb_ctx *ctx, int redop, int axis, const ndb_view *i
     }
     base.ndim = in->ndim - 1;
     const int64_t n = in->dim[axis];
-    if (peer && (n == 0 || n_global < n)) return NDB_ERR_UNSUPPORTED;  // an empty shard cannot take the fused path
+    if (peer && n_global < n) return NDB_ERR_UNSUPPORTED;
+    if (peer && n_global == 0) return NDB_ERR_UNSUPPORTED;  // the empty-axis conventions are the unsharded call's business
     const int64_t n_stat = peer ? n_global : n;  // the length mean / var / std divide by: the whole axis, all shards
     const bool welford = redop == NDB_RED_VAR || redop == NDB_RED_STD || redop == -1;
     if (welford && !dtype_is_float(in->dtype)) {
@@ -1187,7 +1234,7 @@ static int reduce_axis_impl(ndb_ctx *ctx, int redop, int axis, const ndb_view *i
     NDB_TRY(st);
     if (z.kernel == NDB_KERNEL_NOOP) return NDB_OK;  // no outputs at all
     DeviceGuard g(ctx->device);
-    if (n == 0) {
+    if (n == 0 && !peer) {  // (a rank whose SHARD is empty still takes part in the fused exchange, contributing no rows)
         // sum -> 0, product -> 1, mean -> None, var/std -> NaN (0/0), min/max -> nothing to fold
         if (redop == NDB_RED_SUM) return fill_view(ctx, out, 0.0);
         if (redop == NDB_RED_PROD) return fill_view(ctx, out, 1.0);
@@ -1213,7 +1260,7 @@ static int reduce_axis_impl(ndb_ctx *ctx, int redop, int axis, const ndb_view *i
         a.k.out2_stride[d] = out2 ? z.stride[2][d] : 0;
     }
     a.n = n;
-    a.s = n > 1 ? in->stride[axis] : 1;
+    a.s = (n > 1 || peer) ? in->stride[axis] : 1;  // peer: kernel choice must not depend on this rank's row count
     a.nT = nT;
     a.dof = dof;
     a.splits = 1;

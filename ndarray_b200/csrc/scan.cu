@@ -6,6 +6,10 @@
 //               neighbouring addresses, every step is coalesced.
 //   scan_lanes  the scanned axis is the dense one: a warp owns a lane and scans it 32 elements at a time with shuffles
 //               plus a running carry (coalesced; the association differs, so floats agree to rounding, integers exactly).
+//   scan_chunk_* a long strided axis with few lanes (n >= 512): the axis is cut into chunks scanned by separate
+//               threads; this re-associates float sums too (tolerance-class), integers stay exact.
+// Exactness by path: scan_cols = ndarray's association (floats bit-identical); scan_lanes(_vec) and scan_chunk_* =
+// re-associated (floats to rounding).  No path folds an identity into element 0, so a leading -0.0 is preserved.
 #include <algorithm>
 
 #include "zip_kernels.cuh"
@@ -82,7 +86,8 @@ __global__ void __launch_bounds__(256) scan_lanes(ScanArgs a)
             const T up = __shfl_up_sync(0xffffffffu, v, d);
             if (lane_id >= d) v = comb<T, MUL>(up, v);
         }
-        v = comb<T, MUL>(carry, v);
+        // no identity is ever folded in: element 0 stays as it is (-0.0 stays -0.0, impl_methods.rs:3243 starts at 1)
+        if (i0 > 0) v = comb<T, MUL>(carry, v);
         if (live) p[i * a.s] = v;
         carry = __shfl_sync(0xffffffffu, v, 31);
     }
@@ -171,11 +176,15 @@ __global__ void __launch_bounds__(256) scan_lanes_vec(ScanArgs a)
             const T up = __shfl_up_sync(0xffffffffu, inc, d);
             if (lane_id >= d) inc = comb<T, MUL>(up, inc);
         }
-        T excl = __shfl_up_sync(0xffffffffu, inc, 1);
-        if (lane_id == 0) excl = ident;
-        const T off = comb<T, MUL>(carry, excl);
+        const T excl = __shfl_up_sync(0xffffffffu, inc, 1);
+        // what precedes this thread's vector: nothing (first vector of the lane), the carry alone (thread 0 of a later
+        // step), the warp prefix alone (first step) or both - an identity is never folded in, so -0.0 survives
+        const bool first = i0 == 0;
+        const T off = lane_id == 0 ? carry : (first ? excl : comb<T, MUL>(carry, excl));
+        if (!(first && lane_id == 0)) {
 #pragma unroll
-        for (int e = 0; e < N; ++e) v.v[e] = comb<T, MUL>(off, v.v[e]);
+            for (int e = 0; e < N; ++e) v.v[e] = comb<T, MUL>(off, v.v[e]);
+        }
         if (whole) {
             *reinterpret_cast<V *>(p + i) = v;
         } else {
@@ -183,7 +192,8 @@ __global__ void __launch_bounds__(256) scan_lanes_vec(ScanArgs a)
             for (int e = 0; e < N; ++e)
                 if (i + e < a.n) p[i + e] = v.v[e];
         }
-        carry = comb<T, MUL>(carry, __shfl_sync(0xffffffffu, inc, 31));
+        const T step_total = __shfl_sync(0xffffffffu, inc, 31);
+        carry = first ? step_total : comb<T, MUL>(carry, step_total);
     }
 }
 
@@ -255,6 +265,12 @@ extern "C" int ndb_accumulate_axis(ndb_ctx *ctx, int op, int axis, const ndb_vie
     for (int i = 0; i < v->ndim; ++i)
         if (v->dim[i] == 0) return NDB_OK;
     if (n <= 1) return NDB_OK;
+    {
+        // the WHOLE view is written in place: a zero or aliasing stride on the scanned axis would race
+        ndb_view whole[2] = {*v, *v};
+        ZipPlan zw;
+        NDB_TRY(make_zip_plan(NDB_OP_COPY, 2, whole, &zw));
+    }
     // collapse the kept axes of the (written) view with the Zip planner: checks self-aliasing, flips, merges
     ndb_view kept = *v;
     for (int i = axis; i + 1 < v->ndim; ++i) {

@@ -139,6 +139,25 @@ static bool is_predicate(int op) { return op >= NDB_OP_EQ && op <= NDB_OP_GE; }
 
 }  // namespace ndb
 
+// acc = redop(acc, x) on the host, in the element type (wrapping integers, Rust's NaN-ignoring min / max)
+template <typename T>
+static void host_combine(int redop, T *acc, T x)
+{
+    using U = typename UnsignedOf<T>::type;
+    switch (redop) {
+    case NDB_RED_SUM:
+        if constexpr (std::is_floating_point<T>::value) *acc = *acc + x;
+        else *acc = (T)((U)*acc + (U)x);
+        break;
+    case NDB_RED_PROD:
+        if constexpr (std::is_floating_point<T>::value) *acc = *acc * x;
+        else *acc = (T)((U)*acc * (U)x);
+        break;
+    case NDB_RED_MIN: *acc = (x < *acc || *acc != *acc) ? x : *acc; break;
+    default: *acc = (x > *acc || *acc != *acc) ? x : *acc; break;
+    }
+}
+
 extern "C" {
 
 int ndb_zip_all(ndb_ctx *ctx, int op, const void *scalars, int n_inputs, const ndb_view *inputs, int *result)
@@ -178,6 +197,55 @@ int ndb_zip_fold_sum(ndb_ctx *ctx, int op, const void *scalars, int n_inputs, co
     return NDB_OK;
 }
 
+int ndb_zip_fold(ndb_ctx *ctx, int op, const void *scalars, int n_inputs, const ndb_view *inputs, int redop, const void *init,
+                 void *out_host)
+{
+    if (!out_host || redop < NDB_RED_SUM || redop > NDB_RED_MAX) {
+        set_error("Zip::fold: the accumulator must be sum, product, min or max (an associative fold) and the result non-null");
+        return NDB_ERR_INVALID_ARG;
+    }
+    if (!init && (redop == NDB_RED_MIN || redop == NDB_RED_MAX) && inputs && n_inputs >= 1) {
+        int64_t total = 1;
+        for (int i = 0; i < inputs[0].ndim; ++i) total *= inputs[0].dim[i];
+        if (total == 0) {
+            set_error("Zip::fold(min/max) over an empty shape needs an initial value");
+            return NDB_ERR_EMPTY;
+        }
+    }
+    bool empty = false;
+    unsigned char v[8] = {0};
+    NDB_TRY(zip_then_reduce(ctx, op, scalars, n_inputs, inputs, redop, v, &empty));
+    const int dt = inputs[0].dtype;
+    const size_t esz = dtype_size(dt);
+    if (empty) {  // fold over nothing returns the initial accumulator (src/zip/mod.rs:622); without one, the identity
+        if (init) memcpy(out_host, init, esz);
+        else {
+            memset(out_host, 0, esz);
+            if (redop == NDB_RED_PROD) {
+                switch (dt) {
+                case NDB_F32: *(float *)out_host = 1.f; break;
+                case NDB_F64: *(double *)out_host = 1.0; break;
+                case NDB_I32: *(int32_t *)out_host = 1; break;
+                default: *(int64_t *)out_host = 1; break;
+                }
+            }
+        }
+        return NDB_OK;
+    }
+    if (!init) {
+        memcpy(out_host, v, esz);
+        return NDB_OK;
+    }
+    memcpy(out_host, init, esz);
+    switch (dt) {
+    case NDB_F32: host_combine<float>(redop, (float *)out_host, *(const float *)v); break;
+    case NDB_F64: host_combine<double>(redop, (double *)out_host, *(const double *)v); break;
+    case NDB_I32: host_combine<int32_t>(redop, (int32_t *)out_host, *(const int32_t *)v); break;
+    default: host_combine<int64_t>(redop, (int64_t *)out_host, *(const int64_t *)v); break;
+    }
+    return NDB_OK;
+}
+
 }  // extern "C"
 
 // ---------------------------------------------------------------------------------------------
@@ -212,9 +280,12 @@ bool slabs_disjoint(const ndb_view &v)
 
 }  // namespace
 
-extern "C" {
+extern "C" int ndb_reduce_all_dev(ndb_ctx *ctx, int redop, const ndb_view *in, void *out_dev);
 
-int ndb_zip_host(ndb_ctx *ctx, int op, const void *scalars, int n_parts, const ndb_view *parts)
+// redop < 0: plain Zip.  Otherwise every slab's output is also reduced on the device while it is still resident (one
+// scalar per slab, in slab order), and the reduction of those scalars is written to `fold_out` (host, element type):
+// Zip::fold over the values the Zip has just produced, with no second pass over host memory.
+static int zip_host_impl(ndb_ctx *ctx, int op, const void *scalars, int n_parts, const ndb_view *parts, int redop, void *fold_out)
 {
     if (!ctx) {
         set_error("ndb_zip_host: null context (no CPU fallback exists)");
@@ -222,30 +293,40 @@ int ndb_zip_host(ndb_ctx *ctx, int op, const void *scalars, int n_parts, const n
     }
     ZipPlan probe;
     NDB_TRY(make_zip_plan(op, n_parts, parts, &probe));  // validates shapes, arity, aliasing
-    if (probe.kernel == NDB_KERNEL_NOOP) return NDB_OK;
-    DeviceGuard g(ctx->device);
     const int64_t esz = (int64_t)dtype_size(parts[0].dtype);
+    if (probe.kernel == NDB_KERNEL_NOOP) {
+        if (redop >= 0) {  // fold over nothing: sum -> 0, product -> 1; min / max have no value
+            if (redop != NDB_RED_SUM && redop != NDB_RED_PROD) {
+                set_error("Zip::fold(min/max) over an empty shape has no value");
+                return NDB_ERR_EMPTY;
+            }
+            ndb_view none = parts[0];
+            return ndb_reduce_all(ctx, redop, &none, fold_out);
+        }
+        return NDB_OK;
+    }
+    DeviceGuard g(ctx->device);
 
-    // mirror every producer's span on the device
+    // inputs that alias the output (a += b passes `a` twice) ride on the output's buffer
+    bool alias_out[NDB_MAX_PARTS] = {false};
+    for (int p = 1; p < n_parts; ++p)
+        alias_out[p] = parts[p].ptr == parts[0].ptr && memcmp(parts[p].dim, parts[0].dim, sizeof(parts[0].dim)) == 0 &&
+                       memcmp(parts[p].stride, parts[0].stride, sizeof(parts[0].stride)) == 0;
+    // mirror every other producer's span on the device
     ndb_view dev[NDB_MAX_PARTS];
     Span span[NDB_MAX_PARTS];
     for (int p = 0; p < n_parts; ++p) {
+        dev[p] = parts[p];
+        if (alias_out[p]) {
+            dev[p].ptr = dev[0].ptr;
+            continue;
+        }
         span[p] = view_span(parts[p]);
         const size_t bytes = (size_t)((span[p].hi - span[p].lo + 1) * esz);
         NDB_TRY(ensure_stage(ctx, p, bytes));
-        dev[p] = parts[p];
         dev[p].ptr = (char *)ctx->stage[p] - span[p].lo * esz;
     }
     const bool out_dense = ndb_view_is_contiguous(&parts[0]) != 0;
-    // inputs that alias the output (a += b passes `a` twice) ride on the output's buffer
-    bool alias_out[NDB_MAX_PARTS] = {false};
-    for (int p = 1; p < n_parts; ++p) {
-        if (parts[p].ptr == parts[0].ptr && memcmp(parts[p].dim, parts[0].dim, sizeof(parts[0].dim)) == 0 &&
-            memcmp(parts[p].stride, parts[0].stride, sizeof(parts[0].stride)) == 0) {
-            alias_out[p] = true;
-            dev[p].ptr = dev[0].ptr;
-        }
-    }
     bool out_is_read = !out_dense;
     for (int p = 1; p < n_parts; ++p) out_is_read |= alias_out[p];
 
@@ -308,6 +389,8 @@ int ndb_zip_host(ndb_ctx *ctx, int op, const void *scalars, int n_parts, const n
     NDB_CUDA(cudaEventRecord(ev_whole, s_in));
     NDB_CUDA(cudaStreamWaitEvent(s_k, ev_whole, 0));
 
+    char *fold_part = nullptr;  // one scalar per slab (8-byte slots)
+    if (redop >= 0) NDB_CUDA(cudaMallocAsync((void **)&fold_part, (size_t)chunks * 8, s_k));
     int status = NDB_OK;
     for (int c = 0; c < chunks && status == NDB_OK; ++c) {
         const int64_t lo = n0 * c / chunks, hi = n0 * (c + 1) / chunks;
@@ -334,6 +417,10 @@ int ndb_zip_host(ndb_ctx *ctx, int op, const void *scalars, int n_parts, const n
         status = make_zip_plan(op, n_parts, dv, &z);
         if (status == NDB_OK) status = zip_launch_plan(ctx, z, scalars);
         if (status != NDB_OK) break;
+        if (redop >= 0) {
+            status = ndb_reduce_all_dev(ctx, redop, &dv[0], fold_part + (size_t)c * esz);
+            if (status != NDB_OK) break;
+        }
         NDB_CUDA(cudaEventRecord(ev_k[c], s_k));
         NDB_CUDA(cudaStreamWaitEvent(s_out, ev_k[c], 0));
         status = copy_view(hv[0], dv[0], cudaMemcpyDeviceToHost, s_out);
@@ -345,12 +432,39 @@ int ndb_zip_host(ndb_ctx *ctx, int op, const void *scalars, int n_parts, const n
         cudaEventDestroy(ev_in[c]);
         cudaEventDestroy(ev_k[c]);
     }
+    if (status == NDB_OK && e1 == cudaSuccess && e2 == cudaSuccess && e3 == cudaSuccess && redop >= 0) {
+        ndb_view pv;
+        memset(&pv, 0, sizeof(pv));
+        pv.ptr = fold_part;
+        pv.ndim = 1;
+        pv.dtype = parts[0].dtype;
+        pv.dim[0] = chunks;
+        pv.stride[0] = 1;
+        status = ndb_reduce_all(ctx, redop, &pv, fold_out);  // synchronises
+    }
+    if (fold_part) cudaFreeAsync(fold_part, s_k);
     if (status != NDB_OK) return status;
     NDB_CUDA(e1);
     NDB_CUDA(e2);
     NDB_CUDA(e3);
     if (op_can_trap(op, parts[0].dtype)) return check_trap(ctx);
     return NDB_OK;
+}
+
+extern "C" {
+
+int ndb_zip_host(ndb_ctx *ctx, int op, const void *scalars, int n_parts, const ndb_view *parts)
+{
+    return zip_host_impl(ctx, op, scalars, n_parts, parts, -1, nullptr);
+}
+
+int ndb_zip_host_fold(ndb_ctx *ctx, int op, const void *scalars, int n_parts, const ndb_view *parts, int redop, void *out_host)
+{
+    if (!out_host || redop < NDB_RED_SUM || redop > NDB_RED_MAX) {
+        set_error("ndb_zip_host_fold: redop must be sum, product, min or max and the result pointer non-null");
+        return NDB_ERR_INVALID_ARG;
+    }
+    return zip_host_impl(ctx, op, scalars, n_parts, parts, redop, out_host);
 }
 
 }  // extern "C"

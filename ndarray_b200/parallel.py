@@ -62,7 +62,6 @@ class PeerGroup:
     def __init__(self, ctx, dist, slot_bytes: int = 1 << 20):
         self.ctx, self.rank, self.world = ctx, dist.get_rank(), dist.get_world_size()
         self._dist = dist
-        self._fused_ok = {}  # (shape, strides, dtype, redop) -> all ranks can take ndb_reduce_axis_peer
         # Collective-safe construction: a failure on ONE rank (IPC not permitted, out of memory) must not leave the others
         # waiting in a collective, so every step's outcome is exchanged and all ranks raise together.
         handle = (C.c_ubyte * 64)()
@@ -111,25 +110,16 @@ class PeerGroup:
 
 def _fused_axis0(local: Array, redop: int, ddof: float, n_global: int, peers: "PeerGroup"):
     """ndb_reduce_axis_peer along Axis(0): the whole sharded reduction (local column reduction, exchange of the per-tile
-    states through peer memory, rank-ordered merge, finalisation with the global length) in ONE launch.  Returns None
-    when the library rules the layout out (shape-derived, so every rank gets the same answer)."""
+    states through peer memory, rank-ordered merge, finalisation with the global length) in ONE cooperative launch.
+    Returns None when the library rules the layout out.  The library's rule uses only quantities that are the same on
+    every rank for shards of one global array (kept shape, strides, dtype, op, n_global, window size, SM count): a
+    rank-local accident - a shard that starts off a 16-byte boundary, holds a single row or is empty - changes how that
+    rank loads its rows, never whether it takes part, so no cross-rank vote is needed and no rank can be left waiting."""
     from . import _ffi
     out = Array.uninit(local.shape[1:], local.dtype, ctx=local.ctx)
-    # agree ONCE per (shape, strides, dtype, op) that every rank takes the fused path: a rank that fell back while the
-    # others wait inside the kernel would only be caught by the watchdog
-    key = (tuple(local.shape[1:]), tuple(local.strides), str(local.dtype), int(redop))
-    agreed = peers._fused_ok.get(key)
-    if agreed is None:
-        mine = lib().ndb_reduce_axis_peer_ok(local.ctx.handle, redop, 0, C.byref(local.v), C.byref(out.v), float(ddof), int(n_global)) == 0
-        votes = [None] * peers.world
-        peers._dist.all_gather_object(votes, bool(mine))
-        agreed = all(votes)
-        peers._fused_ok[key] = agreed
-    if not agreed:
-        return None
     st = lib().ndb_reduce_axis_peer(local.ctx.handle, redop, 0, C.byref(local.v), C.byref(out.v), float(ddof), int(n_global))
     if st == _ffi.ERR_UNSUPPORTED:
-        raise _ffi.NdbError(st, "fused sharded reduction refused after all ranks had agreed on it")
+        return None
     check(st)
     return out
 
@@ -153,11 +143,13 @@ def global_sum(local: Array, dist=None, peers: PeerGroup | None = None):
     return out.to_numpy()[()]
 
 
-def sum_axis0(local: Array, dist=None, peers: PeerGroup | None = None) -> Array:
+def sum_axis0(local: Array, dist=None, peers: PeerGroup | None = None, n_global: int | None = None) -> Array:
     """sum_axis(Axis(0)) when axis 0 is the sharded axis: local partial vector, then all-reduce(sum) — one peer-memory
-    exchange kernel with a PeerGroup, NCCL otherwise."""
-    if peers is not None and peers.world > 1 and local.shape[0] > 0:
-        fused = _fused_axis0(local, Red.SUM, 0.0, local.shape[0], peers)
+    exchange kernel with a PeerGroup, NCCL otherwise.  With the GLOBAL axis length the whole thing is one fused launch;
+    whether that path is taken is decided from n_global and the (rank-invariant) layout only, never from this rank's own
+    row count, so ranks cannot diverge."""
+    if peers is not None and peers.world > 1 and n_global is not None and n_global > 0:
+        fused = _fused_axis0(local, Red.SUM, 0.0, n_global, peers)
         if fused is not None:
             return fused
     part = local.sum_axis(0)
@@ -171,11 +163,11 @@ def sum_axis0(local: Array, dist=None, peers: PeerGroup | None = None) -> Array:
 
 def mean_axis0(local: Array, n_global: int, dist=None, peers: PeerGroup | None = None) -> Array:
     """mean_axis(Axis(0)): divide by the GLOBAL length after the all-reduce (impl_numeric.rs:342-355)."""
-    if peers is not None and peers.world > 1 and n_global >= peers.world and local.dtype.kind == "f":
+    if peers is not None and peers.world > 1 and n_global > 0 and local.dtype.kind == "f":
         fused = _fused_axis0(local, Red.MEAN, 0.0, n_global, peers)
         if fused is not None:
             return fused
-    s = sum_axis0(local, dist, peers)
+    s = sum_axis0(local, dist, peers, n_global)
     s /= local.dtype.type(n_global)
     return s
 
@@ -186,7 +178,7 @@ def var_axis0(local: Array, ddof: float, dist=None, want_std: bool = False, peer
     PeerGroup and the global axis length the whole thing is one launch (ndb_reduce_axis_peer)."""
     import torch
     shape = local.shape[1:]
-    if peers is not None and peers.world > 1 and n_global is not None and n_global >= peers.world:
+    if peers is not None and peers.world > 1 and n_global is not None and n_global > 0:
         fused = _fused_axis0(local, Red.STD if want_std else Red.VAR, ddof, n_global, peers)
         if fused is not None:
             return fused

@@ -1057,6 +1057,152 @@ extern "C" int orc_cast(const orc_view *out, const orc_view *in)
     return ORC_UNSUPPORTED;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Synthetic data + BASELINE config 5 (2^32-element f32 `a = b*c + a`, then `a.sum()`).
+//
+// The counter generator is the harness's, not ndarray's: value(seed, i) is a pure function of the flat index so that any
+// shard of a logical array can be regenerated anywhere (same definition as ndarray_b200/csrc/rng.cu, restated here).
+static inline uint64_t counter_hash(uint64_t seed, uint64_t i)
+{
+    uint64_t z = seed + (i + 1) * 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+static inline float counter_f32(uint64_t seed, uint64_t i) { return (float)(uint32_t)(counter_hash(seed, i) >> 40) * 0x1p-23f - 1.0f; }
+static inline double counter_f64(uint64_t seed, uint64_t i) { return (double)(counter_hash(seed, i) >> 11) * 0x1p-52 - 1.0; }
+
+extern "C" int orc_counter_fill(void *dst, int dtype, int64_t n, uint64_t seed, uint64_t first, int threads)
+{
+    const int nt = threads > 0 ? threads : 1;
+    switch (dtype) {
+    case F32:
+#pragma omp parallel for num_threads(nt) schedule(static)
+        for (int64_t i = 0; i < n; ++i) ((float *)dst)[i] = counter_f32(seed, first + (uint64_t)i);
+        return ORC_OK;
+    case F64:
+#pragma omp parallel for num_threads(nt) schedule(static)
+        for (int64_t i = 0; i < n; ++i) ((double *)dst)[i] = counter_f64(seed, first + (uint64_t)i);
+        return ORC_OK;
+    case I32:
+#pragma omp parallel for num_threads(nt) schedule(static)
+        for (int64_t i = 0; i < n; ++i) ((int32_t *)dst)[i] = (int32_t)(uint32_t)(counter_hash(seed, first + (uint64_t)i) >> 32);
+        return ORC_OK;
+    case I64:
+#pragma omp parallel for num_threads(nt) schedule(static)
+        for (int64_t i = 0; i < n; ++i) ((int64_t *)dst)[i] = (int64_t)counter_hash(seed, first + (uint64_t)i);
+        return ORC_OK;
+    }
+    return ORC_UNSUPPORTED;
+}
+
+// The parallel global sum ndarray users write, tests/par_rayon.rs:19 (and benches/par_rayon.rs):
+//     a.axis_iter(Axis(0)).into_par_iter().map(|row| row.sum()).sum()
+// every row's sum() is the 8-lane unrolled_fold (impl_numeric.rs:32-47 -> numeric_util.rs:14-51); rayon's `sum()` adds
+// the row sums inside each task left to right and merges the tasks' subtotals in a tree whose shape is unspecified -
+// restated as a static split into `threads` blocks of rows, subtotals added in block order.
+template <typename T>
+static int par_row_sum_typed(const orc_view *v, int threads, void *out)
+{
+    if (v->ndim != 2) return ORC_UNSUPPORTED;
+    const int64_t rows = v->dim[0], cols = v->dim[1];
+    const int nt = (int)std::max<int64_t>(1, std::min<int64_t>(threads, rows));
+    std::vector<T> sub((size_t)nt, (T)0);
+#pragma omp parallel for num_threads(nt) schedule(static)
+    for (int t = 0; t < nt; ++t) {
+        const int64_t lo = rows * t / nt, hi = rows * (t + 1) / nt;
+        T acc = (T)0;
+        for (int64_t r = lo; r < hi; ++r) {
+            const T *row = (const T *)v->ptr + r * v->stride[0];
+            T part;
+            if (cols <= 1 || v->stride[1] == 1) {
+                part = unrolled_fold<T>(row, cols, (T)0, [](T a, T b) { return wadd(a, b); });
+            } else {
+                part = (T)0;
+                for (int64_t i = 0; i < cols; ++i) part = wadd(part, row[i * v->stride[1]]);
+            }
+            acc = wadd(acc, part);
+        }
+        sub[(size_t)t] = acc;
+    }
+    T total = (T)0;
+    for (int t = 0; t < nt; ++t) total = wadd(total, sub[(size_t)t]);
+    *(T *)out = total;
+    return ORC_OK;
+}
+
+extern "C" int orc_par_row_sum(const orc_view *v, int threads, void *out)
+{
+    switch (v->dtype) {
+    case F32: return par_row_sum_typed<float>(v, threads, out);
+    case F64: return par_row_sum_typed<double>(v, threads, out);
+    case I32: return par_row_sum_typed<int32_t>(v, threads, out);
+    case I64: return par_row_sum_typed<int64_t>(v, threads, out);
+    }
+    return ORC_UNSUPPORTED;
+}
+
+// Config 5 without materialising 48 GiB: for the flat indices [first, first + n) of a = counter(seed_a), b, c this
+// regenerates the inputs on the fly and returns
+//   sum_f64      sum of fl32(fl32(b*c) + a) accumulated in f64 (error ~1e-16 * n: the tolerance oracle for ANY summation order)
+//   abs_f64      sum of |a'|                                   (scale for the relative tolerance)
+//   sum_ndarray  (only if want_ndarray_order) what ndarray's own `a.sum()` returns in f32: ONE unrolled_fold over the whole
+//                block in memory order, i.e. eight interleaved sequential chains (numeric_util.rs:14-51).  The chains are
+//                independent until the final combine, so each runs on its own thread - same result, 8x sooner.
+extern "C" int orc_c5_sums(uint64_t seed_a, uint64_t seed_b, uint64_t seed_c, uint64_t first, int64_t n, int threads,
+                           double *sum_f64, double *abs_f64, int want_ndarray_order, float *sum_ndarray)
+{
+    const int nt = threads > 0 ? threads : 1;
+    double s = 0.0, sa = 0.0;
+#pragma omp parallel for num_threads(nt) schedule(static) reduction(+ : s, sa)
+    for (int64_t i = 0; i < n; ++i) {
+        const uint64_t g = first + (uint64_t)i;
+        const float prod = counter_f32(seed_b, g) * counter_f32(seed_c, g);
+        const float v = prod + counter_f32(seed_a, g);
+        s += (double)v;
+        sa += fabs((double)v);
+    }
+    *sum_f64 = s;
+    *abs_f64 = sa;
+    if (want_ndarray_order && sum_ndarray) {
+        float p[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        const int64_t groups = n / 8;
+#pragma omp parallel for num_threads(nt < 8 ? nt : 8) schedule(static, 1)
+        for (int lane = 0; lane < 8; ++lane) {
+            float acc = 0.f;
+            for (int64_t k = 0; k < groups; ++k) {
+                const uint64_t g = first + (uint64_t)(k * 8 + lane);
+                const float prod = counter_f32(seed_b, g) * counter_f32(seed_c, g);
+                acc = acc + (prod + counter_f32(seed_a, g));
+            }
+            p[lane] = acc;
+        }
+        float acc = 0.f;
+        acc = acc + (p[0] + p[4]);
+        acc = acc + (p[1] + p[5]);
+        acc = acc + (p[2] + p[6]);
+        acc = acc + (p[3] + p[7]);
+        for (int64_t i = groups * 8; i < n; ++i) {
+            const uint64_t g = first + (uint64_t)i;
+            const float prod = counter_f32(seed_b, g) * counter_f32(seed_c, g);
+            acc = acc + (prod + counter_f32(seed_a, g));
+        }
+        *sum_ndarray = acc;
+    }
+    return ORC_OK;
+}
+
+// threads this process may run on (sched affinity), whatever OMP_NUM_THREADS says: torchrun exports OMP_NUM_THREADS=1
+// to every rank, which would silently turn the multi-threaded CPU arm into a single-threaded one
+extern "C" int orc_hw_threads(void)
+{
+#ifdef _OPENMP
+    return omp_get_num_procs();
+#else
+    return 1;
+#endif
+}
+
 extern "C" int orc_max_threads(void)
 {
 #ifdef _OPENMP

@@ -169,7 +169,44 @@ def zip_prefer_f(inputs) -> bool:
 
 
 def max_threads() -> int:
-    return lib().orc_max_threads()
+    """Host threads the CPU arm may use: the cores this process is allowed on.  Deliberately NOT omp_get_max_threads():
+    torchrun exports OMP_NUM_THREADS=1 to every rank; the oracle's parallel loops carry explicit num_threads clauses."""
+    import os
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    return max(1, min(n, lib().orc_hw_threads()))
+
+
+def counter_fill(out: np.ndarray, seed: int, first: int = 0, threads: int = 1) -> np.ndarray:
+    """out.flat[j] = value(seed, first + j): the harness's index-addressable generator (csrc/rng.cu)."""
+    assert out.flags.c_contiguous
+    st = lib().orc_counter_fill(C.c_void_p(out.ctypes.data), DTYPES[out.dtype], C.c_int64(out.size), C.c_uint64(seed),
+                                C.c_uint64(first), threads)
+    if st:
+        raise RuntimeError(f"oracle status {st}")
+    return out
+
+
+def par_row_sum(a: np.ndarray, threads: int = 1):
+    """a.axis_iter(Axis(0)).into_par_iter().map(|r| r.sum()).sum()  (tests/par_rayon.rs:19)."""
+    out = np.zeros((), dtype=a.dtype)
+    v = view(a)
+    st = lib().orc_par_row_sum(C.byref(v), threads, C.c_void_p(out.ctypes.data))
+    if st:
+        raise RuntimeError(f"oracle status {st}")
+    return out[()]
+
+
+def c5_sums(seed_a: int, seed_b: int, seed_c: int, first: int, n: int, threads: int = 1, ndarray_order: bool = False):
+    """Config 5 from the counter generator, nothing materialised: (sum in f64, sum of |.| in f64, ndarray-order f32 sum|None)."""
+    s, sa, f = C.c_double(), C.c_double(), C.c_float()
+    st = lib().orc_c5_sums(C.c_uint64(seed_a), C.c_uint64(seed_b), C.c_uint64(seed_c), C.c_uint64(first), C.c_int64(n), threads,
+                           C.byref(s), C.byref(sa), int(ndarray_order), C.byref(f))
+    if st:
+        raise RuntimeError(f"oracle status {st}")
+    return s.value, sa.value, (np.float32(f.value) if ndarray_order else None)
 
 
 def cast(out: np.ndarray, a: np.ndarray) -> int:

@@ -153,20 +153,55 @@ def test_broadcast_and_reversed_operands(nd):  # tests/oper.rs:427-460
     np.testing.assert_allclose(rev.dot(da).to_numpy(), a[::-1, ::-1] @ a, rtol=1e-12)
 
 
-def test_gemv_and_vec_mat(nd):  # tests/oper.rs:686-790
+def test_gemv_and_vec_mat(nd, oracle):  # tests/oper.rs:686-790
+    """general_mat_vec_mul / mat.dot(vec) / vec.dot(mat) against the ORACLE: ndarray computes a gemv row by row with its
+    1-D dot (impl_linalg.rs:657-743 -> numeric_util.rs:56-93 unrolled_dot), so the reference for y[i] is
+    alpha * orc_dot(a[i, :], x) + beta * y[i] in the element type; tolerance 1e-12 (f64) / 1e-5 (f32) x sqrt(k)."""
     rng = np.random.default_rng(2)
-    for (m, k) in [(10, 10), (17, 15), (64, 130), (300, 77)]:
-        a = rng.standard_normal((m, k))
-        x = rng.standard_normal(k)
-        y0 = rng.standard_normal(m)
-        for order in ("C", "F"):
-            da = nd.Array.from_numpy(np.asfortranarray(a) if order == "F" else a)
-            y = nd.Array.from_numpy(y0)
-            nd.general_mat_vec_mul(-2.3, da, nd.Array.from_numpy(x), math.pi, y)
-            np.testing.assert_allclose(y.to_numpy(), -2.3 * (a @ x) + math.pi * y0, rtol=1e-10, atol=1e-12)
-            np.testing.assert_allclose(da.dot(nd.Array.from_numpy(x)).to_numpy(), a @ x, rtol=1e-10, atol=1e-12)
-            v = rng.standard_normal(m)
-            np.testing.assert_allclose(nd.Array.from_numpy(v).dot(da).to_numpy(), v @ a, rtol=1e-10, atol=1e-12)
+    for dt, tol in ((np.float64, 1e-12), (np.float32, 1e-5)):
+        for (m, k) in [(10, 10), (17, 15), (64, 130), (300, 77)]:
+            a = rng.standard_normal((m, k)).astype(dt)
+            x = rng.standard_normal(k).astype(dt)
+            y0 = rng.standard_normal(m).astype(dt)
+            v = rng.standard_normal(m).astype(dt)
+            ax = np.array([oracle.dot(np.ascontiguousarray(a[i]), x) for i in range(m)], dtype=dt)
+            va = np.array([oracle.dot(v, np.ascontiguousarray(a[:, j])) for j in range(k)], dtype=dt)
+            want_y = dt(-2.3) * ax + dt(math.pi) * y0
+            lim = tol * np.sqrt(k) * max(1.0, np.abs(want_y).max())
+            for order in ("C", "F"):
+                da = nd.Array.from_numpy(np.asfortranarray(a) if order == "F" else a)
+                y = nd.Array.from_numpy(y0)
+                nd.general_mat_vec_mul(-2.3, da, nd.Array.from_numpy(x), math.pi, y)
+                assert np.abs(y.to_numpy() - want_y).max() <= lim, (dt, m, k, order)
+                assert np.abs(da.dot(nd.Array.from_numpy(x)).to_numpy() - ax).max() <= lim
+                assert np.abs(nd.Array.from_numpy(v).dot(da).to_numpy() - va).max() <= tol * np.sqrt(m) * max(1.0, np.abs(va).max())
+
+
+def test_dot_1d_against_the_oracle(nd, oracle):
+    """1-D dot (impl_linalg.rs:74-133): the oracle restates unrolled_dot's 8-lane association; integers are exact,
+    floats agree within 1e-12 / 1e-5 x sqrt(n) of the sum of |products|/n (summation order differs)."""
+    rng = np.random.default_rng(12)
+    for n in (0, 1, 7, 8, 1000, 100003):
+        for dt in (np.float64, np.float32, np.int32, np.int64):
+            if np.dtype(dt).kind == "i":
+                x = rng.integers(-2 ** 20, 2 ** 20, n).astype(dt)
+                y = rng.integers(-2 ** 20, 2 ** 20, n).astype(dt)
+            else:
+                x, y = rng.standard_normal(n).astype(dt), rng.standard_normal(n).astype(dt)
+            dx, dy = nd.Array.from_numpy(x), nd.Array.from_numpy(y)
+            cases = [(x, y, dx, dy), (x[::-1], y, dx.slice(nd.s_[::-1]), dy)]
+            if n > 1:
+                h = len(x[::2])
+                cases.append((x[::2], y[1::2] if len(y[1::2]) == h else y[:h], dx.slice(nd.s_[::2]),
+                              dy.slice(nd.s_[1::2]) if len(y[1::2]) == h else dy.slice(nd.s_[:h])))
+            for hx, hy, vx, vy in cases:
+                got = vx.dot(vy)
+                want = oracle.dot(np.ascontiguousarray(hx), np.ascontiguousarray(hy))
+                if np.dtype(dt).kind == "i":
+                    assert got == want, (n, dt)
+                else:
+                    tol = (1e-12 if dt == np.float64 else 1e-5) * np.sqrt(max(n, 1)) * max(1e-30, float(np.abs(hx * hy).mean()) if n else 1.0)
+                    assert abs(float(got) - float(want)) <= tol, (n, dt, got, want)
 
 
 def test_cblas_dropin_symbols(nd):

@@ -455,3 +455,60 @@ def test_gemm_kahan_reference_is_tighter():  # accuracy.rs:143-165
     e0 = np.abs(c0 - exact).max() / np.abs(exact).max()
     e1 = np.abs(c1 - exact).max() / np.abs(exact).max()
     assert e1 <= e0 and e0 < 1e-5
+
+
+# ---- round 2: the config-5 helpers ------------------------------------------------------------------------------
+def test_counter_generator_is_index_addressable():
+    """value(seed, i) is a pure function of the flat index: any split of a stream reproduces the whole; known answers
+    pin the definition (splitmix64 output i, top 24 / 53 bits) so the device kernel and the oracle cannot drift together."""
+    whole = orc.counter_fill(np.empty(1000, np.float32), 0x5EED0001, 0, 3)
+    parts = [orc.counter_fill(np.empty(n, np.float32), 0x5EED0001, first, 1) for first, n in ((0, 1), (1, 332), (333, 667))]
+    assert np.array_equal(np.concatenate(parts), whole)
+    assert whole.min() >= -1.0 and whole.max() < 1.0
+
+    def splitmix(seed, i):
+        m = (1 << 64) - 1
+        z = (seed + (i + 1) * 0x9E3779B97F4A7C15) & m
+        z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & m
+        z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & m
+        return z ^ (z >> 31)
+
+    for i in (0, 1, 999):
+        h = splitmix(0x5EED0001, i)
+        assert whole[i] == np.float32((h >> 40) * 2.0 ** -23 - 1.0)
+    f64 = orc.counter_fill(np.empty(4, np.float64), 7, 2 ** 40, 1)
+    assert f64[3] == (splitmix(7, 2 ** 40 + 3) >> 11) * 2.0 ** -52 - 1.0
+    i64 = orc.counter_fill(np.empty(4, np.int64), 7, 5, 1)
+    assert int(i64[2]) == (splitmix(7, 7) ^ (1 << 63)) - (1 << 63)
+    i32 = orc.counter_fill(np.empty(4, np.int32), 7, 5, 1)
+    assert int(i32[2]) == ((splitmix(7, 7) >> 32) ^ (1 << 31)) - (1 << 31)
+
+
+def test_parallel_row_sum_idiom():
+    """a.axis_iter(Axis(0)).into_par_iter().map(|x| x.sum()).sum() (tests/par_rayon.rs:12-24): integers equal the plain
+    sum exactly, floats agree with it within rounding, whatever the thread count; tests/par_rayon.rs' own case (M x N
+    array whose row i is filled with i) gives N * sum(i)."""
+    m, n = 1024 // 4, 100
+    a = np.zeros((m, n), np.float64)
+    for i in range(m):
+        a[i] = i
+    for t in (1, 2, 5):
+        assert orc.par_row_sum(a, t) == n * (m * (m - 1) // 2)
+    rng = np.random.default_rng(4)
+    ai = rng.integers(-2 ** 62, 2 ** 62, (37, 21), dtype=np.int64)
+    with np.errstate(over="ignore"):
+        assert orc.par_row_sum(ai, 3) == ai.sum(dtype=np.int64) == orc.reduce_all(0, ai)
+    af = rng.standard_normal((64, 333)).astype(np.float32)
+    assert abs(float(orc.par_row_sum(af, 4)) - af.astype(np.float64).sum()) < 1e-3
+    assert abs(float(orc.par_row_sum(af[:, ::3], 4)) - af[:, ::3].astype(np.float64).sum()) < 1e-3
+
+
+def test_config5_streaming_sums_match_the_materialised_form():
+    """orc_c5_sums regenerates a, b, c on the fly: its f64 sum equals the f64 sum of the oracle's materialised
+    a = b*c + a, and its ndarray-order f32 sum equals orc_reduce_all (ndarray's own `a.sum()`) bit for bit."""
+    n = 8 * 1000 + 5
+    a, b, c = (orc.counter_fill(np.empty(n, np.float32), s, 77, 2) for s in (1, 2, 3))
+    assert orc.zip_(7, a, [b, c, a]) == 0
+    s, sa, f = orc.c5_sums(1, 2, 3, 77, n, 3, True)
+    assert abs(s - a.astype(np.float64).sum()) < 1e-9 and abs(sa - np.abs(a.astype(np.float64)).sum()) < 1e-9
+    assert f == orc.reduce_all(0, a)
