@@ -118,7 +118,7 @@ def test_zip_fold_associative_accumulators(nd, oracle):
                 assert z.fold(None, op, "min") == v.min()
                 assert z.fold(None, op, "max") == v.max()
                 assert z.fold(dtype(7), op, "max") == max(dtype(7), v.max())
-                assert z.fold(dtype(-1000), op, "min") == -1000
+                assert z.fold(dtype(-100000), op, "min") == -100000
                 got = z.fold(dtype(5), op, "sum")
                 if kind == "i":
                     assert got == dtype(5) + v.sum(dtype=dtype)
