@@ -36,6 +36,7 @@ __device__ __forceinline__ TO cast_one(TI x)
 template <typename TO, typename TI>
 __global__ void __launch_bounds__(256) cast_rows(CastArgs a)
 {
+    pdl_enter();
     const int TX = blockDim.x, TY = blockDim.y;
     for (int64_t vb = blockIdx.x; vb < a.total_blocks; vb += gridDim.x) {
         int64_t t = vb;
@@ -76,7 +77,7 @@ int launch_cast(ndb_ctx *ctx, CastArgs &a)
     for (int k = 0; k < a.n_batch; ++k) batches *= a.bdim[k];
     a.total_blocks = a.blocks_inner * a.blocks_rows * batches;
     const unsigned blocks = (unsigned)std::min<int64_t>(a.total_blocks, (int64_t)1 << 30);
-    cast_rows<TO, TI><<<blocks, dim3(tx, ty, 1), 0, ctx->stream>>>(a);
+    launch_pdl(cast_rows<TO, TI>, blocks, dim3(tx, ty, 1), 0, ctx->stream, a);
     NDB_CHECK_LAUNCH();
     return NDB_OK;
 }

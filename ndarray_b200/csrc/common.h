@@ -54,6 +54,40 @@ inline size_t dtype_size(int dt)
 
 inline bool dtype_is_float(int dt) { return dt == NDB_F32 || dt == NDB_F64; }
 
+// ---- programmatic dependent launch ---------------------------------------------------------------------------------
+// Back-to-back kernels in one stream are spaced by ~3-4 us on these boxes (an EMPTY kernel sustains one launch per
+// 3.9 us; benchmarks/micro/launch_gap.cu): more than a third of a 10 us reduction.  Every streaming kernel therefore
+// begins with pdl_enter() and is launched through launch_pdl(): the next kernel's blocks are scheduled while this one's
+// last wave drains, and block at griddepcontrol.wait until this grid has completed and flushed, so stream order is kept
+// exactly (64 MiB cold read, 12 in a row: 13.0 -> 11.75 us per kernel).  A kernel launched without the attribute, or after
+// a memcpy / event, sees the usual full serialisation; pdl_enter() is then a no-op.  NDB_NO_PDL=1 turns the attribute off.
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_enter()
+{
+    asm volatile("griddepcontrol.launch_dependents;");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
+bool pdl_enabled();
+
+template <typename... KArgs, typename... Args>
+inline void launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args)
+{
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    (void)cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);  // errors surface through cudaGetLastError (NDB_CHECK_LAUNCH)
+}
+#endif
+
 // number of *input* producers an op consumes (ADD_N: variable, returns -1)
 int op_arity(int op);
 // number of scalars the op reads

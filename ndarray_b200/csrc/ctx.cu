@@ -23,6 +23,12 @@ void set_error(const char *fmt, ...)
 
 void clear_error() { tl_error[0] = 0; }
 
+bool pdl_enabled()
+{
+    static const bool on = getenv("NDB_NO_PDL") == nullptr;
+    return on;
+}
+
 int op_arity(int op)
 {
     switch (op) {

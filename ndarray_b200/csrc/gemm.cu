@@ -27,6 +27,7 @@ __device__ __forceinline__ T mul_add(T a, T b, T c)
 template <typename T>
 __global__ void __launch_bounds__(256) gemm_any(GemmArgs g, T alpha, T beta)
 {
+    pdl_enter();
     constexpr int BM = 64, BN = 64, BK = 16;
     __shared__ T As[BK][BM + 1];
     __shared__ T Bs[BK][BN + 1];
@@ -114,6 +115,7 @@ struct GemvArgs {
 template <typename T>
 __global__ void __launch_bounds__(256) gemv_rows(GemvArgs g, T alpha, T beta)
 {
+    pdl_enter();
     const int lane = threadIdx.x & 31;
     const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
     if (row >= g.m) return;
@@ -142,6 +144,7 @@ __global__ void __launch_bounds__(256) gemv_rows(GemvArgs g, T alpha, T beta)
 template <typename T>
 __global__ void __launch_bounds__(256) gemv_rows_vec(GemvArgs g, T alpha, T beta)
 {
+    pdl_enter();
     using V = Vec128<T>;
     constexpr int N = V::N;
     const int lane = threadIdx.x & 31;
@@ -183,6 +186,7 @@ __global__ void __launch_bounds__(256) gemv_rows_vec(GemvArgs g, T alpha, T beta
 template <typename T>
 __global__ void __launch_bounds__(256) gemv_cols_split(GemvArgs g, int splits, T *partial)
 {
+    pdl_enter();
     const int64_t row = (int64_t)blockIdx.x * 256 + threadIdx.x;
     if (row >= g.m) return;
     const int64_t chunk = (g.k + splits - 1) / splits;
@@ -211,6 +215,7 @@ __global__ void __launch_bounds__(256) gemv_cols_split(GemvArgs g, int splits, T
 template <typename T>
 __global__ void __launch_bounds__(256) gemv_cols_split_vec(GemvArgs g, int splits, T *partial)
 {
+    pdl_enter();
     using V = Vec128<T>;
     constexpr int N = V::N;
     const int64_t row = ((int64_t)blockIdx.x * 256 + threadIdx.x) * N;
@@ -247,6 +252,7 @@ __global__ void __launch_bounds__(256) gemv_cols_split_vec(GemvArgs g, int split
 template <typename T>
 __global__ void __launch_bounds__(256) gemv_cols_finish(GemvArgs g, int splits, const T *partial, T alpha, T beta)
 {
+    pdl_enter();
     const int64_t row = (int64_t)blockIdx.x * 256 + threadIdx.x;
     if (row >= g.m) return;
     T r = partial[row];
@@ -263,8 +269,8 @@ static int gemv_launch(ndb_ctx *ctx, const GemvArgs &g, T alpha, T beta)
     if (llabs(g.csa) <= llabs(g.rsa) || g.m < 2048) {
         const bool vec = g.csa == 1 && g.sx == 1 && g.k % N == 0 && g.k >= 4 * N && g.rsa % N == 0 &&
                          ((uintptr_t)g.a % 16) == 0 && ((uintptr_t)g.x % 16) == 0;
-        if (vec) gemv_rows_vec<T><<<(unsigned)((g.m + 7) / 8), 256, 0, ctx->stream>>>(g, alpha, beta);
-        else gemv_rows<T><<<(unsigned)((g.m + 7) / 8), 256, 0, ctx->stream>>>(g, alpha, beta);
+        if (vec) launch_pdl(gemv_rows_vec<T>, (unsigned)((g.m + 7) / 8), 256, 0, ctx->stream, g, alpha, beta);
+        else launch_pdl(gemv_rows<T>, (unsigned)((g.m + 7) / 8), 256, 0, ctx->stream, g, alpha, beta);
         NDB_CHECK_LAUNCH();
         return NDB_OK;
     }
@@ -274,10 +280,10 @@ static int gemv_launch(ndb_ctx *ctx, const GemvArgs &g, T alpha, T beta)
                                                                                   std::max<int64_t>(1, g.k / 64)), 1024));
     NDB_TRY(ensure_workspace(ctx, (size_t)splits * (size_t)g.m * sizeof(T)));
     dim3 grid((unsigned)row_blocks, (unsigned)splits, 1);
-    if (cvec) gemv_cols_split_vec<T><<<grid, 256, 0, ctx->stream>>>(g, splits, (T *)ctx->workspace);
-    else gemv_cols_split<T><<<grid, 256, 0, ctx->stream>>>(g, splits, (T *)ctx->workspace);
+    if (cvec) launch_pdl(gemv_cols_split_vec<T>, grid, 256, 0, ctx->stream, g, splits, (T *)ctx->workspace);
+    else launch_pdl(gemv_cols_split<T>, grid, 256, 0, ctx->stream, g, splits, (T *)ctx->workspace);
     NDB_CHECK_LAUNCH();
-    gemv_cols_finish<T><<<(unsigned)((g.m + 255) / 256), 256, 0, ctx->stream>>>(g, splits, (const T *)ctx->workspace, alpha, beta);
+    launch_pdl(gemv_cols_finish<T>, (unsigned)((g.m + 255) / 256), 256, 0, ctx->stream, g, splits, (const T *)ctx->workspace, alpha, beta);
     NDB_CHECK_LAUNCH();
     return NDB_OK;
 }
@@ -286,6 +292,7 @@ static int gemv_launch(ndb_ctx *ctx, const GemvArgs &g, T alpha, T beta)
 template <typename T>
 __global__ void __launch_bounds__(256) scale_c(GemmArgs g, T beta)
 {
+    pdl_enter();
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= g.m * g.n) return;
     const int64_t r = i / g.n, c = i - r * g.n;
@@ -297,7 +304,7 @@ template <typename T>
 static int gemm_any_launch(ndb_ctx *ctx, const GemmArgs &g, T alpha, T beta)
 {
     if (g.k == 0) {
-        scale_c<T><<<(unsigned)((g.m * g.n + 255) / 256), 256, 0, ctx->stream>>>(g, beta);
+        launch_pdl(scale_c<T>, (unsigned)((g.m * g.n + 255) / 256), 256, 0, ctx->stream, g, beta);
         NDB_CHECK_LAUNCH();
         return NDB_OK;
     }
@@ -306,7 +313,7 @@ static int gemm_any_launch(ndb_ctx *ctx, const GemmArgs &g, T alpha, T beta)
         set_error("gemm: m = %lld exceeds the fallback kernel's grid", (long long)g.m);
         return NDB_ERR_UNSUPPORTED;
     }
-    gemm_any<T><<<grid, 256, 0, ctx->stream>>>(g, alpha, beta);
+    launch_pdl(gemm_any<T>, grid, 256, 0, ctx->stream, g, alpha, beta);
     NDB_CHECK_LAUNCH();
     return NDB_OK;
 }

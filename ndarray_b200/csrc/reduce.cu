@@ -300,6 +300,7 @@ __device__ __forceinline__ void store_result(const RedArgs &a, const Acc<T, R> &
 template <typename T, int R, int FIN, bool WARP, bool VEC>
 __global__ void __launch_bounds__(256) red_lanes(RedArgs a)
 {
+    pdl_enter();
     using V = Vec128<T>;
     constexpr int N = V::N;
     __shared__ Acc<T, R> smem[32];
@@ -397,6 +398,7 @@ __device__ __forceinline__ A merge_splits(const A *p, int splits, int64_t pitch)
 template <typename T, int R, int FIN, int W, bool PEER = false>
 __global__ void __launch_bounds__(256, R == R_WELFORD ? NDB_RED_COLS_MINB_W : 3) red_cols(RedArgs a)  // 3 CTAs/SM register budget (<= 85): f64 sum 6.52 -> 6.95 TB/s vs the default allocation
 {
+    pdl_enter();
     using V = Vec128<T>;
     static_assert(W == 1 || W == V::N, "W is 1 or one 128-bit vector");
     __shared__ Acc<T, R> smem[8][32 * W + 1];
@@ -547,6 +549,7 @@ __global__ void __launch_bounds__(256, R == R_WELFORD ? NDB_RED_COLS_MINB_W : 3)
 template <typename T, int R, int FIN>
 __global__ void __launch_bounds__(256) red_finish_cols(RedArgs a)
 {
+    pdl_enter();
     const int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (o >= a.n_out) return;
     const Acc<T, R> *p = reinterpret_cast<const Acc<T, R> *>(a.partial);
@@ -560,6 +563,7 @@ __global__ void __launch_bounds__(256) red_finish_cols(RedArgs a)
 template <typename T, int R, int FIN>
 __global__ void __launch_bounds__(256) red_generic(RedArgs a)
 {
+    pdl_enter();
     for (int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; o < a.n_out; o += (int64_t)gridDim.x * blockDim.x) {
         int64_t in_off, out_off, out2_off;
         kept_offsets(a.k, o, in_off, out_off, out2_off);
@@ -587,6 +591,7 @@ struct AllArgs {
 template <typename T, int R>
 __global__ void __launch_bounds__(256) red_all_flat(AllArgs a)
 {
+    pdl_enter();
     using V = Vec128<T>;
     constexpr int N = V::N;
     __shared__ Acc<T, R> smem[32];
@@ -630,6 +635,7 @@ __global__ void __launch_bounds__(256) red_all_flat(AllArgs a)
 template <typename T, int R>
 __global__ void __launch_bounds__(256) red_all_rows(AllArgs a)
 {
+    pdl_enter();
     __shared__ Acc<T, R> smem[32];
     const T *src = reinterpret_cast<const T *>(a.in);
     const int inner = a.ndim - 1;
@@ -667,6 +673,7 @@ __global__ void __launch_bounds__(256) red_all_rows(AllArgs a)
 template <typename T, int R>
 __global__ void __launch_bounds__(256) red_all_finish(const void *partial, int n, T *out, T dof, int want_std)
 {
+    pdl_enter();
     __shared__ Acc<T, R> smem[32];
     const Acc<T, R> *p = reinterpret_cast<const Acc<T, R> *>(partial);
     Acc<T, R> acc;
@@ -690,6 +697,7 @@ __global__ void __launch_bounds__(256) red_all_finish(const void *partial, int n
 template <typename T, int R>
 __global__ void __launch_bounds__(256) red_all_finish_peer(const void *partial, int n, T *out, PeerArgs pa)
 {
+    pdl_enter();
     __shared__ Acc<T, R> smem[32];
     const Acc<T, R> *p = reinterpret_cast<const Acc<T, R> *>(partial);
     Acc<T, R> acc;
@@ -720,6 +728,7 @@ __global__ void __launch_bounds__(256) red_all_finish_peer(const void *partial, 
 template <typename T>
 __global__ void __launch_bounds__(256) dot_partials(const T *x, int64_t sx, const T *y, int64_t sy, int64_t n, void *partial)
 {
+    pdl_enter();
     __shared__ Acc<T, R_SUM> smem[32];
     Acc<T, R_SUM> acc;
     acc.reset();
@@ -742,6 +751,7 @@ __global__ void __launch_bounds__(256) dot_partials(const T *x, int64_t sx, cons
 template <typename T>
 __global__ void __launch_bounds__(256) dot_partials_vec(const T *x, const T *y, int64_t n, void *partial)
 {
+    pdl_enter();
     using V = Vec128<T>;
     constexpr int N = V::N;
     __shared__ Acc<T, R_SUM> smem[32];
@@ -783,6 +793,7 @@ __global__ void __launch_bounds__(256) dot_partials_vec(const T *x, const T *y, 
 template <typename T, int OP, int R>
 __global__ void __launch_bounds__(256) zip2_reduce_flat(const T *x, const T *y, int64_t n, void *partial)
 {
+    pdl_enter();
     using V = Vec128<T>;
     constexpr int N = V::N;
     __shared__ Acc<T, R> smem[32];
@@ -833,9 +844,9 @@ static int zip2_reduce_launch(ndb_ctx *ctx, const void *x, const void *y, int64_
     NDB_TRY(ensure_workspace(ctx, (size_t)max_blocks * sizeof(Acc<T, R>) + 4096));
     void *dev_scalar = (char *)ctx->workspace + ctx->workspace_bytes - 64;
     const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>(max_blocks, (n / Vec128<T>::N + 1023) / 1024));
-    zip2_reduce_flat<T, OP, R><<<blocks, 256, 0, ctx->stream>>>((const T *)x, (const T *)y, n, ctx->workspace);
+    launch_pdl(zip2_reduce_flat<T, OP, R>, blocks, 256, 0, ctx->stream, (const T *)x, (const T *)y, n, ctx->workspace);
     NDB_CHECK_LAUNCH();
-    red_all_finish<T, R><<<1, 256, 0, ctx->stream>>>(ctx->workspace, blocks, (T *)dev_scalar, T(1), 0);
+    launch_pdl(red_all_finish<T, R>, 1, 256, 0, ctx->stream, ctx->workspace, blocks, (T *)dev_scalar, T(1), 0);
     NDB_CHECK_LAUNCH();
     NDB_CUDA(cudaMemcpyAsync(ctx->host_scalar, dev_scalar, sizeof(T), cudaMemcpyDeviceToHost, ctx->stream));
     NDB_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -935,25 +946,25 @@ static int reduce_all_typed(ndb_ctx *ctx, const ndb_view *v, T *out_dev, T dof =
     if (a.ndim == 1 && a.stride[0] == 1) {
         const int64_t nv = a.total / Vec128<T>::N;
         blocks = (int)std::max<int64_t>(1, std::min<int64_t>(max_blocks, (nv + 1023) / 1024));
-        red_all_flat<T, R><<<blocks, 256, 0, ctx->stream>>>(a);
+        launch_pdl(red_all_flat<T, R>, blocks, 256, 0, ctx->stream, a);
     } else {
         const int inner = a.ndim - 1;
         a.inner_chunks = (a.dim[inner] + 1023) / 1024;
         a.n_rows = a.total / a.dim[inner];
         blocks = (int)std::max<int64_t>(1, std::min<int64_t>(max_blocks, a.n_rows * a.inner_chunks));
-        red_all_rows<T, R><<<blocks, 256, 0, ctx->stream>>>(a);
+        launch_pdl(red_all_rows<T, R>, blocks, 256, 0, ctx->stream, a);
     }
     NDB_CHECK_LAUNCH();
     if constexpr (R != R_WELFORD) {
         if (peer) {
             PeerArgs pa;
             NDB_TRY(peer_begin(ctx, 1, sizeof(T), &pa));
-            red_all_finish_peer<T, R><<<1, 256, 0, ctx->stream>>>(a.partial, blocks, out_dev, pa);
+            launch_pdl(red_all_finish_peer<T, R>, 1, 256, 0, ctx->stream, a.partial, blocks, out_dev, pa);
             NDB_CHECK_LAUNCH();
             return NDB_OK;
         }
     }
-    red_all_finish<T, R><<<1, 256, 0, ctx->stream>>>(a.partial, blocks, out_dev, dof, want_std);
+    launch_pdl(red_all_finish<T, R>, 1, 256, 0, ctx->stream, a.partial, blocks, out_dev, dof, want_std);
     NDB_CHECK_LAUNCH();
     return NDB_OK;
 }
@@ -1051,11 +1062,11 @@ static int reduce_axis_launch(ndb_ctx *ctx, RedArgs &a, const ZipPlan &z)
         unsigned blocks = (unsigned)std::min<int64_t>(groups, (int64_t)1 << 30);
         if (getenv("NDB_RED_LANES_BLOCKS")) blocks = std::min<unsigned>(blocks, (unsigned)atoi(getenv("NDB_RED_LANES_BLOCKS")));
         if (warp) {
-            if (vec) red_lanes<T, R, FIN, true, true><<<blocks, 32 * wpb, 0, st>>>(a);
-            else red_lanes<T, R, FIN, true, false><<<blocks, 32 * wpb, 0, st>>>(a);
+            if (vec) launch_pdl(red_lanes<T, R, FIN, true, true>, blocks, 32 * wpb, 0, st, a);
+            else launch_pdl(red_lanes<T, R, FIN, true, false>, blocks, 32 * wpb, 0, st, a);
         } else {
-            if (vec) red_lanes<T, R, FIN, false, true><<<blocks, 256, 0, st>>>(a);
-            else red_lanes<T, R, FIN, false, false><<<blocks, 256, 0, st>>>(a);
+            if (vec) launch_pdl(red_lanes<T, R, FIN, false, true>, blocks, 256, 0, st, a);
+            else launch_pdl(red_lanes<T, R, FIN, false, false>, blocks, 256, 0, st, a);
         }
         NDB_CHECK_LAUNCH();
         return NDB_OK;
@@ -1121,11 +1132,11 @@ static int reduce_axis_launch(ndb_ctx *ctx, RedArgs &a, const ZipPlan &z)
                 return NDB_OK;
             }
         }
-        if (vec) red_cols<T, R, FIN, Vec128<T>::N><<<grid, block, 0, st>>>(a);
-        else red_cols<T, R, FIN, 1><<<grid, block, 0, st>>>(a);
+        if (vec) launch_pdl(red_cols<T, R, FIN, Vec128<T>::N>, grid, block, 0, st, a);
+        else launch_pdl(red_cols<T, R, FIN, 1>, grid, block, 0, st, a);
         NDB_CHECK_LAUNCH();
         if (splits > 1 && a.tickets == nullptr) {
-            red_finish_cols<T, R, FIN><<<(unsigned)((a.n_out + 255) / 256), 256, 0, st>>>(a);
+            launch_pdl(red_finish_cols<T, R, FIN>, (unsigned)((a.n_out + 255) / 256), 256, 0, st, a);
             NDB_CHECK_LAUNCH();
         }
         return NDB_OK;
@@ -1133,7 +1144,7 @@ static int reduce_axis_launch(ndb_ctx *ctx, RedArgs &a, const ZipPlan &z)
     (void)esz;
     (void)z;
     const unsigned blocks = (unsigned)std::min<int64_t>((a.n_out + 255) / 256, (int64_t)1 << 30);
-    red_generic<T, R, FIN><<<blocks, 256, 0, st>>>(a);
+    launch_pdl(red_generic<T, R, FIN>, blocks, 256, 0, st, a);
     NDB_CHECK_LAUNCH();
     return NDB_OK;
 }
@@ -1284,6 +1295,7 @@ template <typename T>
 __global__ void __launch_bounds__(256) welford_merge_kernel(int n_shards, const int64_t *counts, const T *const *means,
                                                             const T *const *m2s, int64_t n_out, T dof, int want_std, T *out)
 {
+    pdl_enter();
     const int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (o >= n_out) return;
     using Rd = Reducer<T, R_WELFORD>;
@@ -1468,13 +1480,13 @@ int ndb_welford_merge(ndb_ctx *ctx, int n_shards, const int64_t *counts, const n
     const unsigned blocks = (unsigned)((n_out + 255) / 256);
     if (out->dtype == NDB_F32) {
         const float dof = (float)total - (float)ddof;
-        welford_merge_kernel<float><<<blocks, 256, 0, ctx->stream>>>(
+        launch_pdl(welford_merge_kernel<float>, blocks, 256, 0, ctx->stream, 
             n_shards, dc, (const float *const *)(dev_tbl + n_shards * sizeof(int64_t)),
             (const float *const *)(dev_tbl + n_shards * (sizeof(int64_t) + sizeof(void *))), n_out, dof, want_std,
             (float *)out->ptr);
     } else {
         const double dof = (double)total - ddof;
-        welford_merge_kernel<double><<<blocks, 256, 0, ctx->stream>>>(
+        launch_pdl(welford_merge_kernel<double>, blocks, 256, 0, ctx->stream, 
             n_shards, dc, (const double *const *)(dev_tbl + n_shards * sizeof(int64_t)),
             (const double *const *)(dev_tbl + n_shards * (sizeof(int64_t) + sizeof(void *))), n_out, dof, want_std,
             (double *)out->ptr);
@@ -1502,11 +1514,11 @@ int ndb_dot(ndb_ctx *ctx, const ndb_view *x, const ndb_view *y, void *out_host)
     const int64_t sx = n > 1 ? x->stride[0] : 1, sy = n > 1 ? y->stride[0] : 1;
     const bool dense = sx == 1 && sy == 1 && ((uintptr_t)x->ptr % 16) == 0 && ((uintptr_t)y->ptr % 16) == 0 && n >= 64;
 #define NDB_DOT(T)                                                                                            \
-    if (dense) dot_partials_vec<T><<<blocks, 256, 0, ctx->stream>>>((const T *)x->ptr, (const T *)y->ptr, n, ctx->workspace); \
-    else dot_partials<T><<<blocks, 256, 0, ctx->stream>>>((const T *)x->ptr, sx, (const T *)y->ptr, sy, n,    \
+    if (dense) launch_pdl(dot_partials_vec<T>, blocks, 256, 0, ctx->stream, (const T *)x->ptr, (const T *)y->ptr, n, ctx->workspace); \
+    else launch_pdl(dot_partials<T>, blocks, 256, 0, ctx->stream, (const T *)x->ptr, sx, (const T *)y->ptr, sy, n,    \
                                                      ctx->workspace);                                         \
     NDB_CHECK_LAUNCH();                                                                                       \
-    red_all_finish<T, R_SUM><<<1, 256, 0, ctx->stream>>>(ctx->workspace, blocks, (T *)dev_scalar, T(1), 0);   \
+    launch_pdl(red_all_finish<T, R_SUM>, 1, 256, 0, ctx->stream, ctx->workspace, blocks, (T *)dev_scalar, T(1), 0);   \
     NDB_CHECK_LAUNCH();
     switch (x->dtype) {
     case NDB_F32: { NDB_DOT(float) } break;

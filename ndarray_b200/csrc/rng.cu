@@ -35,6 +35,7 @@ __device__ __forceinline__ T counter_value(uint64_t seed, uint64_t i)
 template <typename T>
 __global__ void __launch_bounds__(256) counter_fill(T *dst, int64_t n, uint64_t seed, uint64_t first)
 {
+    pdl_enter();
     using V = Vec128<T>;
     constexpr int N = V::N;
     const int64_t nv = n / N;
@@ -80,10 +81,10 @@ extern "C" int ndb_fill_counter_rng(ndb_ctx *ctx, const ndb_view *out, uint64_t 
     const int64_t nv = n / (16 / (int64_t)dtype_size(out->dtype));
     const unsigned blocks = (unsigned)std::max<int64_t>(1, std::min<int64_t>((int64_t)ctx->sm_count * 16, (nv + 255) / 256));
     switch (out->dtype) {
-    case NDB_F32: counter_fill<float><<<blocks, 256, 0, ctx->stream>>>((float *)out->ptr, n, seed, first_index); break;
-    case NDB_F64: counter_fill<double><<<blocks, 256, 0, ctx->stream>>>((double *)out->ptr, n, seed, first_index); break;
-    case NDB_I32: counter_fill<int32_t><<<blocks, 256, 0, ctx->stream>>>((int32_t *)out->ptr, n, seed, first_index); break;
-    case NDB_I64: counter_fill<int64_t><<<blocks, 256, 0, ctx->stream>>>((int64_t *)out->ptr, n, seed, first_index); break;
+    case NDB_F32: launch_pdl(counter_fill<float>, blocks, 256, 0, ctx->stream, (float *)out->ptr, n, seed, first_index); break;
+    case NDB_F64: launch_pdl(counter_fill<double>, blocks, 256, 0, ctx->stream, (double *)out->ptr, n, seed, first_index); break;
+    case NDB_I32: launch_pdl(counter_fill<int32_t>, blocks, 256, 0, ctx->stream, (int32_t *)out->ptr, n, seed, first_index); break;
+    case NDB_I64: launch_pdl(counter_fill<int64_t>, blocks, 256, 0, ctx->stream, (int64_t *)out->ptr, n, seed, first_index); break;
     default: return NDB_ERR_UNSUPPORTED;
     }
     NDB_CHECK_LAUNCH();

@@ -47,6 +47,7 @@ __device__ __forceinline__ int64_t lane_offset(const ScanArgs &a, int64_t lin)
 template <typename T, bool MUL>
 __global__ void __launch_bounds__(256) scan_cols(ScanArgs a)
 {
+    pdl_enter();
     const int64_t lane = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (lane >= a.n_lanes) return;
     T *p = reinterpret_cast<T *>(a.base) + lane_offset(a, lane);
@@ -72,6 +73,7 @@ __global__ void __launch_bounds__(256) scan_cols(ScanArgs a)
 template <typename T, bool MUL>
 __global__ void __launch_bounds__(256) scan_lanes(ScanArgs a)
 {
+    pdl_enter();
     const int lane_id = threadIdx.x & 31;
     const int64_t lane = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
     if (lane >= a.n_lanes) return;
@@ -100,6 +102,7 @@ __global__ void __launch_bounds__(256) scan_lanes(ScanArgs a)
 template <typename T, bool MUL>
 __global__ void __launch_bounds__(256) scan_chunk_totals(ScanArgs a, T *totals, int chunks, int64_t chunk_len)
 {
+    pdl_enter();
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= a.n_lanes * chunks) return;
     const int64_t lane = idx % a.n_lanes, chunk = idx / a.n_lanes;  // neighbouring threads -> neighbouring lanes
@@ -113,6 +116,7 @@ __global__ void __launch_bounds__(256) scan_chunk_totals(ScanArgs a, T *totals, 
 template <typename T, bool MUL>
 __global__ void __launch_bounds__(256) scan_chunk_carries(T *totals, int64_t n_lanes, int chunks)
 {
+    pdl_enter();
     const int64_t lane = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (lane >= n_lanes) return;
     T running = totals[lane];  // carry into chunk 1 = total of chunk 0; chunk 0 itself takes no carry
@@ -126,6 +130,7 @@ __global__ void __launch_bounds__(256) scan_chunk_carries(T *totals, int64_t n_l
 template <typename T, bool MUL>
 __global__ void __launch_bounds__(256) scan_chunk_apply(ScanArgs a, const T *carries, int chunks, int64_t chunk_len)
 {
+    pdl_enter();
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= a.n_lanes * chunks) return;
     const int64_t lane = idx % a.n_lanes, chunk = idx / a.n_lanes;
@@ -150,6 +155,7 @@ __global__ void __launch_bounds__(256) scan_chunk_apply(ScanArgs a, const T *car
 template <typename T, bool MUL>
 __global__ void __launch_bounds__(256) scan_lanes_vec(ScanArgs a)
 {
+    pdl_enter();
     using V = Vec128<T>;
     constexpr int N = V::N;
     const int lane_id = threadIdx.x & 31;
@@ -207,10 +213,10 @@ int scan_dispatch(ndb_ctx *ctx, int op, const ScanArgs &a, bool lanes)
         bool vec = a.s == 1 && ((uintptr_t)a.base % 16) == 0 && a.n >= 2 * VN && !getenv("NDB_SCAN_SCALAR");
         for (int d = 0; d < a.n_kept && vec; ++d) vec = a.kdim[d] == 1 || a.kstride[d] % VN == 0;
         if (vec) {
-            if (mul) scan_lanes_vec<T, true><<<blocks, 256, 0, ctx->stream>>>(a);
-            else scan_lanes_vec<T, false><<<blocks, 256, 0, ctx->stream>>>(a);
-        } else if (mul) scan_lanes<T, true><<<blocks, 256, 0, ctx->stream>>>(a);
-        else scan_lanes<T, false><<<blocks, 256, 0, ctx->stream>>>(a);
+            if (mul) launch_pdl(scan_lanes_vec<T, true>, blocks, 256, 0, ctx->stream, a);
+            else launch_pdl(scan_lanes_vec<T, false>, blocks, 256, 0, ctx->stream, a);
+        } else if (mul) launch_pdl(scan_lanes<T, true>, blocks, 256, 0, ctx->stream, a);
+        else launch_pdl(scan_lanes<T, false>, blocks, 256, 0, ctx->stream, a);
     } else if (a.n >= 512 && a.n_lanes < (int64_t)ctx->sm_count * 512 && !getenv("NDB_SCAN_NO_CHUNKS")) {
         const int64_t target = (int64_t)ctx->sm_count * 2048;  // threads that fill the machine
         int chunks = (int)std::min<int64_t>((target + a.n_lanes - 1) / a.n_lanes, a.n / 64);
@@ -222,18 +228,18 @@ int scan_dispatch(ndb_ctx *ctx, int op, const ScanArgs &a, bool lanes)
         const unsigned blocks = (unsigned)((a.n_lanes * chunks + 255) / 256);
         const unsigned lane_blocks = (unsigned)((a.n_lanes + 255) / 256);
         if (mul) {
-            scan_chunk_totals<T, true><<<blocks, 256, 0, ctx->stream>>>(a, totals, chunks, chunk_len);
-            scan_chunk_carries<T, true><<<lane_blocks, 256, 0, ctx->stream>>>(totals, a.n_lanes, chunks);
-            scan_chunk_apply<T, true><<<blocks, 256, 0, ctx->stream>>>(a, totals, chunks, chunk_len);
+            launch_pdl(scan_chunk_totals<T, true>, blocks, 256, 0, ctx->stream, a, totals, chunks, chunk_len);
+            launch_pdl(scan_chunk_carries<T, true>, lane_blocks, 256, 0, ctx->stream, totals, a.n_lanes, chunks);
+            launch_pdl(scan_chunk_apply<T, true>, blocks, 256, 0, ctx->stream, a, totals, chunks, chunk_len);
         } else {
-            scan_chunk_totals<T, false><<<blocks, 256, 0, ctx->stream>>>(a, totals, chunks, chunk_len);
-            scan_chunk_carries<T, false><<<lane_blocks, 256, 0, ctx->stream>>>(totals, a.n_lanes, chunks);
-            scan_chunk_apply<T, false><<<blocks, 256, 0, ctx->stream>>>(a, totals, chunks, chunk_len);
+            launch_pdl(scan_chunk_totals<T, false>, blocks, 256, 0, ctx->stream, a, totals, chunks, chunk_len);
+            launch_pdl(scan_chunk_carries<T, false>, lane_blocks, 256, 0, ctx->stream, totals, a.n_lanes, chunks);
+            launch_pdl(scan_chunk_apply<T, false>, blocks, 256, 0, ctx->stream, a, totals, chunks, chunk_len);
         }
     } else {
         const unsigned blocks = (unsigned)((a.n_lanes + 255) / 256);
-        if (mul) scan_cols<T, true><<<blocks, 256, 0, ctx->stream>>>(a);
-        else scan_cols<T, false><<<blocks, 256, 0, ctx->stream>>>(a);
+        if (mul) launch_pdl(scan_cols<T, true>, blocks, 256, 0, ctx->stream, a);
+        else launch_pdl(scan_cols<T, false>, blocks, 256, 0, ctx->stream, a);
     }
     NDB_CHECK_LAUNCH();
     return NDB_OK;

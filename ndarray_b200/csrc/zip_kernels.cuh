@@ -238,6 +238,7 @@ struct FlatArgs {
 template <typename T, int OP, int NIN, int UNROLL>
 __global__ void __launch_bounds__(256) zip_flat_vec(FlatArgs<NIN + 1> a, T s0, T s1, int *flag)
 {
+    pdl_enter();
     using V = Vec128<T>;
     constexpr int N = V::N;
     constexpr int NI = NIN > 0 ? NIN : 1;
@@ -308,6 +309,7 @@ struct RowsArgs {
 template <typename T, int OP, int NIN, bool VEC, bool PLAIN, int ITEMS>
 __global__ void __launch_bounds__(256, (NIN <= 3 ? 3 : 1)) zip_rows(RowsArgs<NIN + 1> a, int ci_shift, T s0, T s1, int *flag)
 {
+    pdl_enter();
     using V = Vec128<T>;
     using E = typename std::conditional<VEC, V, T>::type;  // the unit moved per access
     constexpr int N = VEC ? V::N : 1;
@@ -506,6 +508,7 @@ __device__ __forceinline__ void tile_coords(const TileArgs<NP> &a, int64_t vb, i
 template <typename T, int OP, int NIN>
 __global__ void __launch_bounds__(256) zip_tile(TileArgs<NIN + 1> a, T s0, T s1, int *flag)
 {
+    pdl_enter();
     constexpr int TS = TileShape<T>::TS;
     constexpr int PASS = 256 / TS;  // rows (or columns) covered per pass
     constexpr int NI = NIN > 0 ? NIN : 1;
@@ -669,6 +672,7 @@ __device__ __forceinline__ void zip_tile_vec_body(const TileArgs<NIN + 1> &a, T 
 template <typename T, int OP, int NIN, bool STEP2>
 __global__ void __launch_bounds__(256, STEP2 ? NDB_TILE_MINB_STEP2 : (NIN <= 1 ? 6 : (NIN <= 2 ? NDB_TILE_MINB2 : NDB_TILE_MINB3))) zip_tile_vec(TileArgs<NIN + 1> a, T s0, T s1, int *flag)
 {
+    pdl_enter();
     constexpr int TS = TileShape<T>::TS;
     extern __shared__ __align__(16) unsigned char tile_raw[];  // one padded TS x (TS+1) tile per staged producer
     const int64_t full_x = a.nx / TS, full_y = a.ny / TS;
@@ -717,7 +721,7 @@ int launch_zip(ndb_ctx *ctx, const ZipPlan &z, const void *scalars)
             set_error("Zip: %lld elements exceed one launch", (long long)z.total);
             return NDB_ERR_UNSUPPORTED;
         }
-        zip_flat_vec<T, OP, NIN, UNROLL><<<(unsigned)blocks, 256, 0, st>>>(a, s0, s1, ctx->dev_flag);
+        launch_pdl(zip_flat_vec<T, OP, NIN, UNROLL>, (unsigned)blocks, 256, 0, st, a, s0, s1, ctx->dev_flag);
         NDB_CHECK_LAUNCH();
         return NDB_OK;
     }
@@ -765,9 +769,9 @@ int launch_zip(ndb_ctx *ctx, const ZipPlan &z, const void *scalars)
         if (env_int("NDB_TILE_SCALAR", 0)) vec = false;
         int64_t blocks = a.total_tiles < (int64_t)1 << 30 ? a.total_tiles : (int64_t)1 << 30;
         const size_t smem = (size_t)nslot * TS * (TS + 1) * sizeof(T);
-        if (vec && step2) zip_tile_vec<T, OP, NIN, true><<<(unsigned)blocks, 256, smem, st>>>(a, s0, s1, ctx->dev_flag);
-        else if (vec) zip_tile_vec<T, OP, NIN, false><<<(unsigned)blocks, 256, smem, st>>>(a, s0, s1, ctx->dev_flag);
-        else zip_tile<T, OP, NIN><<<(unsigned)blocks, 256, smem, st>>>(a, s0, s1, ctx->dev_flag);
+        if (vec && step2) launch_pdl(zip_tile_vec<T, OP, NIN, true>, (unsigned)blocks, 256, smem, st, a, s0, s1, ctx->dev_flag);
+        else if (vec) launch_pdl(zip_tile_vec<T, OP, NIN, false>, (unsigned)blocks, 256, smem, st, a, s0, s1, ctx->dev_flag);
+        else launch_pdl(zip_tile<T, OP, NIN>, (unsigned)blocks, 256, smem, st, a, s0, s1, ctx->dev_flag);
         NDB_CHECK_LAUNCH();
         return NDB_OK;
     }
@@ -817,9 +821,9 @@ int launch_zip(ndb_ctx *ctx, const ZipPlan &z, const void *scalars)
         int64_t blocks = a.total_blocks < (int64_t)1 << 30 ? a.total_blocks : (int64_t)1 << 30;
         dim3 bd(tx, ty, 1);
         const unsigned gb = (unsigned)blocks;
-        if (vec && plain) zip_rows<T, OP, NIN, true, true, ITEMS><<<gb, bd, 0, st>>>(a, ci_shift, s0, s1, ctx->dev_flag);
-        else if (vec) zip_rows<T, OP, NIN, true, false, ITEMS><<<gb, bd, 0, st>>>(a, ci_shift, s0, s1, ctx->dev_flag);
-        else zip_rows<T, OP, NIN, false, false, ITEMS><<<gb, bd, 0, st>>>(a, ci_shift, s0, s1, ctx->dev_flag);
+        if (vec && plain) launch_pdl(zip_rows<T, OP, NIN, true, true, ITEMS>, gb, bd, 0, st, a, ci_shift, s0, s1, ctx->dev_flag);
+        else if (vec) launch_pdl(zip_rows<T, OP, NIN, true, false, ITEMS>, gb, bd, 0, st, a, ci_shift, s0, s1, ctx->dev_flag);
+        else launch_pdl(zip_rows<T, OP, NIN, false, false, ITEMS>, gb, bd, 0, st, a, ci_shift, s0, s1, ctx->dev_flag);
         NDB_CHECK_LAUNCH();
         return NDB_OK;
     }
