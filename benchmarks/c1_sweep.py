@@ -73,3 +73,22 @@ for per_sm in ("2", "3", "4", "6", "8"):
     os.environ["NDB_RED_COLS_PER_SM"] = per_sm
     med, best = run_batch(0)
     print(f"axis0 back-to-back per_sm={per_sm}: {med:5.2f} us", flush=True)
+os.environ.pop("NDB_RED_COLS_PER_SM")
+for splits in ("4", "6", "8", "9", "12", "18", "37"):
+    os.environ["NDB_RED_COLS_SPLITS"] = splits
+    med, best = run_batch(0)
+    print(f"axis0 back-to-back splits={splits}: {med:5.2f} us", flush=True)
+os.environ.pop("NDB_RED_COLS_SPLITS")
+os.environ["NDB_RED_TWO_KERNELS"] = "1"
+med, best = run_batch(0)
+print(f"axis0 back-to-back two kernels (no ticket): {med:5.2f} us", flush=True)
+os.environ.pop("NDB_RED_TWO_KERNELS")
+for wmax in ("2048", "8192"):
+    os.environ["NDB_RED_WARP_MAX"] = wmax
+    med, best = run_batch(1)
+    print(f"axis1 back-to-back warp_max={wmax} ({'block' if wmax == '2048' else 'warp'} per row): {med:5.2f} us", flush=True)
+os.environ.pop("NDB_RED_WARP_MAX")
+for nb in ("296", "444", "592", "888"):
+    os.environ["NDB_RED_LANES_BLOCKS"] = nb
+    med, best = run_batch(1)
+    print(f"axis1 back-to-back blocks={nb}: {med:5.2f} us", flush=True)

@@ -127,6 +127,44 @@ def run_checks(ctx, dist, rank, world, gemm: bool = True, peers=None):
                 par.general_mat_mul_rowsharded_peer(-2.3, dA, dB, np.pi, dC, peers, src=0)
                 err = np.max(np.abs(dC.to_numpy() - ref)) / np.max(np.abs(ref)) if hi > lo else 0.0
                 ok(f"row-sharded gemm over peer windows {np.dtype(dt).name}", err <= tol_mm * np.sqrt(512), f"rel err {err:.3e}")
+    # ---- the sharded entry points of the C ABI (csrc/dist.cu): library-owned NCCL communicator, no Python collectives ----
+    import ndarray_b200 as nd
+    for label, cctx in (("nccl only", nd.Context(ctx.device)), ("nccl + peer windows", ctx)):
+        comm = par.Comm(cctx, dist)
+        ca, cf = Array.from_numpy(a, cctx), Array.from_numpy(f, cctx)
+        csa, csf = par.shard_axis0(ca, rank, world), par.shard_axis0(cf, rank, world)
+        with np.errstate(over="ignore"):
+            ok(f"C ABI [{label}] sum() i64", par.reduce_all_sharded(csa) == a.sum(dtype=np.int64))
+            ok(f"C ABI [{label}] sum_axis0 i64", np.array_equal(par.reduce_axis0_sharded(csa, Red.SUM, n0).to_numpy(), a.sum(axis=0, dtype=np.int64)))
+            ok(f"C ABI [{label}] fold_axis0 min i64", np.array_equal(par.reduce_axis0_sharded(csa, Red.MIN, n0).to_numpy(), a.min(axis=0)))
+        close(f"C ABI [{label}] sum() f64", par.reduce_all_sharded(csf), f.sum(), tol * 300 * 8)
+        close(f"C ABI [{label}] sum_axis0 f64", par.reduce_axis0_sharded(csf, Red.SUM, n0).to_numpy(), f.sum(axis=0), tol * 8)
+        close(f"C ABI [{label}] mean_axis0", par.reduce_axis0_sharded(csf, Red.MEAN, n0).to_numpy(), f.mean(axis=0), tol)
+        close(f"C ABI [{label}] var_axis0", par.reduce_axis0_sharded(csf, Red.VAR, n0, 1.0).to_numpy(), f.var(axis=0, ddof=1), tol * 8)
+        close(f"C ABI [{label}] std_axis0", par.reduce_axis0_sharded(csf, Red.STD, n0, 0.0).to_numpy(), f.std(axis=0), tol * 8)
+        cw = par.shard_axis0(Array.from_numpy(wide, cctx), rank, world)
+        close(f"C ABI [{label}] var_axis0 wide", par.reduce_axis0_sharded(cw, Red.VAR, n0, 1.0).to_numpy(), wide.var(axis=0, ddof=1), tol * 8)
+        # a kept axis: no exchange, outputs sharded like the input
+        kept = Array.uninit((csf.shape[0],), np.float64, ctx=cctx)
+        from ndarray_b200._ffi import check as _check, lib as _lib
+        import ctypes as _C
+        _check(_lib().ndb_reduce_axis_sharded(cctx.handle, Red.SUM, 1, _C.byref(csf.v), _C.byref(kept.v), 0.0, n0))
+        close(f"C ABI [{label}] sum_axis1 (kept axis)", kept.to_numpy(), f[lo:hi].sum(axis=1), tol * 8)
+        if gemm:
+            for dt, tol_mm in ((np.float64, 1e-12), (np.float32, 1e-5)):
+                A = rng.standard_normal((n0, 512)).astype(dt)
+                B = rng.standard_normal((512, 300)).astype(dt)
+                C0 = rng.standard_normal((n0, 300)).astype(dt)
+                ref = (-2.3 * (A.astype(np.float64) @ B.astype(np.float64)) + np.pi * C0)[lo:hi]
+                dA = par.shard_axis0(Array.from_numpy(A, cctx), rank, world)
+                dC = par.shard_axis0(Array.from_numpy(C0, cctx), rank, world)
+                dB = Array.from_numpy(B if rank == 0 else np.zeros_like(B), cctx)  # only rank 0 holds B
+                par.gemm_rowsharded(-2.3, dA, dB, np.pi, dC, src=0)
+                err = np.max(np.abs(dC.to_numpy() - ref)) / np.max(np.abs(ref)) if hi > lo else 0.0
+                ok(f"C ABI [{label}] ndb_gemm_rowsharded {np.dtype(dt).name}", err <= tol_mm * np.sqrt(512), f"rel err {err:.3e}")
+        cctx.sync()
+        dist.barrier()
+        comm.close()
     x = rng.standard_normal(n0 * 300)
     lo1, hi1 = par.shard_bounds(x.size, rank, world)
     dx = Array.from_numpy(x[lo1:hi1], ctx)

@@ -85,6 +85,26 @@ def run_extras(nd, ctx, torch, dist, rank, world, local, peak_gbs):
                 c1_sum_into(ax)
         med, best = _time(ctx, c1_sum_x12, 10, 2)
         rec(f"C1_sum_axis{ax}_f32_4096^2_into_preallocated_12_back_to_back", 12 * (4 * n * n + 4 * n), med, best)
+    # the C1 loop as ONE CUDA graph (~10-40 us kernels): a = b*c + a, sum_axis(0), sum_axis(1) on each of the four
+    # buffer sets = 12 kernels per replay, edges kept as programmatic dependent launches
+    try:
+        o0, o1v = Array.zeros((n,), np.float32, ctx=ctx), Array.zeros((n,), np.float32, ctx=ctx)
+
+        def c1_body():
+            for a, b, c in sets:
+                Zip.from_(a).and_(b).and_(c).for_each("a=b*c+a")
+                check(lib().ndb_reduce_axis(ctx.handle, 0, 0, C.byref(a.v), C.byref(o0.v), 0.0))
+                check(lib().ndb_reduce_axis(ctx.handle, 0, 1, C.byref(a.v), C.byref(o1v.v), 0.0))
+        step_bytes = 4 * (4 * 4 * n * n + 2 * (4 * n * n + 4 * n))
+        med, best = _time(ctx, c1_body, 10, 2)
+        rec("C1_step(zip+sum_axis0+sum_axis1)x4_stream_launches", step_bytes, med, best)
+        with ctx.capture() as g:
+            c1_body()
+        med, best = _time(ctx, g.launch, 10, 2)
+        rec("C1_step(zip+sum_axis0+sum_axis1)x4_one_cuda_graph", step_bytes, med, best)
+        g.close()
+    except Exception as e:  # noqa: BLE001
+        out["C1_graph"] = {"error": repr(e)}
     del sets
     # ---- C2 variants: inner-axis step, map_collect (fresh output), all three views combined ------------
     n = 512

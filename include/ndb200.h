@@ -200,6 +200,15 @@ int ndb_event_destroy(void *ev);
 int ndb_event_record(ndb_ctx *ctx, void *ev);
 int ndb_event_elapsed_ms(void *start, void *stop, float *ms); /* synchronises on `stop` */
 
+/* CUDA graphs: record the calls issued on the context between begin and end (asynchronous entry points only: Zip, axis
+ * reductions, scans, GEMM - nothing that returns a host scalar or grows a workspace for the first time) and replay them
+ * with one launch.  Kernels keep their programmatic-dependent-launch edges inside the graph.  For loops of ~10 us kernels,
+ * where the host cannot issue launches as fast as the GPU retires them. */
+int ndb_graph_begin(ndb_ctx *ctx);
+int ndb_graph_end(ndb_ctx *ctx, void **graph_out);
+int ndb_graph_launch(ndb_ctx *ctx, void *graph);
+int ndb_graph_destroy(void *graph);
+
 /* ---- view arithmetic: pure host code, identical to ndarray's ---------------
  * All of these only rewrite (ptr, dim, stride); `elem_size` comes from dtype.
  */
@@ -310,6 +319,31 @@ int ndb_reduce_axis_peer(ndb_ctx *ctx, int redop, int axis, const ndb_view *in, 
 int ndb_reduce_axis_peer_ok(ndb_ctx *ctx, int redop, int axis, const ndb_view *in, const ndb_view *out, double ddof, int64_t n_global);
 /* ndb_reduce_all_dev over ALL shards: the kernel that finishes this rank's reduction tree also performs the exchange. */
 int ndb_reduce_all_peer(ndb_ctx *ctx, int redop, const ndb_view *in, void *out_dev);
+
+/* ---- sharded entry points: everything a non-Python host needs to run the multi-GPU paths of SURVEY.md 8e -------------------
+ * One process per GPU, Axis(0) is the sharded axis.  The communicator is NCCL's, owned by the library: libnccl.so.2 is
+ * dlopen'ed on first use (NDB_NCCL_LIB overrides the name), so libndb200 has no link-time NCCL dependency.  Rank 0 calls
+ * ndb_comm_unique_id and ships the 128 bytes to the other ranks by any means (file, socket, MPI, torch.distributed); every
+ * rank then calls ndb_comm_init.  Collectives run on the context stream; all ranks must issue the same sequence of calls. */
+int ndb_comm_unique_id(void *id_out /* 128 bytes */);
+int ndb_comm_init(ndb_ctx *ctx, int rank, int world, const void *id /* 128 bytes */);
+int ndb_comm_destroy(ndb_ctx *ctx);
+/* Replicate a dense device array from rank `src` (ncclBroadcast on the context stream). */
+int ndb_broadcast(ndb_ctx *ctx, const ndb_view *v, int src);
+/* general_mat_mul with A and C sharded along Axis(0) and B replicated: `b` is a dense [k, n] buffer on every rank whose
+ * contents are valid on rank `src`; it is broadcast, then every rank multiplies its own rows (row sharding changes no
+ * row's arithmetic).  With one rank (no communicator) this is ndb_gemm. */
+int ndb_gemm_rowsharded(ndb_ctx *ctx, const void *alpha, const ndb_view *a_local, const ndb_view *b, const void *beta,
+                        const ndb_view *c_local, int src);
+/* sum_axis / product_axis / mean_axis / var_axis / std_axis / fold_axis(min|max) over ALL shards.  axis != 0: plain
+ * ndb_reduce_axis (outputs are sharded like the input).  axis == 0: the fused cooperative kernel over the peer windows when
+ * they are attached and the layout qualifies (ndb_reduce_axis_peer), else local partial + all-reduce (mean divides by
+ * n_global afterwards), or for var/std per-shard Welford states + all-gather + Chan merge in rank order (deterministic).
+ * Every rank receives the full result in `out`. */
+int ndb_reduce_axis_sharded(ndb_ctx *ctx, int redop, int axis, const ndb_view *in, const ndb_view *out, double ddof, int64_t n_global);
+/* sum() / product() / min / max over all shards, result (element type) to host on every rank: the kernel that finishes the
+ * local tree also does the exchange when peer windows are attached, else an NCCL all-reduce of one element follows. */
+int ndb_reduce_all_sharded(ndb_ctx *ctx, int redop, const ndb_view *in, void *out_host);
 
 /* accumulate_axis_inplace (src/impl_methods.rs:3243) with op NDB_OP_ADD (running sum) or NDB_OP_MUL (cumprod,
  * src/numeric/impl_numeric.rs:125): v[.., i, ..] = op(v[.., i-1, ..], v[.., i, ..]) along `axis`, in place, one launch. */

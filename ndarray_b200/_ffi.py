@@ -84,6 +84,10 @@ def lib():
         "ndb_d2d": (i32, [vp, vp, vp, C.c_size_t]),
         "ndb_host_alloc": (i32, [C.c_size_t, C.POINTER(vp)]),
         "ndb_host_free": (i32, [vp]),
+        "ndb_graph_begin": (i32, [vp]),
+        "ndb_graph_end": (i32, [vp, C.POINTER(vp)]),
+        "ndb_graph_launch": (i32, [vp, vp]),
+        "ndb_graph_destroy": (i32, [vp]),
         "ndb_event_create": (i32, [C.POINTER(vp)]),
         "ndb_event_destroy": (i32, [vp]),
         "ndb_event_record": (i32, [vp, vp]),
@@ -124,6 +128,13 @@ def lib():
         "ndb_reduce_all_peer": (i32, [vp, i32, PV, vp]),
         "ndb_reduce_axis_peer": (i32, [vp, i32, i32, PV, PV, C.c_double, C.c_int64]),
         "ndb_reduce_axis_peer_ok": (i32, [vp, i32, i32, PV, PV, C.c_double, C.c_int64]),
+        "ndb_comm_unique_id": (i32, [vp]),
+        "ndb_comm_init": (i32, [vp, i32, i32, vp]),
+        "ndb_comm_destroy": (i32, [vp]),
+        "ndb_broadcast": (i32, [vp, PV, i32]),
+        "ndb_gemm_rowsharded": (i32, [vp, vp, PV, PV, vp, PV, i32]),
+        "ndb_reduce_axis_sharded": (i32, [vp, i32, i32, PV, PV, dbl, C.c_int64]),
+        "ndb_reduce_all_sharded": (i32, [vp, i32, PV, vp]),
         "ndb_accumulate_axis": (i32, [vp, i32, i32, PV]),
         "ndb_dot": (i32, [vp, PV, PV, vp]),
         "ndb_gemm": (i32, [vp, vp, PV, PV, vp, PV]),

@@ -115,6 +115,10 @@ class Context:
             lib().ndb_ctx_destroy(self.handle)
             self.handle = None
 
+    # CUDA graphs: `with ctx.capture() as g: ...calls...` then g.launch() replays them with one host call
+    def capture(self):
+        return _Capture(self)
+
     # event timing on the context stream
     def event(self):
         e = C.c_void_p()
@@ -129,6 +133,31 @@ class Context:
         ms = C.c_float()
         check(lib().ndb_event_elapsed_ms(start, stop, C.byref(ms)))
         return ms.value
+
+
+class _Capture:
+    def __init__(self, ctx: Context):
+        self.ctx, self.graph = ctx, None
+
+    def __enter__(self):
+        check(lib().ndb_graph_begin(self.ctx.handle))
+        return self
+
+    def __exit__(self, et, ev, tb):
+        g = C.c_void_p()
+        st = lib().ndb_graph_end(self.ctx.handle, C.byref(g))
+        if et is None:
+            check(st)
+            self.graph = g
+        return False
+
+    def launch(self):
+        check(lib().ndb_graph_launch(self.ctx.handle, self.graph))
+
+    def close(self):
+        if self.graph:
+            lib().ndb_graph_destroy(self.graph)
+            self.graph = None
 
 
 _default_ctx: dict[int, Context] = {}

@@ -70,7 +70,7 @@ def build(verbose: bool = False, jobs: int | None = None) -> Path:
     if LIB.exists() and all(LIB.stat().st_mtime > o.stat().st_mtime for o in objs):
         return LIB
     cmd = [_nvcc(), "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", str(LIB), *map(str, objs),
-           "-Xcompiler", "-fPIC", "-cudart", "static"]
+           "-Xcompiler", "-fPIC", "-cudart", "static", "-ldl"]
     if verbose:
         print(" ".join(cmd), flush=True)
     r = subprocess.run(cmd, capture_output=True, text=True)

@@ -126,6 +126,9 @@ struct ndb_ctx {
     // pinned bounce buffers for PAGEABLE host memory (the CBLAS boundary hands in ndarray's Vec storage)
     void *bounce[2] = {nullptr, nullptr};
     cudaEvent_t bounce_ev[2] = {nullptr, nullptr};
+    // NCCL communicator owned by the library (dist.cu; libnccl is dlopen'ed on first use)
+    void *nccl_comm = nullptr;
+    int comm_rank = -1, comm_world = 0;
 };
 
 namespace ndb {
@@ -136,6 +139,8 @@ int ensure_stage(ndb_ctx *ctx, int slot, size_t bytes);
 // Ordered after / before work on ctx->stream; returns after the last chunk has been ISSUED (h2d) or has LANDED (d2h).
 int staged_h2d(ndb_ctx *ctx, void *dst_dev, const void *src_host, size_t bytes);
 int staged_d2h(ndb_ctx *ctx, void *dst_host, const void *src_dev, size_t bytes);
+int welford_merge_gathered(ndb_ctx *ctx, int dtype, int world, const int64_t *counts_dev, const void *means_dev, const void *m2s_dev,
+                           int64_t n_out, int64_t pitch, double ddof, int want_std, void *out_dev);  // reduce.cu
 struct PeerArgs;
 int peer_begin(ndb_ctx *ctx, int blocks, size_t bytes, PeerArgs *out);  // peer.cu
 struct DeviceGuard {

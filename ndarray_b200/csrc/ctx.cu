@@ -299,6 +299,7 @@ int ndb_ctx_destroy(ndb_ctx *ctx)
 {
     if (!ctx) return NDB_OK;
     ndb_peer_window_destroy(ctx);
+    ndb_comm_destroy(ctx);
     DeviceGuard g(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     if (ctx->workspace) cudaFree(ctx->workspace);
@@ -400,6 +401,45 @@ int ndb_host_alloc(size_t bytes, void **hptr)
 int ndb_host_free(void *hptr)
 {
     if (hptr) NDB_CUDA(cudaFreeHost(hptr));
+    return NDB_OK;
+}
+
+// ---- CUDA graphs: replay a fixed sequence of calls without per-launch host cost ---------------------------------------
+int ndb_graph_begin(ndb_ctx *ctx)
+{
+    if (!ctx) return NDB_ERR_INVALID_ARG;
+    DeviceGuard g(ctx->device);
+    NDB_CUDA(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+    return NDB_OK;
+}
+
+int ndb_graph_end(ndb_ctx *ctx, void **graph_out)
+{
+    if (!ctx || !graph_out) return NDB_ERR_INVALID_ARG;
+    *graph_out = nullptr;
+    DeviceGuard g(ctx->device);
+    cudaGraph_t graph = nullptr;
+    NDB_CUDA(cudaStreamEndCapture(ctx->stream, &graph));
+    cudaGraphExec_t exec = nullptr;
+    cudaError_t e = cudaGraphInstantiate(&exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaGraphInstantiate", __FILE__, __LINE__);
+    *graph_out = (void *)exec;
+    return NDB_OK;
+}
+
+int ndb_graph_launch(ndb_ctx *ctx, void *graph)
+{
+    if (!ctx || !graph) return NDB_ERR_INVALID_ARG;
+    DeviceGuard g(ctx->device);
+    NDB_CUDA(cudaGraphLaunch((cudaGraphExec_t)graph, ctx->stream));
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return NDB_OK;
+}
+
+int ndb_graph_destroy(void *graph)
+{
+    if (graph) NDB_CUDA(cudaGraphExecDestroy((cudaGraphExec_t)graph));
     return NDB_OK;
 }
 

@@ -32,6 +32,12 @@
 #ifndef NDB_RED_COLS_MINB_W
 #define NDB_RED_COLS_MINB_W 3
 #endif
+#ifndef NDB_RED_COLS_MINB
+#define NDB_RED_COLS_MINB 3
+#endif
+#ifndef NDB_RED_COLS_U
+#define NDB_RED_COLS_U 8
+#endif
 #ifndef NDB_RED_COLS_WU
 #define NDB_RED_COLS_WU 8
 #endif
@@ -262,6 +268,7 @@ struct RedArgs {
     double nT;      // n as the element type
     double dof;     // n - ddof in the element type
     int splits;     // red_cols: blocks along the reduced axis
+    int lane_warps; // red_lanes<WARP>: warps sharing one lane (1, 2, 4 or 8)
     void *partial;  // [splits][n_out] states
     unsigned *tickets;  // red_cols: one zeroed counter per column tile; non-null = the last split to finish merges (one launch)
     int peer_on;                      // red_cols<PEER>: exchange every tile's state with the other ranks before finalizing
@@ -304,17 +311,21 @@ __global__ void __launch_bounds__(256) red_lanes(RedArgs a)
     using V = Vec128<T>;
     constexpr int N = V::N;
     __shared__ Acc<T, R> smem[32];
-    const int lane = threadIdx.x & 31;
-    const int wpb = blockDim.x >> 5;  // WARP: one lane per warp, wpb lanes per block
-    const int64_t groups = WARP ? (a.n_out + wpb - 1) / wpb : a.n_out;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int wpb = blockDim.x >> 5;
+    // WARP: P = a.lane_warps warps share one lane (P = 1: a warp per lane), so a block covers wpb / P lanes; short
+    // problems want every thread slot of the machine busy with a few loads each rather than few threads with many
+    const int P = WARP ? a.lane_warps : 1;
+    const int lanes_pb = wpb / P;
+    const int64_t groups = WARP ? (a.n_out + lanes_pb - 1) / lanes_pb : a.n_out;
     for (int64_t g = blockIdx.x; g < groups; g += gridDim.x) {
-        const int64_t o = WARP ? g * wpb + (threadIdx.x >> 5) : g;
+        const int64_t o = WARP ? g * lanes_pb + warp / P : g;
         const bool live = o < a.n_out;
         int64_t in_off = 0, out_off = 0, out2_off = 0;
         if (live) kept_offsets(a.k, o, in_off, out_off, out2_off);
         const T *src = reinterpret_cast<const T *>(a.in) + in_off;
-        const int tid = WARP ? lane : threadIdx.x;
-        const int nt = WARP ? 32 : blockDim.x;
+        const int tid = WARP ? (warp % P) * 32 + lane : threadIdx.x;
+        const int nt = WARP ? 32 * P : blockDim.x;
         Acc<T, R> acc;
         acc.reset();
         if (live) {
@@ -350,7 +361,17 @@ __global__ void __launch_bounds__(256) red_lanes(RedArgs a)
         }
         if constexpr (WARP) {
             acc = warp_reduce(acc);
-            if (live && lane == 0) store_result<T, R, FIN>(a, acc, out_off, out2_off);
+            if (P == 1) {
+                if (live && lane == 0) store_result<T, R, FIN>(a, acc, out_off, out2_off);
+            } else {  // the P warps of a lane meet in shared memory and merge in warp order
+                if (lane == 0) smem[warp] = acc;
+                __syncthreads();
+                if (live && lane == 0 && warp % P == 0) {
+                    for (int q = 1; q < P; ++q) acc.merge(smem[warp + q]);
+                    store_result<T, R, FIN>(a, acc, out_off, out2_off);
+                }
+                __syncthreads();
+            }
         } else {
             acc = block_reduce(acc, smem);
             if (threadIdx.x == 0) store_result<T, R, FIN>(a, acc, out_off, out2_off);
@@ -396,7 +417,7 @@ __device__ __forceinline__ A merge_splits(const A *p, int splits, int64_t pitch)
 // blockDim = (32, 8).  A block owns 32*W consecutive outputs along the last kept axis (in_stride 1) and
 // rows [split*chunk, ...) of the reduced axis; thread (tx, ty) strides rows ty, ty+8, ...
 template <typename T, int R, int FIN, int W, bool PEER = false>
-__global__ void __launch_bounds__(256, R == R_WELFORD ? NDB_RED_COLS_MINB_W : 3) red_cols(RedArgs a)  // 3 CTAs/SM register budget (<= 85): f64 sum 6.52 -> 6.95 TB/s vs the default allocation
+__global__ void __launch_bounds__(256, R == R_WELFORD ? NDB_RED_COLS_MINB_W : NDB_RED_COLS_MINB) red_cols(RedArgs a)  // 3 CTAs/SM register budget (<= 85): f64 sum 6.52 -> 6.95 TB/s vs the default allocation
 {
     pdl_enter();
     using V = Vec128<T>;
@@ -435,7 +456,7 @@ __global__ void __launch_bounds__(256, R == R_WELFORD ? NDB_RED_COLS_MINB_W : 3)
         const T *src = reinterpret_cast<const T *>(a.in) + in_off + c0;
         if (c0 < ncol) {  // ncol % W == 0 when W > 1 (host check), so a vector is all-in or all-out
             int64_t r = r0 + ty;
-            constexpr int U = (R == R_WELFORD) ? NDB_RED_COLS_WU : 8;  // rows in flight per thread
+            constexpr int U = (R == R_WELFORD) ? NDB_RED_COLS_WU : NDB_RED_COLS_U;  // rows in flight per thread
             if constexpr (W > 1) {
                 if constexpr (PEER) {
                     // The tile geometry of the fused sharded reduction must be the same on every rank, so a rank whose
@@ -1056,9 +1077,16 @@ static int reduce_axis_launch(ndb_ctx *ctx, RedArgs &a, const ZipPlan &z)
         // warp-per-lane: smaller blocks when 8 lanes per block would leave the SMs unevenly loaded (4096 lanes = 3.46
         // blocks of 8 per SM: the SMs holding 4 set the pace)
         int wpb = 8;
+        // warps per lane (NDB_RED_LANES_P): two or four warps can share a lane and meet in shared memory.  Measured on
+        // C1 (4096 lanes of 16 KiB, cold, back to back): P = 1 / 2 / 4 -> 13.3 / 14.2 / 14.5 us, so one warp per lane stays
+        // the default; the knob is kept for shapes with few, long lanes.
+        int P = 1;
+        if (warp && getenv("NDB_RED_LANES_P")) P = std::max(1, std::min(8, atoi(getenv("NDB_RED_LANES_P"))));
+        a.lane_warps = P;
         if (getenv("NDB_RED_WPB")) wpb = atoi(getenv("NDB_RED_WPB"));
-        else while (wpb > 2 && (a.n_out + wpb - 1) / wpb < (int64_t)ctx->sm_count * 6) wpb >>= 1;
-        const int64_t groups = warp ? (a.n_out + wpb - 1) / wpb : a.n_out;
+        else while (wpb > 2 && wpb > P && (a.n_out * P + wpb - 1) / wpb < (int64_t)ctx->sm_count * 6) wpb >>= 1;
+        if (wpb < P || wpb % P) wpb = P;
+        const int64_t groups = warp ? (a.n_out * P + wpb - 1) / wpb : a.n_out;
         unsigned blocks = (unsigned)std::min<int64_t>(groups, (int64_t)1 << 30);
         if (getenv("NDB_RED_LANES_BLOCKS")) blocks = std::min<unsigned>(blocks, (unsigned)atoi(getenv("NDB_RED_LANES_BLOCKS")));
         if (warp) {
@@ -1307,6 +1335,41 @@ __global__ void __launch_bounds__(256) welford_merge_kernel(int n_shards, const 
     T v = s.m2 / dof;
     if (want_std) v = std::is_same<T, float>::value ? (T)sqrtf((float)v) : (T)sqrt((double)v);
     out[o] = v;
+}
+
+// shards gathered from all ranks (means / m2s are [world][n_out], counts [world], all on the device): merge in rank order
+template <typename T>
+__global__ void __launch_bounds__(256) welford_merge_gathered_kernel(int world, const int64_t *counts, const T *means, const T *m2s,
+                                                                     int64_t n_out, int64_t pitch, T ddof, int want_std, T *out)
+{
+    pdl_enter();
+    const int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (o >= n_out) return;
+    using Rd = Reducer<T, R_WELFORD>;
+    typename Rd::State s = Rd::init();
+    for (int k = 0; k < world; ++k) {
+        typename Rd::State t{(T)counts[k], means[(int64_t)k * pitch + o], m2s[(int64_t)k * pitch + o]};
+        Rd::merge(s, t);
+    }
+    T v = s.m2 / (s.n - ddof);
+    if (want_std) v = std::is_same<T, float>::value ? (T)sqrtf((float)v) : (T)sqrt((double)v);
+    out[o] = v;
+}
+
+int welford_merge_gathered(ndb_ctx *ctx, int dtype, int world, const int64_t *counts_dev, const void *means_dev, const void *m2s_dev,
+                           int64_t n_out, int64_t pitch, double ddof, int want_std, void *out_dev)
+{
+    if (n_out <= 0) return NDB_OK;
+    const unsigned blocks = (unsigned)((n_out + 255) / 256);
+    if (dtype == NDB_F32)
+        launch_pdl(welford_merge_gathered_kernel<float>, blocks, 256, 0, ctx->stream, world, counts_dev, (const float *)means_dev,
+                   (const float *)m2s_dev, n_out, pitch, (float)ddof, want_std, (float *)out_dev);
+    else if (dtype == NDB_F64)
+        launch_pdl(welford_merge_gathered_kernel<double>, blocks, 256, 0, ctx->stream, world, counts_dev, (const double *)means_dev,
+                   (const double *)m2s_dev, n_out, pitch, ddof, want_std, (double *)out_dev);
+    else return NDB_ERR_UNSUPPORTED;
+    NDB_CHECK_LAUNCH();
+    return NDB_OK;
 }
 
 }  // namespace ndb

@@ -108,6 +108,61 @@ class PeerGroup:
         check(lib().ndb_peer_window_destroy(self.ctx.handle))
 
 
+class Comm:
+    """The library-owned NCCL communicator of one context (csrc/dist.cu): what a non-Python host would set up with
+    ndb_comm_unique_id / ndb_comm_init.  Here the 128-byte id travels through torch.distributed's object broadcast (host side,
+    any backend); after that the sharded entry points (ndb_gemm_rowsharded, ndb_reduce_axis_sharded, ndb_reduce_all_sharded)
+    involve no Python collectives at all."""
+
+    def __init__(self, ctx, dist):
+        self.ctx, self.rank, self.world = ctx, dist.get_rank(), dist.get_world_size()
+        uid = (C.c_ubyte * 128)()
+        err = None
+        if self.rank == 0:
+            try:
+                check(lib().ndb_comm_unique_id(uid))
+            except Exception as e:  # noqa: BLE001
+                err = repr(e)
+        box = [(err, bytes(uid))]
+        dist.broadcast_object_list(box, src=0)
+        if box[0][0]:
+            raise RuntimeError(f"ndb_comm_unique_id failed on rank 0: {box[0][0]}")
+        blob = (C.c_ubyte * 128).from_buffer_copy(box[0][1])
+        try:
+            check(lib().ndb_comm_init(ctx.handle, self.rank, self.world, blob))
+        except Exception as e:  # noqa: BLE001
+            err = repr(e)
+        errs = [None] * self.world
+        dist.all_gather_object(errs, err)
+        if any(errs):
+            lib().ndb_comm_destroy(ctx.handle)
+            raise RuntimeError(f"ndb_comm_init failed on some rank: {errs}")
+
+    def close(self):
+        check(lib().ndb_comm_destroy(self.ctx.handle))
+
+
+def gemm_rowsharded(alpha, a_local: Array, b: Array, beta, c_local: Array, src: int = 0) -> None:
+    """ndb_gemm_rowsharded: B (valid on rank `src`) is broadcast by the library's own communicator, then the local GEMM."""
+    al, be = np.asarray(alpha, dtype=a_local.dtype), np.asarray(beta, dtype=a_local.dtype)
+    check(lib().ndb_gemm_rowsharded(a_local.ctx.handle, C.c_void_p(al.ctypes.data), C.byref(a_local.v), C.byref(b.v),
+                                    C.c_void_p(be.ctypes.data), C.byref(c_local.v), int(src)))
+
+
+def reduce_axis0_sharded(local: Array, redop: int, n_global: int, ddof: float = 0.0) -> Array:
+    """ndb_reduce_axis_sharded along the sharded axis: fused over peer windows when possible, NCCL otherwise - decided
+    inside the library, identically on every rank."""
+    out = Array.uninit(local.shape[1:], local.dtype, ctx=local.ctx)
+    check(lib().ndb_reduce_axis_sharded(local.ctx.handle, redop, 0, C.byref(local.v), C.byref(out.v), float(ddof), int(n_global)))
+    return out
+
+
+def reduce_all_sharded(local: Array, redop: int = Red.SUM):
+    out = np.zeros((), dtype=local.dtype)
+    check(lib().ndb_reduce_all_sharded(local.ctx.handle, redop, C.byref(local.v), C.c_void_p(out.ctypes.data)))
+    return out[()]
+
+
 def _fused_axis0(local: Array, redop: int, ddof: float, n_global: int, peers: "PeerGroup"):
     """ndb_reduce_axis_peer along Axis(0): the whole sharded reduction (local column reduction, exchange of the per-tile
     states through peer memory, rank-ordered merge, finalisation with the global length) in ONE cooperative launch.
