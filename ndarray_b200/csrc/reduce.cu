@@ -960,7 +960,9 @@ static int reduce_all_typed(ndb_ctx *ctx, const ndb_view *v, T *out_dev, T dof =
     AllArgs a;
     memset(&a, 0, sizeof(a));
     collapse_for_all(v, &a);
-    const int max_blocks = ctx->sm_count * (getenv("NDB_RED_ALL_PER_SM") ? std::max(1, atoi(getenv("NDB_RED_ALL_PER_SM"))) : 4);  // one resident wave; measured 1/2/3/4/5/6/8 per SM: 3.8/6.0/6.5/6.7/6.7/6.0/6.5 TB/s (C3 sum, f64)
+    // one resident wave: the pairwise-batch kernel needs 32 registers, so eight 256-thread blocks fit per SM; measured
+    // 2/3/4/6/8 per SM: 3.2/4.5/5.5/6.6/6.9 TB/s (C3 sum, f64 16384^2), 4.3/5.7/6.4/6.8/6.9 TB/s (f32)
+    const int max_blocks = ctx->sm_count * (getenv("NDB_RED_ALL_PER_SM") ? std::max(1, atoi(getenv("NDB_RED_ALL_PER_SM"))) : 8);
     NDB_TRY(ensure_workspace(ctx, (size_t)max_blocks * sizeof(Acc<T, R>)));
     a.partial = ctx->workspace;
     int blocks;

@@ -93,6 +93,20 @@ extern "C" {
     pub fn ndb_reduce_axis_peer_ok(ctx: *mut ndb_ctx, redop: c_int, axis: c_int, input: *const ndb_view, out: *const ndb_view, ddof: c_double, n_global: i64) -> c_int;
     pub fn ndb_reduce_all_peer(ctx: *mut ndb_ctx, redop: c_int, input: *const ndb_view, out_dev: *mut c_void) -> c_int;
     pub fn ndb_accumulate_axis(ctx: *mut ndb_ctx, op: c_int, axis: c_int, v: *const ndb_view) -> c_int;
+    pub fn ndb_zip_fold(ctx: *mut ndb_ctx, op: c_int, scalars: *const c_void, n_inputs: c_int, inputs: *const ndb_view, redop: c_int, init: *const c_void, out_host: *mut c_void) -> c_int;
+    pub fn ndb_zip_host_fold(ctx: *mut ndb_ctx, op: c_int, scalars: *const c_void, n_parts: c_int, parts: *const ndb_view, redop: c_int, out_host: *mut c_void) -> c_int;
+    pub fn ndb_fill_counter_rng(ctx: *mut ndb_ctx, out: *const ndb_view, seed: u64, first_index: u64) -> c_int;
+    pub fn ndb_graph_begin(ctx: *mut ndb_ctx) -> c_int;
+    pub fn ndb_graph_end(ctx: *mut ndb_ctx, graph_out: *mut *mut c_void) -> c_int;
+    pub fn ndb_graph_launch(ctx: *mut ndb_ctx, graph: *mut c_void) -> c_int;
+    pub fn ndb_graph_destroy(graph: *mut c_void) -> c_int;
+    pub fn ndb_comm_unique_id(id_out: *mut c_void) -> c_int;
+    pub fn ndb_comm_init(ctx: *mut ndb_ctx, rank: c_int, world: c_int, id: *const c_void) -> c_int;
+    pub fn ndb_comm_destroy(ctx: *mut ndb_ctx) -> c_int;
+    pub fn ndb_broadcast(ctx: *mut ndb_ctx, v: *const ndb_view, src: c_int) -> c_int;
+    pub fn ndb_gemm_rowsharded(ctx: *mut ndb_ctx, alpha: *const c_void, a_local: *const ndb_view, b: *const ndb_view, beta: *const c_void, c_local: *const ndb_view, src: c_int) -> c_int;
+    pub fn ndb_reduce_axis_sharded(ctx: *mut ndb_ctx, redop: c_int, axis: c_int, input: *const ndb_view, out: *const ndb_view, ddof: c_double, n_global: i64) -> c_int;
+    pub fn ndb_reduce_all_sharded(ctx: *mut ndb_ctx, redop: c_int, input: *const ndb_view, out_host: *mut c_void) -> c_int;
     // ndarray's own CBLAS boundary (src/linalg/impl_linalg.rs:466-491, :116-122); normally bound through cblas-sys
     pub fn cblas_sgemm(layout: c_int, transa: c_int, transb: c_int, m: c_int, n: c_int, k: c_int, alpha: f32, a: *const f32, lda: c_int, b: *const f32, ldb: c_int, beta: f32, c: *mut f32, ldc: c_int);
     pub fn cblas_dgemm(layout: c_int, transa: c_int, transb: c_int, m: c_int, n: c_int, k: c_int, alpha: f64, a: *const f64, lda: c_int, b: *const f64, ldb: c_int, beta: f64, c: *mut f64, ldc: c_int);

@@ -315,3 +315,27 @@ def test_planner_combined_views_and_config5():
     assert st == 0 and pl.kernel in (1, 2) and pl.dim[0] == 77
     st, pl = plan(17, *([v] * 10))
     assert st != 0  # more than 9 producers: ndarray's Zip stops at 9 too
+
+
+def test_rust_ffi_declares_exactly_the_header():
+    """rust/ndarray-b200/src/ffi.rs cannot be compiled here (no rustc), so its agreement with include/ndb200.h is
+    checked mechanically: the same set of symbols, each with the same number of parameters; and every `ffi::` call
+    in lib.rs names a declared symbol."""
+    hdr = (ROOT / "include" / "ndb200.h").read_text()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    decl = {}
+    for m in re.finditer(r"\b((?:ndb|cblas)_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", hdr):
+        args = m.group(2).strip()
+        decl[m.group(1)] = 0 if args in ("", "void") else args.count(",") + 1
+    rs = (ROOT / "rust" / "ndarray-b200" / "src" / "ffi.rs").read_text()
+    rust = {}
+    for m in re.finditer(r"pub fn ((?:ndb|cblas)_[a-z0-9_]+)\s*\(([^;]*?)\)\s*(?:->[^;]*)?;", rs):
+        args = m.group(2).strip()
+        rust[m.group(1)] = 0 if not args else args.count(",") + 1
+    assert set(rust) == set(decl), (sorted(set(decl) - set(rust)), sorted(set(rust) - set(decl)))
+    wrong = {n: (decl[n], rust[n]) for n in decl if decl[n] != rust[n]}
+    assert not wrong, wrong
+    lib_rs = (ROOT / "rust" / "ndarray-b200" / "src" / "lib.rs").read_text()
+    used = set(re.findall(r"ffi::((?:ndb|cblas)_[a-z0-9_]+)\s*\(", lib_rs))
+    assert used <= set(rust), sorted(used - set(rust))
+    assert len(used) >= 40  # the crate actually covers the ABI, not a corner of it
