@@ -1,6 +1,6 @@
 """One small workload per invocation, for `ncu --set full` captures (kept short: ncu replays every kernel ~40x).
 
-  python benchmarks/ncu_target.py zip|combined|reduce|gemm64|gemm32
+  python benchmarks/ncu_target.py zip|c5|combined|reduce|gemm64|gemm32
 """
 import sys
 from pathlib import Path
@@ -27,6 +27,16 @@ def main():
             Zip.from_(out.slice(s_[: n // 2, :, :])).and_(x.slice(s_[::-2, :, :])).and_(y.slice(s_[::2, :, :])).for_each("a=b+c")
             Zip.from_(out).and_(x).and_broadcast(row).for_each("a=b*c")
             Zip.from_(out).and_(x.slice(s_[:, :, ::-1])).and_(y).for_each("a=b+c")
+    elif which == "c5":
+        # one 8-GPU shard of the bench workload (config 5): a = b*c + a over 2^29 f32, then the global sum
+        import ctypes as C
+        rows, cols = 8192, 65536
+        a, b, c = (Array.uninit((rows, cols), np.float32) for _ in range(3))
+        for arr, seed in ((a, 1), (b, 2), (c, 3)):
+            nd.lib().ndb_fill_counter_rng(ctx.handle, C.byref(arr.v), seed, 0)
+        for _ in range(2):
+            Zip.from_(a).and_(b).and_(c).for_each("a=b*c+a")
+            a.sum()
     elif which == "combined":
         n = 512
         x = Array.from_numpy(rng.random((n, n, n), dtype=np.float32))

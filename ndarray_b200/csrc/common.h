@@ -137,8 +137,8 @@ int ensure_stage(ndb_ctx *ctx, int slot, size_t bytes);
 // pageable host <-> device through two pinned bounce buffers: a few host threads copy chunk i+1 while the DMA engine
 // moves chunk i (cudaMemcpy from pageable memory runs at ~12 GB/s on these boxes, this pipeline at the threads' memcpy rate).
 // Ordered after / before work on ctx->stream; returns after the last chunk has been ISSUED (h2d) or has LANDED (d2h).
-int staged_h2d(ndb_ctx *ctx, void *dst_dev, const void *src_host, size_t bytes);
-int staged_d2h(ndb_ctx *ctx, void *dst_host, const void *src_dev, size_t bytes);
+int staged_h2d(ndb_ctx *ctx, void *dst_dev, const void *src_host, size_t bytes, cudaStream_t st = nullptr);
+int staged_d2h(ndb_ctx *ctx, void *dst_host, const void *src_dev, size_t bytes, cudaStream_t st = nullptr);
 int welford_merge_gathered(ndb_ctx *ctx, int dtype, int world, const int64_t *counts_dev, const void *means_dev, const void *m2s_dev,
                            int64_t n_out, int64_t pitch, double ddof, int want_std, void *out_dev);  // reduce.cu
 struct PeerArgs;

@@ -162,10 +162,11 @@ void parallel_memcpy(void *dst, const void *src, size_t bytes)
 
 }  // namespace
 
-int staged_h2d(ndb_ctx *ctx, void *dst_dev, const void *src_host, size_t bytes)
+int staged_h2d(ndb_ctx *ctx, void *dst_dev, const void *src_host, size_t bytes, cudaStream_t st)
 {
+    if (!st) st = ctx->stream;
     if (bytes < (size_t(4) << 20) || getenv("NDB_NO_BOUNCE")) {
-        NDB_CUDA(cudaMemcpyAsync(dst_dev, src_host, bytes, cudaMemcpyHostToDevice, ctx->stream));
+        NDB_CUDA(cudaMemcpyAsync(dst_dev, src_host, bytes, cudaMemcpyHostToDevice, st));
         return NDB_OK;
     }
     NDB_TRY(ensure_bounce(ctx));
@@ -175,8 +176,8 @@ int staged_h2d(ndb_ctx *ctx, void *dst_dev, const void *src_host, size_t bytes)
         const size_t len = std::min(BOUNCE_BYTES, bytes - done);
         if (i >= 2) NDB_CUDA(cudaEventSynchronize(ctx->bounce_ev[b]));  // the DMA that last read this buffer is done
         parallel_memcpy(ctx->bounce[b], (const char *)src_host + done, len);
-        NDB_CUDA(cudaMemcpyAsync((char *)dst_dev + done, ctx->bounce[b], len, cudaMemcpyHostToDevice, ctx->stream));
-        NDB_CUDA(cudaEventRecord(ctx->bounce_ev[b], ctx->stream));
+        NDB_CUDA(cudaMemcpyAsync((char *)dst_dev + done, ctx->bounce[b], len, cudaMemcpyHostToDevice, st));
+        NDB_CUDA(cudaEventRecord(ctx->bounce_ev[b], st));
         done += len;
     }
     // the bounce buffers are reused by the next call: wait until the DMA engine has drained them
@@ -185,19 +186,20 @@ int staged_h2d(ndb_ctx *ctx, void *dst_dev, const void *src_host, size_t bytes)
     return NDB_OK;
 }
 
-int staged_d2h(ndb_ctx *ctx, void *dst_host, const void *src_dev, size_t bytes)
+int staged_d2h(ndb_ctx *ctx, void *dst_host, const void *src_dev, size_t bytes, cudaStream_t st)
 {
+    if (!st) st = ctx->stream;
     if (bytes < (size_t(4) << 20) || getenv("NDB_NO_BOUNCE")) {
-        NDB_CUDA(cudaMemcpyAsync(dst_host, src_dev, bytes, cudaMemcpyDeviceToHost, ctx->stream));
-        NDB_CUDA(cudaStreamSynchronize(ctx->stream));
+        NDB_CUDA(cudaMemcpyAsync(dst_host, src_dev, bytes, cudaMemcpyDeviceToHost, st));
+        NDB_CUDA(cudaStreamSynchronize(st));
         return NDB_OK;
     }
     NDB_TRY(ensure_bounce(ctx));
     const size_t chunks = (bytes + BOUNCE_BYTES - 1) / BOUNCE_BYTES;
     auto issue = [&](size_t i) -> cudaError_t {
         const size_t off = i * BOUNCE_BYTES, len = std::min(BOUNCE_BYTES, bytes - off);
-        cudaError_t e = cudaMemcpyAsync(ctx->bounce[i & 1], (const char *)src_dev + off, len, cudaMemcpyDeviceToHost, ctx->stream);
-        if (e == cudaSuccess) e = cudaEventRecord(ctx->bounce_ev[i & 1], ctx->stream);
+        cudaError_t e = cudaMemcpyAsync(ctx->bounce[i & 1], (const char *)src_dev + off, len, cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaEventRecord(ctx->bounce_ev[i & 1], st);
         return e;
     };
     NDB_CUDA(issue(0));
