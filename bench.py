@@ -452,9 +452,6 @@ def main():
         breakdown["exchange_alone_us_nccl_1elt"] = lat(nccl_one)
         if peers is not None:
             breakdown["exchange_alone_us_peer_1elt"] = lat(lambda: peers.allreduce_(acc))
-        # local reduction without any exchange, for the difference
-        breakdown["sum_local_only_ms"] = lat(lambda: sum_step("local"), 100) / 1e3
-        breakdown["zip_only_ms"] = lat(lambda: z.for_each("a=b*c+a"), 50) / 1e3
         breakdown["note"] = ("a step is zip + local sum + exchange; what separates N-GPU time from 1/N of the 1-GPU time is the exchange "
                              "(~12 us peer / ~33 us NCCL per step, all ranks meet there) plus the first steps after the barrier")
 

@@ -9,7 +9,7 @@ import ndarray_b200 as nd  # noqa: E402
 from ndarray_b200 import Array, Zip  # noqa: E402
 ctx = nd.default_context()
 L = nd.lib()
-rows, cols = 8192, 65536
+rows, cols = int(sys.argv[1]) if len(sys.argv) > 1 else 8192, 65536
 a, b, c = (Array.uninit((rows, cols), np.float32, ctx=ctx) for _ in range(3))
 for arr, seed in ((a, 1), (b, 2), (c, 3)):
     L.ndb_fill_counter_rng(ctx.handle, C.byref(arr.v), seed, 0)
@@ -43,4 +43,4 @@ def step():
     s()
 
 
-print(f"sum x20  {timed(s):.4f} ms   zip x20  {timed(zf):.4f} ms   step x20  {timed(step):.4f} ms", flush=True)
+print(f"rows {rows}: sum x100  {timed(s, 100):.4f} ms   zip x20  {timed(zf):.4f} ms   step x20  {timed(step):.4f} ms   sum x100 again {timed(s, 100):.4f} ms", flush=True)

@@ -266,6 +266,14 @@ int ndb_zip_fold_sum(ndb_ctx *ctx, int op, const void *scalars, int n_inputs, co
  * evaluated as a tree and are out of scope (fold_axis has the same restriction). */
 int ndb_zip_fold(ndb_ctx *ctx, int op, const void *scalars, int n_inputs, const ndb_view *inputs, int redop, const void *init,
                  void *out_host);
+/* Zip::fold_while (src/zip/mod.rs:640-655) for the same associative accumulators.  FoldWhile::Done only means something
+ * relative to a traversal order, so the order is kept explicit: the values op(inputs...) are laid out in Zip's traversal
+ * order (C, or F when the producers prefer it, zip/mod.rs:278-281), the FIRST position whose value satisfies
+ * `value <stop_op> *stop_value` (stop_op in NDB_OP_EQ..NDB_OP_GE) is found, and the fold covers the elements before it:
+ *     fold_while(init, |acc, ..| if v <stop_op> s { Done(acc) } else { Continue(acc <redop> v) })
+ * *done = 1 if the predicate fired (FoldWhile::Done), 0 if every element was folded (Continue). */
+int ndb_zip_fold_while(ndb_ctx *ctx, int op, const void *scalars, int n_inputs, const ndb_view *inputs, int redop, const void *init,
+                       int stop_op, const void *stop_value, void *out_host, int *done);
 /* Zip::map_collect's output-order rule (src/zip/mod.rs:278-281,764-789): returns 1 if the fresh
  * output must be F-order, 0 for C-order, given the INPUT producers only. */
 int ndb_zip_prefer_f(int n_inputs, const ndb_view *inputs);

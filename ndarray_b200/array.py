@@ -876,6 +876,23 @@ class Zip:
 
     par_fold = fold
 
+    def fold_while(self, init, op: int, fold: str, stop_op: int, stop_value, scalars=()):
+        """Zip::fold_while (src/zip/mod.rs:640): fold op(inputs) in traversal order until the first value with
+        `value <stop_op> stop_value`; returns (accumulator, done) where done is True for FoldWhile::Done."""
+        redop = {"sum": Red.SUM, "prod": Red.PROD, "min": Red.MIN, "max": Red.MAX}[fold]
+        n = len(self.parts)
+        dt = self.parts[0].dtype
+        views = (View * n)(*[p.v for p in self.parts])
+        sc = np.asarray(scalars, dtype=dt) if len(scalars) else None
+        ini = np.asarray(init, dtype=dt) if init is not None else None
+        sv = np.asarray(stop_value, dtype=dt)
+        out = np.zeros((), dtype=dt)
+        done = C.c_int()
+        check(lib().ndb_zip_fold_while(self._ctx().handle, op, C.c_void_p(sc.ctypes.data) if sc is not None else None, n, views, redop,
+                                       C.c_void_p(ini.ctypes.data) if ini is not None else None, stop_op, C.c_void_p(sv.ctypes.data),
+                                       C.c_void_p(out.ctypes.data), C.byref(done)))
+        return out[()], bool(done.value)
+
     @staticmethod
     def indexed(p: "Array") -> "Zip":
         """Zip::indexed (src/zip/mod.rs:237): the index along each axis rides along as extra producers (broadcast

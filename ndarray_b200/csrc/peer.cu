@@ -22,6 +22,7 @@ __device__ __forceinline__ T combine(T a, T b)
 template <typename T, int REDOP>
 __global__ void __launch_bounds__(256) peer_exchange(PeerArgs p, const T *local, T *out, int64_t n)
 {
+    pdl_wait_only();
     constexpr int VEC = 16 / sizeof(T);
     int64_t per = (n + gridDim.x - 1) / gridDim.x;
     per = (per + VEC - 1) / VEC * VEC;  // slices start on 16-byte boundaries

@@ -718,7 +718,7 @@ __global__ void __launch_bounds__(256) red_all_finish(const void *partial, int n
 template <typename T, int R>
 __global__ void __launch_bounds__(256) red_all_finish_peer(const void *partial, int n, T *out, PeerArgs pa)
 {
-    pdl_enter();
+    pdl_wait_only();
     __shared__ Acc<T, R> smem[32];
     const Acc<T, R> *p = reinterpret_cast<const Acc<T, R> *>(partial);
     Acc<T, R> acc;

@@ -139,6 +139,23 @@ static bool is_predicate(int op) { return op >= NDB_OP_EQ && op <= NDB_OP_GE; }
 
 }  // namespace ndb
 
+// ---- Zip::fold_while (src/zip/mod.rs:640-655) -----------------------------------------------------------------------
+// FoldWhile::Done has a meaning only relative to a traversal ORDER, which a tree reduction does not have; the device form
+// keeps the order explicit: the closure's values are materialised in Zip's traversal order (C, or F when the producers
+// prefer it), the FIRST position where the stop predicate holds is found, and the fold runs over the prefix before it.
+template <typename T>
+__global__ void __launch_bounds__(256) first_nonzero_kernel(const T *flags, int64_t n, unsigned long long *first)
+{
+    pdl_enter();
+    const int64_t stride = (int64_t)gridDim.x * 256;
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += stride) {
+        if (flags[i] != T(0)) {
+            atomicMin(first, (unsigned long long)i);
+            break;  // this thread's later indices are larger
+        }
+    }
+}
+
 // acc = redop(acc, x) on the host, in the element type (wrapping integers, Rust's NaN-ignoring min / max)
 template <typename T>
 static void host_combine(int redop, T *acc, T x)
@@ -245,6 +262,95 @@ int ndb_zip_fold(ndb_ctx *ctx, int op, const void *scalars, int n_inputs, const 
     }
     return NDB_OK;
 }
+
+int ndb_zip_fold_while(ndb_ctx *ctx, int op, const void *scalars, int n_inputs, const ndb_view *inputs, int redop, const void *init,
+                       int stop_op, const void *stop_value, void *out_host, int *done)
+{
+    clear_error();
+    if (!ctx || !out_host || !done || !inputs || !stop_value || redop < NDB_RED_SUM || redop > NDB_RED_MAX || !is_predicate(stop_op)) {
+        set_error("Zip::fold_while: need an associative accumulator (sum/prod/min/max), a stop predicate (NDB_OP_EQ..GE) with its value, and result pointers");
+        return NDB_ERR_INVALID_ARG;
+    }
+    if (n_inputs < 1 || n_inputs > NDB_MAX_PARTS - 1) {
+        set_error("Zip: between 1 and %d input producers are supported", NDB_MAX_PARTS - 1);
+        return NDB_ERR_UNSUPPORTED;
+    }
+    *done = 0;
+    NDB_TRY(validate_view(&inputs[0], "Zip producer"));
+    const int dt = inputs[0].dtype;
+    const size_t esz = dtype_size(dt);
+    // scratch in traversal order: F-order iff the producers prefer it (src/zip/mod.rs:278-281)
+    const bool f_order = ndb_zip_prefer_f(n_inputs, inputs) != 0;
+    ndb_view parts[NDB_MAX_PARTS];
+    ndb_view &vals = parts[0];
+    memset(&vals, 0, sizeof(vals));
+    vals.ndim = inputs[0].ndim;
+    vals.dtype = dt;
+    int64_t total = 1;
+    for (int k = 0; k < vals.ndim; ++k) {
+        const int i = f_order ? k : vals.ndim - 1 - k;
+        vals.dim[i] = inputs[0].dim[i];
+        vals.stride[i] = total;
+        total *= vals.dim[i];
+    }
+    for (int p = 0; p < n_inputs; ++p) parts[p + 1] = inputs[p];
+    if (total == 0) {  // nothing to visit: the initial accumulator, not Done
+        vals.ptr = inputs[0].ptr;
+        ZipPlan z;
+        NDB_TRY(make_zip_plan(op, n_inputs + 1, parts, &z));
+        return ndb_zip_fold(ctx, op, scalars, n_inputs, inputs, redop, init, out_host);
+    }
+    DeviceGuard g(ctx->device);
+    char *buf = nullptr;  // [values | flags | stop value | first index]
+    const size_t vec = ((size_t)total * esz + 255) & ~(size_t)255;
+    NDB_CUDA(cudaMallocAsync((void **)&buf, 2 * vec + 512, ctx->stream));
+    vals.ptr = buf;
+    int st = ndb_zip(ctx, op, scalars, n_inputs + 1, parts);
+    unsigned long long first = (unsigned long long)total;
+    if (st == NDB_OK) {
+        ndb_view flat = vals, flags, sv;
+        flat.ndim = 1;
+        flat.dim[0] = total;
+        flat.stride[0] = 1;
+        flags = flat;
+        flags.ptr = buf + vec;
+        sv = flat;
+        sv.ptr = buf + 2 * vec;
+        sv.stride[0] = 0;  // the stop value, broadcast
+        memcpy(ctx->host_scalar, stop_value, esz);
+        *(unsigned long long *)((char *)ctx->host_scalar + 8) = first;
+        if (cudaMemcpyAsync(buf + 2 * vec, ctx->host_scalar, 16, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) st = NDB_ERR_CUDA;
+        ndb_view cmp[3] = {flags, flat, sv};
+        if (st == NDB_OK) st = ndb_zip(ctx, stop_op, nullptr, 3, cmp);
+        if (st == NDB_OK) {
+            unsigned long long *dev_first = (unsigned long long *)(buf + 2 * vec + 8);
+            const unsigned blocks = (unsigned)std::max<int64_t>(1, std::min<int64_t>((int64_t)ctx->sm_count * 8, (total + 255) / 256));
+            switch (dt) {
+            case NDB_F32: launch_pdl(first_nonzero_kernel<float>, blocks, 256, 0, ctx->stream, (const float *)flags.ptr, total, dev_first); break;
+            case NDB_F64: launch_pdl(first_nonzero_kernel<double>, blocks, 256, 0, ctx->stream, (const double *)flags.ptr, total, dev_first); break;
+            case NDB_I32: launch_pdl(first_nonzero_kernel<int32_t>, blocks, 256, 0, ctx->stream, (const int32_t *)flags.ptr, total, dev_first); break;
+            default: launch_pdl(first_nonzero_kernel<int64_t>, blocks, 256, 0, ctx->stream, (const int64_t *)flags.ptr, total, dev_first); break;
+            }
+            g_launches.fetch_add(1, std::memory_order_relaxed);
+            if (cudaMemcpyAsync(ctx->host_scalar, dev_first, 8, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess ||
+                cudaStreamSynchronize(ctx->stream) != cudaSuccess)
+                st = NDB_ERR_CUDA;
+            else first = *(unsigned long long *)ctx->host_scalar;
+        }
+        if (st == NDB_OK) {
+            *done = first < (unsigned long long)total ? 1 : 0;
+            flat.dim[0] = (int64_t)first;  // the prefix before the stopping element
+            ndb_view one[1] = {flat};
+            st = ndb_zip_fold(ctx, NDB_OP_COPY, nullptr, 1, one, redop, init, out_host);
+            if (st == NDB_ERR_EMPTY) {  // min / max over an empty prefix without an initial value
+                set_error("Zip::fold_while(min/max) stopped before the first element and no initial value was given");
+            }
+        }
+    }
+    cudaFreeAsync(buf, ctx->stream);
+    return st;
+}
+
 
 }  // extern "C"
 

@@ -507,6 +507,15 @@ impl<A: Elem> Zip<A> {
                                          &init as *const A as *const c_void, &mut out as *mut A as *mut c_void) });
         out
     }
+    /// `fold_while(init, |acc, ..| if v <stop> s { FoldWhile::Done(acc) } else { FoldWhile::Continue(acc <fold> v) })`
+    /// (src/zip/mod.rs:640-655) in Zip's traversal order; `FoldWhile` is ndarray's own type.
+    pub fn fold_while(self, init: A, op: Map, fold: Fold, stop: Pred, stop_value: A) -> ndarray::FoldWhile<A> where A: Default {
+        let (mut out, mut done) = (A::default(), 0i32);
+        check(unsafe { ffi::ndb_zip_fold_while(self.ctx, op as i32, std::ptr::null(), self.parts.len() as i32, self.parts.as_ptr(), fold as i32,
+                                               &init as *const A as *const c_void, stop as i32, &stop_value as *const A as *const c_void,
+                                               &mut out as *mut A as *mut c_void, &mut done) });
+        if done != 0 { ndarray::FoldWhile::Done(out) } else { ndarray::FoldWhile::Continue(out) }
+    }
     /// The kernel class the planner picks (debugging / tests).
     pub fn plan(&self, op: Map) -> ffi::ndb_zip_plan_t {
         let mut pl = std::mem::MaybeUninit::<ffi::ndb_zip_plan_t>::zeroed();

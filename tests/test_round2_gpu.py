@@ -238,3 +238,35 @@ def test_config4_full_size_gemm(nd, oracle, dtype, tol):
         err_full = np.abs(got - full).max() / scale
         assert err_rows <= lim, (orders, "vs Kahan rows", err_rows)
         assert err_full <= lim + blas_err, (orders, "vs OpenBLAS full", err_full, blas_err)
+
+
+def test_zip_fold_while(nd):
+    """Zip::fold_while (src/zip/mod.rs:640-655): fold in traversal order until the first value that satisfies the stop
+    predicate; FoldWhile::Done carries the accumulator of the prefix, FoldWhile::Continue the whole fold.  The order is
+    C for standard-layout producers and F when they prefer it (zip/mod.rs:278-281)."""
+    from ndarray_b200 import Array, Zip, Op
+    rng = np.random.default_rng(17)
+    for dtype in (np.int64, np.float64, np.float32, np.int32):
+        h = rng.integers(1, 50, (37, 53)).astype(dtype)
+        h[20, 11] = -5
+        h[30, 2] = -7
+        for order in ("C", "F"):
+            hh = np.asfortranarray(h) if order == "F" else h
+            d = Array.from_numpy(hh)
+            seq = hh.ravel(order=order)  # Zip's traversal order for this layout
+            first = int(np.argmax(seq < 0))
+            acc, done = Zip.from_(d).fold_while(dtype(3), Op.COPY, "sum", 27, 0)  # 27 = LT: stop at the first x < 0
+            assert done and acc == dtype(3) + seq[:first].sum(dtype=dtype), (dtype, order)
+            acc, done = Zip.from_(d).fold_while(None, Op.COPY, "max", 27, 0)
+            assert done and acc == seq[:first].max()
+            acc, done = Zip.from_(d).fold_while(dtype(0), Op.COPY, "sum", 27, -100)  # never fires: Continue(whole fold)
+            assert not done and acc == seq.sum(dtype=dtype)
+            # two producers: stop where a*b < 0
+            acc, done = Zip.from_(d).and_(d.view()).fold_while(dtype(0), Op.ADD, "sum", 27, 0)
+            assert done and acc == (2 * seq[:first]).sum(dtype=dtype)
+        first_elem = Array.from_numpy(np.array([-1, 2, 3], dtype=dtype))
+        acc, done = Zip.from_(first_elem).fold_while(dtype(9), Op.COPY, "sum", 27, 0)
+        assert done and acc == 9  # Done before anything was folded: the initial accumulator
+    e = Array.zeros((0, 3), np.float32)
+    acc, done = Zip.from_(e).fold_while(np.float32(1.5), Op.COPY, "sum", 27, 0)
+    assert not done and acc == 1.5
