@@ -227,6 +227,35 @@ def run_extras(nd, ctx, torch, dist, rank, world, local, peak_gbs):
                 dist.all_reduce(ts, op=dist.ReduceOp.MAX)
                 out[f"C3_sum_axis0_sharded_f64_{label}"] = {"GB/s_aggregate": round(gbs(8 * n * n + 8 * n, float(ts.item())), 1),
                                                            "ms": round(float(ts.item()), 4), "scaling": "strong: 16384^2 f64 over all ranks"}
+            # what actually crosses NVLink for the fused kernel: NVML's per-GPU NVLink data counters (KiB, all links) around
+            # 200 launches - the states are tiny next to the 2 GiB / N each rank streams from its own HBM
+            try:
+                import pynvml as nv
+                nv.nvmlInit()
+                h = nv.nvmlDeviceGetHandleByIndex(local)
+                ids = [getattr(nv, "NVML_FI_DEV_NVLINK_THROUGHPUT_DATA_TX", 138), getattr(nv, "NVML_FI_DEV_NVLINK_THROUGHPUT_DATA_RX", 139)]
+
+                def nvlink_kib():
+                    vals = nv.nvmlDeviceGetFieldValues(h, ids)
+                    return [int(v.value.ullVal) for v in vals]
+
+                if fused_ok:
+                    ctx.sync()
+                    dist.barrier()
+                    t0 = nvlink_kib()
+                    reps = 200
+                    for _ in range(reps):
+                        par._fused_axis0(slab, Red.VAR, 1.0, n, peers)
+                    ctx.sync()
+                    dist.barrier()
+                    t1 = nvlink_kib()
+                    tx, rx = (t1[0] - t0[0]) * 1024 / reps, (t1[1] - t0[1]) * 1024 / reps
+                    expect = (world - 1) * n * 24  # Welford (n, mean, M2) per column to every other rank
+                    out["C3_var_axis0_fused_nvlink_bytes_per_launch"] = {
+                        "tx": round(tx), "rx": round(rx), "expected_payload": expect, "hbm_bytes_read_per_rank": 8 * rows * n,
+                        "source": "NVML NVLINK_THROUGHPUT_DATA_TX/RX (all links of this GPU), rank 0, 200 launches"}
+            except Exception as e:  # noqa: BLE001
+                out["C3_var_axis0_fused_nvlink_bytes_per_launch"] = {"error": repr(e)}
             ctx.sync()
             dist.barrier()
             peers.close()

@@ -131,6 +131,10 @@ struct ndb_ctx {
     // pinned bounce buffers for PAGEABLE host memory (the CBLAS boundary hands in ndarray's Vec storage)
     void *bounce[2] = {nullptr, nullptr};
     cudaEvent_t bounce_ev[2] = {nullptr, nullptr};
+    // chained scan (scan.cu): ticket + per-chunk packets, and the epoch that marks this launch's packets
+    void *scan_chain = nullptr;
+    size_t scan_chain_bytes = 0;
+    uint32_t scan_epoch = 0;
     // NCCL communicator owned by the library (dist.cu; libnccl is dlopen'ed on first use)
     void *nccl_comm = nullptr;
     int comm_rank = -1, comm_world = 0;

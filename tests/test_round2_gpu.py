@@ -270,3 +270,37 @@ def test_zip_fold_while(nd):
     e = Array.zeros((0, 3), np.float32)
     acc, done = Zip.from_(e).fold_while(np.float32(1.5), Op.COPY, "sum", 27, 0)
     assert not done and acc == 1.5
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32, np.int64, np.int32])
+def test_chained_single_pass_scan(nd, dtype):
+    """The chained scan (long strided axis, few dense lanes: 64-row chunks passed from block to block through epoch-tagged
+    packets) against numpy: integers exact, floats to rounding; repeated launches reuse the packets (epochs), an outer kept
+    axis rides along, and a backwards scanned axis is walked in logical order."""
+    from ndarray_b200 import Array, Op, s_
+    rng = np.random.default_rng(41)
+    kind = np.dtype(dtype).kind
+    w = 16 // np.dtype(dtype).itemsize
+    for shape, axis in (((1024, 32 * w * 3), 0), ((3, 640, 32 * w), 1), ((4096, 32 * w), 0)):
+        h = (rng.integers(-3, 4, shape) if kind == "i" else 1.0 + 0.001 * rng.standard_normal(shape)).astype(dtype)
+        for op, ref in ((Op.ADD, np.cumsum), (Op.MUL, np.cumprod)):
+            for rep in range(3):
+                d = Array.from_numpy(h)
+                d.accumulate_axis_inplace(axis, op)
+                got = d.to_numpy()
+                want = ref(h.astype(np.float64) if kind == "f" else h, axis=axis)
+                if kind == "i":
+                    assert np.array_equal(got, want.astype(dtype)), (shape, axis, rep)
+                else:
+                    tol = (1e-12 if dtype == np.float64 else 1e-5) * np.sqrt(shape[axis]) * max(1.0, float(np.abs(want).max()))
+                    assert np.max(np.abs(got - want)) <= tol, (shape, axis, rep)
+    # reversed scanned axis and a leading -0.0 column
+    h = np.ones((1024, 32 * w), dtype)
+    d = Array.from_numpy(h)
+    d.slice(s_[::-1, :]).accumulate_axis_inplace(0, Op.ADD)
+    assert np.array_equal(d.to_numpy(), np.cumsum(h[::-1], axis=0)[::-1])
+    if kind == "f":
+        z = np.full((1024, 32 * w), -0.0, dtype)
+        dz = Array.from_numpy(z)
+        dz.accumulate_axis_inplace(0, Op.ADD)
+        assert np.all(np.signbit(dz.to_numpy()))
