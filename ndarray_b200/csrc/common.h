@@ -131,6 +131,8 @@ struct ndb_ctx {
     // pinned bounce buffers for PAGEABLE host memory (the CBLAS boundary hands in ndarray's Vec storage)
     void *bounce[2] = {nullptr, nullptr};
     cudaEvent_t bounce_ev[2] = {nullptr, nullptr};
+    void *bounce_out[2] = {nullptr, nullptr};  // second pair: a D2H worker thread drains results while the caller's thread uploads
+    cudaEvent_t bounce_out_ev[2] = {nullptr, nullptr};
     // chained scan (scan.cu): ticket + per-chunk packets, and the epoch that marks this launch's packets
     void *scan_chain = nullptr;
     size_t scan_chain_bytes = 0;
@@ -146,8 +148,9 @@ int ensure_stage(ndb_ctx *ctx, int slot, size_t bytes);
 // pageable host <-> device through two pinned bounce buffers: a few host threads copy chunk i+1 while the DMA engine
 // moves chunk i (cudaMemcpy from pageable memory runs at ~12 GB/s on these boxes, this pipeline at the threads' memcpy rate).
 // Ordered after / before work on ctx->stream; returns after the last chunk has been ISSUED (h2d) or has LANDED (d2h).
+int prepare_bounce(ndb_ctx *ctx);  // allocate both bounce pairs now (before a second host thread starts using them)
 int staged_h2d(ndb_ctx *ctx, void *dst_dev, const void *src_host, size_t bytes, cudaStream_t st = nullptr);
-int staged_d2h(ndb_ctx *ctx, void *dst_host, const void *src_dev, size_t bytes, cudaStream_t st = nullptr);
+int staged_d2h(ndb_ctx *ctx, void *dst_host, const void *src_dev, size_t bytes, cudaStream_t st = nullptr, int set = 0);
 int welford_merge_gathered(ndb_ctx *ctx, int dtype, int world, const int64_t *counts_dev, const void *means_dev, const void *m2s_dev,
                            int64_t n_out, int64_t pitch, double ddof, int want_std, void *out_dev);  // reduce.cu
 struct PeerArgs;

@@ -9,6 +9,9 @@
 //                      impl_linalg.rs:601-617; integers wrap).
 #include <algorithm>
 #include <mutex>
+#include <thread>
+#include <vector>
+#include <atomic>
 
 #include "gemm.h"
 #include "zip_kernels.cuh"
@@ -435,6 +438,87 @@ static BlasMat blas_operand(int layout, int trans, int64_t rows, int64_t cols, i
     return o;
 }
 
+// Large row-major products with an untransposed A: B goes up whole, then A and C travel in row blocks while the tensor
+// cores work - H2D of block i+1 (the caller's thread fills the pinned bounce buffers), the GEMM on block i (context stream)
+// and D2H of block i-1 (a worker thread with its own bounce pair) overlap, so the call costs about
+// upload(B) + max(GEMM, copies) instead of upload(A, B) + GEMM + download(C).
+template <typename T>
+static bool cblas_gemm_pipelined(ndb_ctx *ctx, int dtype, int transb, int m, int n, int k, T alpha, const T *a, int lda, const T *b, int ldb,
+                                 T beta, T *c, int ldc, const BlasMat &B, bool need_c)
+{
+    int nb = std::max(2, std::min(8, m / 2048));
+    if (getenv("NDB_CBLAS_BLOCKS")) nb = std::max(1, atoi(getenv("NDB_CBLAS_BLOCKS")));
+    const int64_t rows_per = (((int64_t)m + nb - 1) / nb + 127) / 128 * 128;
+    nb = (int)((m + rows_per - 1) / rows_per);
+    if (prepare_bounce(ctx) != NDB_OK) return false;
+    cudaStream_t s_in = ctx->copy_in, s_k = ctx->stream, s_out = ctx->copy_out;
+    std::vector<cudaEvent_t> ev_in(nb), ev_k(nb);
+    for (int i = 0; i < nb; ++i) {
+        if (cudaEventCreateWithFlags(&ev_in[i], cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&ev_k[i], cudaEventDisableTiming) != cudaSuccess)
+            return false;
+    }
+    cudaEvent_t ev_start, ev_b;
+    cudaEventCreateWithFlags(&ev_start, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&ev_b, cudaEventDisableTiming);
+    cudaEventRecord(ev_start, s_k);  // earlier work on the context stream may still use the staging buffers
+    cudaStreamWaitEvent(s_in, ev_start, 0);
+    cudaStreamWaitEvent(s_out, ev_start, 0);
+    bool ok = B.span == 0 || staged_h2d(ctx, ctx->stage[1], b, B.span * sizeof(T), s_in) == NDB_OK;
+    cudaEventRecord(ev_b, s_in);
+    cudaStreamWaitEvent(s_k, ev_b, 0);
+    std::atomic<int> issued{0};
+    std::atomic<bool> down_ok{true};
+    const int device = ctx->device;
+    std::thread drain([&] {
+        cudaSetDevice(device);
+        for (int i = 0; i < nb; ++i) {
+            while (issued.load(std::memory_order_acquire) <= i) {
+                if (issued.load(std::memory_order_acquire) < 0) return;  // the producer gave up
+                std::this_thread::yield();
+            }
+            const int64_t r0 = (int64_t)i * rows_per, rows = std::min<int64_t>(rows_per, m - r0);
+            const size_t bytes = (size_t)((rows - 1) * ldc + n) * sizeof(T);
+            if (cudaStreamWaitEvent(s_out, ev_k[i], 0) != cudaSuccess ||
+                staged_d2h(ctx, c + r0 * ldc, (const T *)ctx->stage[2] + r0 * ldc, bytes, s_out, 1) != NDB_OK) {
+                down_ok.store(false);
+                return;
+            }
+        }
+    });
+    ndb_view va, vb, vc;
+    memset(&va, 0, sizeof(va));
+    memset(&vb, 0, sizeof(vb));
+    memset(&vc, 0, sizeof(vc));
+    vb.ptr = ctx->stage[1]; vb.ndim = 2; vb.dtype = dtype; vb.dim[0] = k; vb.dim[1] = n; vb.stride[0] = B.rs; vb.stride[1] = B.cs;
+    for (int i = 0; i < nb && ok; ++i) {
+        const int64_t r0 = (int64_t)i * rows_per, rows = std::min<int64_t>(rows_per, m - r0);
+        const size_t a_bytes = (size_t)((rows - 1) * lda + k) * sizeof(T), c_bytes = (size_t)((rows - 1) * ldc + n) * sizeof(T);
+        ok = staged_h2d(ctx, (T *)ctx->stage[0] + r0 * lda, a + r0 * lda, a_bytes, s_in) == NDB_OK;
+        if (ok && need_c) ok = staged_h2d(ctx, (T *)ctx->stage[2] + r0 * ldc, c + r0 * ldc, c_bytes, s_in) == NDB_OK;
+        if (!ok) break;
+        cudaEventRecord(ev_in[i], s_in);
+        cudaStreamWaitEvent(s_k, ev_in[i], 0);
+        va.ptr = (T *)ctx->stage[0] + r0 * lda; va.ndim = 2; va.dtype = dtype; va.dim[0] = rows; va.dim[1] = k; va.stride[0] = lda; va.stride[1] = 1;
+        vc.ptr = (T *)ctx->stage[2] + r0 * ldc; vc.ndim = 2; vc.dtype = dtype; vc.dim[0] = rows; vc.dim[1] = n; vc.stride[0] = ldc; vc.stride[1] = 1;
+        ok = gemm_impl(ctx, &alpha, &va, &vb, &beta, &vc) == NDB_OK;
+        if (!ok) break;
+        cudaEventRecord(ev_k[i], s_k);
+        issued.store(i + 1, std::memory_order_release);
+    }
+    if (!ok) issued.store(-1, std::memory_order_release);
+    drain.join();
+    ok = ok && down_ok.load();
+    if (ok) ok = cudaStreamSynchronize(s_in) == cudaSuccess && cudaStreamSynchronize(s_k) == cudaSuccess && cudaStreamSynchronize(s_out) == cudaSuccess;
+    for (int i = 0; i < nb; ++i) {
+        cudaEventDestroy(ev_in[i]);
+        cudaEventDestroy(ev_k[i]);
+    }
+    cudaEventDestroy(ev_start);
+    cudaEventDestroy(ev_b);
+    (void)transb;
+    return ok;
+}
+
 template <typename T>
 static void cblas_gemm_impl(int dtype, int layout, int transa, int transb, int m, int n, int k, T alpha, const T *a, int lda,
                             const T *b, int ldb, T beta, T *c, int ldc)
@@ -443,19 +527,37 @@ static void cblas_gemm_impl(int dtype, int layout, int transa, int transb, int m
     if (!ctx) abort();  // a void CBLAS call has no error channel; never compute wrong results silently
     std::lock_guard<std::mutex> lk(g_blas_mu);
     DeviceGuard guard(ctx->device);
+    if (m == 0 || n == 0) return;
+    if (layout == NdbCblasColMajor) {
+        // the same memory read row-major holds the transposes: C^T = op(B)^T op(A)^T, i.e. the row-major call with the
+        // operands (and their transpose flags, and m / n) exchanged
+        std::swap(a, b);
+        std::swap(lda, ldb);
+        std::swap(transa, transb);
+        std::swap(m, n);
+        layout = NdbCblasRowMajor;
+    }
     const BlasMat A = blas_operand(layout, transa, m, k, lda);
     const BlasMat B = blas_operand(layout, transb, k, n, ldb);
     const BlasMat Cm = blas_operand(layout, NdbCblasNoTrans, m, n, ldc);
-    if (m == 0 || n == 0) return;
     bool ok = ensure_stage(ctx, 0, std::max<size_t>(16, A.span * sizeof(T))) == NDB_OK &&
               ensure_stage(ctx, 1, std::max<size_t>(16, B.span * sizeof(T))) == NDB_OK &&
               ensure_stage(ctx, 2, std::max<size_t>(16, Cm.span * sizeof(T))) == NDB_OK;
+    // C travels up even for beta == 0 when it has padding (ldc > n), so the padding survives the trip back
+    const bool c_dense = ldc == n;
+    const bool need_c = beta != T(0) || !c_dense;
+    const bool big = (size_t)A.span * sizeof(T) >= (size_t(64) << 20) && m >= 2048 && k > 0;
+    if (ok && big && transa == NdbCblasNoTrans && !getenv("NDB_CBLAS_NO_PIPELINE")) {
+        ok = cblas_gemm_pipelined<T>(ctx, dtype, transb, m, n, k, alpha, a, lda, b, ldb, beta, c, ldc, B, need_c);
+        if (!ok) {
+            fprintf(stderr, "libndb200: cblas gemm failed: %s\n", ndb_last_error());
+            abort();
+        }
+        return;
+    }
     if (ok && A.span) ok = staged_h2d(ctx, ctx->stage[0], a, A.span * sizeof(T)) == NDB_OK;
     if (ok && B.span) ok = staged_h2d(ctx, ctx->stage[1], b, B.span * sizeof(T)) == NDB_OK;
-    // C travels up even for beta == 0 when it has padding (ldc > minor), so the padding survives the trip back
-    const bool c_dense = (layout == NdbCblasRowMajor ? ldc == n : ldc == m);
-    if (ok && (beta != T(0) || !c_dense))
-        ok = staged_h2d(ctx, ctx->stage[2], c, Cm.span * sizeof(T)) == NDB_OK;
+    if (ok && need_c) ok = staged_h2d(ctx, ctx->stage[2], c, Cm.span * sizeof(T)) == NDB_OK;
     ndb_view va, vb, vc;
     memset(&va, 0, sizeof(va));
     memset(&vb, 0, sizeof(vb));

@@ -374,3 +374,52 @@ def test_cblas_large_operands_bounce_pipeline(nd):
     ref = 1.5 * (a @ b) - 0.5 * c0[:, :n]
     assert rel_norm(c[:, :n], ref) < 1e-12 * math.sqrt(k)
     assert np.array_equal(c[:, n:], c0[:, n:])
+
+
+def test_cblas_pipelined_row_blocks(nd):
+    """Large row-major products with an untransposed A take the pipelined path (B up whole, A and C in row blocks, a worker
+    thread draining C): every layout ndarray's `blas` feature produces must come back identical to the one-shot path's
+    result and within tolerance of the reference - row-major, column-major (exchanged into row-major inside), transposed B,
+    padded ldc with beta != 0, and a row count that is not a multiple of the block."""
+    import os
+    L = nd.lib()
+    L.cblas_dgemm.restype = None
+    L.cblas_dgemm.argtypes = [C.c_int] * 6 + [C.c_double, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_double, C.c_void_p, C.c_int]
+    L.cblas_sgemm.restype = None
+    L.cblas_sgemm.argtypes = [C.c_int] * 6 + [C.c_float, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_float, C.c_void_p, C.c_int]
+    rng = np.random.default_rng(33)
+    m, n, k = 4200, 1030, 2100                      # A: 67 MiB (f64) -> pipelined; 4200 rows = 2 blocks of 2176 / 2024
+    a = rng.standard_normal((m, k))
+    b = rng.standard_normal((k, n))
+    bt = np.ascontiguousarray(b.T)
+    c0 = rng.standard_normal((m, n + 6))
+    ref = -2.3 * (a @ b) + math.pi * c0[:, :n]
+
+    def run(pipelined, transb):
+        if pipelined:
+            os.environ.pop("NDB_CBLAS_NO_PIPELINE", None)
+        else:
+            os.environ["NDB_CBLAS_NO_PIPELINE"] = "1"
+        c = c0.copy()
+        if transb:
+            L.cblas_dgemm(101, 111, 112, m, n, k, -2.3, a.ctypes.data, k, bt.ctypes.data, k, math.pi, c.ctypes.data, n + 6)
+        else:
+            L.cblas_dgemm(101, 111, 111, m, n, k, -2.3, a.ctypes.data, k, b.ctypes.data, n, math.pi, c.ctypes.data, n + 6)
+        os.environ.pop("NDB_CBLAS_NO_PIPELINE", None)
+        return c
+
+    for transb in (False, True):
+        one, pipe = run(False, transb), run(True, transb)
+        assert rel_norm(pipe[:, :n], ref) < 1e-12 * math.sqrt(k)
+        assert np.array_equal(pipe[:, n:], c0[:, n:])          # padding untouched
+        assert np.array_equal(one, pipe)                        # row blocks change no row's arithmetic
+    # column-major C = A B with A (m x k) stored column-major is the row-major product C^T = B^T A^T: pipelined over B's columns
+    af, bf = np.asfortranarray(a[:1100]), np.asfortranarray(rng.standard_normal((k, 4300)))
+    cf = np.zeros((1100, 4300), order="F")
+    L.cblas_dgemm(102, 111, 111, 1100, 4300, k, 1.0, af.ctypes.data, 1100, bf.ctypes.data, k, 0.0, cf.ctypes.data, 1100)
+    assert rel_norm(cf, af @ bf) < 1e-12 * math.sqrt(k)
+    # f32
+    a32, b32 = rng.standard_normal((8300, 2100)).astype(np.float32), rng.standard_normal((2100, 520)).astype(np.float32)
+    c32 = np.zeros((8300, 520), np.float32)
+    L.cblas_sgemm(101, 111, 111, 8300, 520, 2100, 1.0, a32.ctypes.data, 2100, b32.ctypes.data, 520, 0.0, c32.ctypes.data, 520)
+    assert rel_norm(c32, a32.astype(np.float64) @ b32.astype(np.float64)) < 1e-5
