@@ -304,3 +304,40 @@ def test_chained_single_pass_scan(nd, dtype):
         dz = Array.from_numpy(z)
         dz.accumulate_axis_inplace(0, Op.ADD)
         assert np.all(np.signbit(dz.to_numpy()))
+
+
+def test_swap_axes_insert_axis_and_azip(nd, oracle):
+    """The axis transforms that had no test in round 1 (src/impl_methods.rs:2487 swap_axes, :2700 insert_axis) and the
+    azip! / par_azip! sugar (src/zip/zipmacro.rs:98): views must address exactly the elements numpy's do, and Zips over
+    them must match the oracle bit for bit."""
+    from ndarray_b200 import Array, NewAxis, Zip, azip, par_azip, s_
+    rng = np.random.default_rng(71)
+    h = rng.integers(-1000, 1000, (5, 7, 9)).astype(np.int64)
+    d = Array.from_numpy(h)
+    for a, b in ((0, 2), (1, 2), (0, 0)):
+        v = d.swap_axes(a, b)
+        assert v.shape == np.swapaxes(h, a, b).shape and v.strides == tuple(s // 8 for s in np.swapaxes(h, a, b).strides)
+        assert np.array_equal(v.to_numpy(), np.swapaxes(h, a, b))
+    for ax in (0, 1, 3):
+        v = d.insert_axis(ax)
+        assert v.shape == np.expand_dims(h, ax).shape
+        assert np.array_equal(v.to_numpy(), np.expand_dims(h, ax))
+        # the new unit axis broadcasts like any other: out[.., j, ..] = v for j in 0..3
+        shape = list(v.shape)
+        shape[ax] = 4
+        out = Array.zeros(tuple(shape), np.int64)
+        Zip.from_(out).and_broadcast(v).for_each("a=b")
+        assert np.array_equal(out.to_numpy(), np.broadcast_to(np.expand_dims(h, ax), shape))
+    # s![.., NewAxis, ..] goes through insert_axis as well
+    v = d.slice(s_[:, NewAxis, ::2, :])
+    assert v.shape == h[:, np.newaxis, ::2, :].shape and np.array_equal(v.to_numpy(), h[:, np.newaxis, ::2, :])
+    # azip!((a in &mut a, &b in &b, &c in &c) *a = b * c + *a) on swapped views
+    fa, fb, fc = (rng.standard_normal((6, 8)).astype(np.float32) for _ in range(3))
+    da, db, dc = Array.from_numpy(fa), Array.from_numpy(np.ascontiguousarray(fb.T)), Array.from_numpy(fc)
+    azip("a=b*c+a", da, db.swap_axes(0, 1), dc)
+    want = fa.copy()
+    assert oracle.zip_(7, want, [fb, fc, want]) == 0
+    assert_bit_equal(da.to_numpy(), want, "azip on a swapped view")
+    par_azip("a+=b", da, dc)
+    assert oracle.zip_(2, want, [want, fc]) == 0
+    assert_bit_equal(da.to_numpy(), want, "par_azip")
