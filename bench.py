@@ -416,6 +416,41 @@ def main():
     # ---- what limits scaling: the A/B exchange, and the exchange alone ---------------------------------
     breakdown = {"zip_ms": zip_ms_max, "sum_with_exchange_ms": sum_ms_max, "exchange": exchange,
                  "ideal_ms_per_step_at_measured_peak": STEP_BYTES / world / (peaks()[0] * 1e9) * 1e3}
+    # the same step as ONE fused pass (Zip::fold whose closure writes `a`: 16 B per element instead of 20), exchange included
+    try:
+        fparts = (View * 4)(a.v, b.v, c.v, a.v)
+        fused_across = 1 if (peers is not None and world > 1) else 0
+
+        def fused_step():
+            check(L.ndb_zip_fold_write(ctx.handle, OP_MUL_ADD, None, 4, fparts, RED_SUM, C.c_void_p(acc.v.ptr), fused_across))
+            if world > 1 and not fused_across:
+                with torch.cuda.stream(stream):
+                    dist.all_reduce(acc_t)
+
+        fill()
+        fused_step()
+        fused_sum = float(acc.to_numpy()[()])
+        fused_rows_ok = all(np.array_equal(a.index_axis(0, r - lo).to_numpy(), want_rows[r]) for r in sample)
+        for _ in range(args.warmup):
+            fused_step()
+        barrier()
+        e0, e1 = ctx.event(), ctx.event()
+        barrier()
+        ctx.record(e0)
+        for _ in range(args.steps):
+            fused_step()
+        ctx.record(e1)
+        barrier()
+        fms = max_over_ranks(ctx.elapsed_ms(e0, e1)) / args.steps
+        breakdown["fused_zip_fold_step"] = {
+            "ms_per_step": fms, "speedup_vs_two_kernels": (total_ms / args.steps) / fms,
+            "actual_GB/s_at_16B_per_element": 16 * n_total / (fms * 1e-3) / 1e9,
+            "rows_bit_exact": bool(fused_rows_ok),
+            "sum_within_tolerance": (bool(abs(fused_sum - parity["sum_f64_oracle"]) <= parity["sum_tolerance"]) if rank == 0 and "sum_f64_oracle" in parity else None),
+            "api": "ndb_zip_fold_write(MUL_ADD, (a; b, c, a), SUM): Zip::fold whose closure also writes a - not the headline (the reference's "
+                   "idiom is two passes), reported as what fusion buys"}
+    except Exception as e:  # noqa: BLE001
+        breakdown["fused_zip_fold_step"] = {"error": repr(e)}
     if peer_err:
         breakdown["peer_windows_error"] = peer_err
     if world > 1:

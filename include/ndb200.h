@@ -266,6 +266,15 @@ int ndb_zip_fold_sum(ndb_ctx *ctx, int op, const void *scalars, int n_inputs, co
  * evaluated as a tree and are out of scope (fold_axis has the same restriction). */
 int ndb_zip_fold(ndb_ctx *ctx, int op, const void *scalars, int n_inputs, const ndb_view *inputs, int redop, const void *init,
                  void *out_host);
+/* Zip::fold whose closure also WRITES through its first producer, e.g.
+ *     Zip::from(&mut a).and(&b).and(&c).fold(0., |acc, a, &b, &c| { *a = b * c + *a; acc + *a })
+ * parts are as in ndb_zip (parts[0] written, the rest read), and the values written are folded with redop into the DEVICE
+ * scalar `out_dev` (element type; asynchronous on the context stream).  Dense producers take one fused pass (elementwise +
+ * reduction: BASELINE config 5 at 16 bytes per element instead of 20); anything else runs the Zip and then the reduction.
+ * across_ranks != 0: the kernel that finishes the fold also exchanges the scalar through the peer windows, every rank
+ * receives the fold over ALL shards (windows must be attached). */
+int ndb_zip_fold_write(ndb_ctx *ctx, int op, const void *scalars, int n_parts, const ndb_view *parts, int redop, void *out_dev,
+                       int across_ranks);
 /* Zip::fold_while (src/zip/mod.rs:640-655) for the same associative accumulators.  FoldWhile::Done only means something
  * relative to a traversal order, so the order is kept explicit: the values op(inputs...) are laid out in Zip's traversal
  * order (C, or F when the producers prefer it, zip/mod.rs:278-281), the FIRST position whose value satisfies

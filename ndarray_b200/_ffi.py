@@ -114,6 +114,7 @@ def lib():
         "ndb_zip_any": (i32, [vp, i32, vp, i32, PV, C.POINTER(i32)]),
         "ndb_zip_fold_sum": (i32, [vp, i32, vp, i32, PV, vp]),
         "ndb_zip_fold": (i32, [vp, i32, vp, i32, PV, i32, vp, vp]),
+        "ndb_zip_fold_write": (i32, [vp, i32, vp, i32, PV, i32, vp, i32]),
         "ndb_zip_fold_while": (i32, [vp, i32, vp, i32, PV, i32, vp, i32, vp, vp, C.POINTER(i32)]),
         "ndb_var": (i32, [vp, PV, dbl, i32, vp]),
         "ndb_reduce_all": (i32, [vp, i32, PV, vp]),

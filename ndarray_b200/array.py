@@ -813,6 +813,25 @@ class Zip:
 
     par_for_each = for_each  # the GPU grid is the rayon pool (src/parallel/impl_par_methods.rs:64)
 
+    def for_each_fold(self, closure, fold: str = "sum", scalars=(), out: "Array | None" = None, across_ranks: bool = False):
+        """Zip::fold whose closure also writes its first producer (src/zip/mod.rs:622), e.g.
+        `fold(0., |acc, a, &b, &c| { *a = b*c + *a; acc + *a })` = for_each_fold("a=b*c+a", "sum"): one fused pass when the
+        producers are dense.  Returns the folded value (host), or leaves it in the 0-d device array `out` (asynchronous)."""
+        redop = {"sum": Red.SUM, "prod": Red.PROD, "min": Red.MIN, "max": Red.MAX}[fold]
+        if isinstance(closure, str):
+            op, out_i, ins = _CLOSURES[closure]
+        else:
+            op, out_i, ins = closure, 0, tuple(range(1, len(self.parts)))
+        parts_l = [self.parts[out_i]] + [self.parts[i] for i in ins]
+        n = len(parts_l)
+        views = (View * n)(*[p.v for p in parts_l])
+        dt = self.parts[0].dtype
+        sc = np.asarray(scalars, dtype=dt) if len(scalars) else None
+        dev = out if out is not None else Array.zeros((), dt, ctx=self._ctx())
+        check(lib().ndb_zip_fold_write(self._ctx().handle, op, C.c_void_p(sc.ctypes.data) if sc is not None else None, n, views, redop,
+                                       C.c_void_p(dev.v.ptr), int(across_ranks)))
+        return None if out is not None else dev.to_numpy()[()]
+
     def map_collect(self, op: int, scalars=()) -> Array:
         """Zip::map_collect (src/zip/mod.rs:764-789): fresh output, F-order iff prefer_f()."""
         n = len(self.parts)

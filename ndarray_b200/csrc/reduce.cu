@@ -38,6 +38,9 @@
 #ifndef NDB_RED_COLS_U
 #define NDB_RED_COLS_U 8
 #endif
+#ifndef NDB_ZIP_FOLD_U
+#define NDB_ZIP_FOLD_U 2
+#endif
 #ifndef NDB_RED_COLS_WU
 #define NDB_RED_COLS_WU 8
 #endif
@@ -905,6 +908,137 @@ int zip2_reduce_dense(ndb_ctx *ctx, int op, int redop, int dtype, const void *x,
     return NDB_ERR_UNSUPPORTED;
 }
 
+// Fused Zip + fold of the WRITTEN values over dense, 16-byte aligned producers: out[i] = op(in...[i]) is stored and, in the
+// same pass, reduced.  This is `Zip::fold` whose closure also writes through its first producer -
+//     Zip::from(&mut a).and(&b).and(&c).fold(0., |acc, a, &b, &c| { *a = b * c + *a; acc + *a })
+// - i.e. BASELINE config 5 (elementwise, then the global sum) in ONE pass: 16 bytes per element instead of 20.
+// Persistent grid (one resident wave), two vectors per producer in flight per thread.
+template <typename T, int OP, int NIN, int R>
+__global__ void __launch_bounds__(256) zip_fold_flat(FlatArgs<NIN + 1> a, T s0, T s1, int *flag, void *partial)
+{
+    pdl_enter();
+    using V = Vec128<T>;
+    constexpr int N = V::N;
+    constexpr int U = NDB_ZIP_FOLD_U;
+    __shared__ Acc<T, R> smem[32];
+    Acc<T, R> acc;
+    acc.reset();
+    const int64_t stride = (int64_t)gridDim.x * 256;
+    int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    for (; i + (U - 1) * stride < a.n_vec; i += U * stride) {
+        V in[U][NIN];
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+#pragma unroll
+            for (int p = 0; p < NIN; ++p) in[u][p] = reinterpret_cast<const V *>(a.ptr[p + 1])[i + u * stride];
+        T outv[U * N];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            V o;
+#pragma unroll
+            for (int e = 0; e < N; ++e) {
+                T x[NIN];
+#pragma unroll
+                for (int p = 0; p < NIN; ++p) x[p] = in[u][p].v[e];
+                o.v[e] = apply_op<T, OP, NIN>(x, s0, s1, flag);
+                outv[u * N + e] = o.v[e];
+            }
+            reinterpret_cast<V *>(a.ptr[0])[i + u * stride] = o;
+        }
+        acc.template add_batch<U * N>(outv);
+    }
+    for (; i < a.n_vec; i += stride) {
+        V o;
+#pragma unroll
+        for (int e = 0; e < N; ++e) {
+            T x[NIN];
+#pragma unroll
+            for (int p = 0; p < NIN; ++p) x[p] = reinterpret_cast<const V *>(a.ptr[p + 1])[i].v[e];
+            o.v[e] = apply_op<T, OP, NIN>(x, s0, s1, flag);
+        }
+        reinterpret_cast<V *>(a.ptr[0])[i] = o;
+        acc.template add_batch<N>(o.v);
+    }
+    if (blockIdx.x == 0) {  // ragged tail (< N elements), one thread each
+        const int64_t t = a.n_vec * N + threadIdx.x;
+        if (t < a.n) {
+            T x[NIN];
+#pragma unroll
+            for (int p = 0; p < NIN; ++p) x[p] = reinterpret_cast<const T *>(a.ptr[p + 1])[t];
+            const T o = apply_op<T, OP, NIN>(x, s0, s1, flag);
+            reinterpret_cast<T *>(a.ptr[0])[t] = o;
+            acc.add(o);
+        }
+    }
+    acc = block_reduce(acc, smem);
+    if (threadIdx.x == 0) reinterpret_cast<Acc<T, R> *>(partial)[blockIdx.x] = acc;
+}
+
+template <typename T, int OP, int NIN, int R>
+static int zip_fold_launch(ndb_ctx *ctx, const ZipPlan &z, const void *scalars, T *out_dev, bool peer)
+{
+    FlatArgs<NIN + 1> a;
+    for (int p = 0; p <= NIN; ++p) a.ptr[p] = z.ptr[p];
+    a.n = z.total;
+    a.n_vec = z.total / Vec128<T>::N;
+    T s0 = T(0), s1 = T(0);
+    const int ns = op_scalars(OP);
+    if (ns >= 1 && scalars) s0 = ((const T *)scalars)[0];
+    if (ns >= 2 && scalars) s1 = ((const T *)scalars)[1];
+    const int max_blocks = ctx->sm_count * (getenv("NDB_ZIP_FOLD_PER_SM") ? std::max(1, atoi(getenv("NDB_ZIP_FOLD_PER_SM"))) : 4);  // 2^32 f32 MUL_ADD + sum, per SM 4 / 6 / 8: 10.18 / 10.49 / 10.58 ms
+    NDB_TRY(ensure_workspace(ctx, (size_t)max_blocks * sizeof(Acc<T, R>)));
+    const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>(max_blocks, (a.n_vec + 511) / 512));
+    launch_pdl(zip_fold_flat<T, OP, NIN, R>, blocks, 256, 0, ctx->stream, a, s0, s1, ctx->dev_flag, ctx->workspace);
+    NDB_CHECK_LAUNCH();
+    if (peer) {
+        PeerArgs pa;
+        NDB_TRY(peer_begin(ctx, 1, sizeof(T), &pa));
+        launch_pdl(red_all_finish_peer<T, R>, 1, 256, 0, ctx->stream, ctx->workspace, blocks, out_dev, pa);
+    } else {
+        launch_pdl(red_all_finish<T, R>, 1, 256, 0, ctx->stream, ctx->workspace, blocks, out_dev, T(1), 0);
+    }
+    NDB_CHECK_LAUNCH();
+    return NDB_OK;
+}
+
+template <typename T, int R>
+static int zip_fold_op(ndb_ctx *ctx, const ZipPlan &z, const void *scalars, T *out_dev, bool peer)
+{
+    switch (z.op) {
+    case NDB_OP_COPY: return zip_fold_launch<T, NDB_OP_COPY, 1, R>(ctx, z, scalars, out_dev, peer);
+    case NDB_OP_ADD: return zip_fold_launch<T, NDB_OP_ADD, 2, R>(ctx, z, scalars, out_dev, peer);
+    case NDB_OP_SUB: return zip_fold_launch<T, NDB_OP_SUB, 2, R>(ctx, z, scalars, out_dev, peer);
+    case NDB_OP_MUL: return zip_fold_launch<T, NDB_OP_MUL, 2, R>(ctx, z, scalars, out_dev, peer);
+    case NDB_OP_AXPY: return zip_fold_launch<T, NDB_OP_AXPY, 2, R>(ctx, z, scalars, out_dev, peer);
+    case NDB_OP_MUL_ADD: return zip_fold_launch<T, NDB_OP_MUL_ADD, 3, R>(ctx, z, scalars, out_dev, peer);
+    default: return NDB_ERR_UNSUPPORTED;
+    }
+}
+
+template <typename T>
+static int zip_fold_typed(ndb_ctx *ctx, const ZipPlan &z, int redop, const void *scalars, void *out_dev, bool peer)
+{
+    switch (redop) {
+    case NDB_RED_SUM: return zip_fold_op<T, R_SUM>(ctx, z, scalars, (T *)out_dev, peer);
+    case NDB_RED_MIN: return zip_fold_op<T, R_MIN>(ctx, z, scalars, (T *)out_dev, peer);
+    case NDB_RED_MAX: return zip_fold_op<T, R_MAX>(ctx, z, scalars, (T *)out_dev, peer);
+    default: return NDB_ERR_UNSUPPORTED;
+    }
+}
+
+// NDB_ERR_UNSUPPORTED (no error text) when no fused kernel covers (plan, op, redop): the caller runs Zip, then the reduction
+int zip_fold_dense(ndb_ctx *ctx, const ZipPlan &z, int redop, const void *scalars, void *out_dev, bool peer)
+{
+    if (z.kernel != NDB_KERNEL_FLAT_VEC || z.n_parts != op_arity(z.op) + 1) return NDB_ERR_UNSUPPORTED;
+    switch (z.dtype) {
+    case NDB_F32: return zip_fold_typed<float>(ctx, z, redop, scalars, out_dev, peer);
+    case NDB_F64: return zip_fold_typed<double>(ctx, z, redop, scalars, out_dev, peer);
+    case NDB_I32: return zip_fold_typed<int32_t>(ctx, z, redop, scalars, out_dev, peer);
+    case NDB_I64: return zip_fold_typed<int64_t>(ctx, z, redop, scalars, out_dev, peer);
+    }
+    return NDB_ERR_UNSUPPORTED;
+}
+
 // ======================================================================================================
 // host side
 
@@ -1400,6 +1534,36 @@ int ndb_reduce_all_peer(ndb_ctx *ctx, int redop, const ndb_view *in, void *out_d
     clear_error();
     DeviceGuard g(ctx->device);
     return reduce_all_dev_impl(ctx, redop, in, out_dev, true);
+}
+
+int ndb_zip_fold_write(ndb_ctx *ctx, int op, const void *scalars, int n_parts, const ndb_view *parts, int redop, void *out_dev,
+                       int across_ranks)
+{
+    clear_error();
+    if (!ctx || !out_dev || !parts) {
+        set_error("zip_fold_write: null context, producers or output (no CPU fallback exists)");
+        return NDB_ERR_INVALID_ARG;
+    }
+    if (redop < NDB_RED_SUM || redop > NDB_RED_MAX) {
+        set_error("zip_fold_write: the accumulator must be sum, product, min or max");
+        return NDB_ERR_UNSUPPORTED;
+    }
+    const bool peer = across_ranks != 0;
+    if (peer && !(ctx->peer_world > 0 && ctx->peer_attached)) {
+        set_error("zip_fold_write: across_ranks needs peer windows attached to this context");
+        return NDB_ERR_INVALID_ARG;
+    }
+    ZipPlan z;
+    NDB_TRY(make_zip_plan(op, n_parts, parts, &z));
+    DeviceGuard g(ctx->device);
+    if (z.kernel != NDB_KERNEL_NOOP) {
+        const int st = zip_fold_dense(ctx, z, redop, scalars, out_dev, peer);
+        if (st != NDB_ERR_UNSUPPORTED) return st;
+        clear_error();
+    }
+    // general producers: the Zip, then the reduction of what it wrote (two passes over the output)
+    NDB_TRY(ndb_zip(ctx, op, scalars, n_parts, parts));
+    return reduce_all_dev_impl(ctx, redop, &parts[0], out_dev, peer);
 }
 
 int ndb_reduce_all(ndb_ctx *ctx, int redop, const ndb_view *in, void *out_host)

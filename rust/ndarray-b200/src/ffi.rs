@@ -94,6 +94,7 @@ extern "C" {
     pub fn ndb_reduce_all_peer(ctx: *mut ndb_ctx, redop: c_int, input: *const ndb_view, out_dev: *mut c_void) -> c_int;
     pub fn ndb_accumulate_axis(ctx: *mut ndb_ctx, op: c_int, axis: c_int, v: *const ndb_view) -> c_int;
     pub fn ndb_zip_fold(ctx: *mut ndb_ctx, op: c_int, scalars: *const c_void, n_inputs: c_int, inputs: *const ndb_view, redop: c_int, init: *const c_void, out_host: *mut c_void) -> c_int;
+    pub fn ndb_zip_fold_write(ctx: *mut ndb_ctx, op: c_int, scalars: *const c_void, n_parts: c_int, parts: *const ndb_view, redop: c_int, out_dev: *mut c_void, across_ranks: c_int) -> c_int;
     pub fn ndb_zip_fold_while(ctx: *mut ndb_ctx, op: c_int, scalars: *const c_void, n_inputs: c_int, inputs: *const ndb_view, redop: c_int, init: *const c_void, stop_op: c_int, stop_value: *const c_void, out_host: *mut c_void, done: *mut c_int) -> c_int;
     pub fn ndb_zip_host_fold(ctx: *mut ndb_ctx, op: c_int, scalars: *const c_void, n_parts: c_int, parts: *const ndb_view, redop: c_int, out_host: *mut c_void) -> c_int;
     pub fn ndb_fill_counter_rng(ctx: *mut ndb_ctx, out: *const ndb_view, seed: u64, first_index: u64) -> c_int;

@@ -507,6 +507,27 @@ impl<A: Elem> Zip<A> {
                                          &init as *const A as *const c_void, &mut out as *mut A as *mut c_void) });
         out
     }
+    /// `Zip::from(&mut a).and(&b).and(&c).fold(acc0, |acc, a, &b, &c| { *a = b <op> c ..; acc <fold> *a })`: the first producer
+    /// is written and the written values are folded in the same pass (`ndb_zip_fold_write`; one fused kernel when dense).
+    pub fn for_each_fold(self, op: Op, fold: Fold) -> A where A: Default {
+        let p = &self.parts;
+        let (code, parts): (i32, Vec<ffi::ndb_view>) = match op {
+            Op::Assign => (0, vec![p[0], p[1]]),
+            Op::Add => (2, vec![p[0], p[1], p[2]]), Op::Sub => (3, vec![p[0], p[1], p[2]]),
+            Op::Mul => (4, vec![p[0], p[1], p[2]]), Op::Div => (5, vec![p[0], p[1], p[2]]),
+            Op::AddAssign => (2, vec![p[0], p[0], p[1]]), Op::SubAssign => (3, vec![p[0], p[0], p[1]]),
+            Op::MulAssign => (4, vec![p[0], p[0], p[1]]), Op::DivAssign => (5, vec![p[0], p[0], p[1]]),
+            Op::MulAddAssign => (7, vec![p[0], p[1], p[2], p[0]]),
+        };
+        let mut dev = std::ptr::null_mut();
+        check(unsafe { ffi::ndb_alloc(self.ctx, 16, &mut dev) });
+        check(unsafe { ffi::ndb_zip_fold_write(self.ctx, code, std::ptr::null(), parts.len() as i32, parts.as_ptr(), fold as i32, dev, 0) });
+        let mut out = A::default();
+        check(unsafe { ffi::ndb_d2h(self.ctx, &mut out as *mut A as *mut c_void, dev, std::mem::size_of::<A>()) });
+        check(unsafe { ffi::ndb_sync(self.ctx) });
+        check(unsafe { ffi::ndb_free(self.ctx, dev) });
+        out
+    }
     /// `fold_while(init, |acc, ..| if v <stop> s { FoldWhile::Done(acc) } else { FoldWhile::Continue(acc <fold> v) })`
     /// (src/zip/mod.rs:640-655) in Zip's traversal order; `FoldWhile` is ndarray's own type.
     pub fn fold_while(self, init: A, op: Map, fold: Fold, stop: Pred, stop_value: A) -> ndarray::FoldWhile<A> where A: Default {

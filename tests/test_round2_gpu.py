@@ -341,3 +341,39 @@ def test_swap_axes_insert_axis_and_azip(nd, oracle):
     par_azip("a+=b", da, dc)
     assert oracle.zip_(2, want, [want, fc]) == 0
     assert_bit_equal(da.to_numpy(), want, "par_azip")
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64, np.int32, np.int64])
+def test_zip_for_each_fold_fused(nd, oracle, dtype):
+    """Zip::fold whose closure writes its first producer (ndb_zip_fold_write): the written array is bit-exact against the
+    oracle's Zip and the folded value equals the fold of that array - dense producers (the fused kernel, ragged tail
+    included), strided ones (Zip + reduction), sum / min / max."""
+    from ndarray_b200 import Array, Zip, Op, s_
+    rng = np.random.default_rng(99)
+    kind = np.dtype(dtype).kind
+    for shape in ((1000003,), (257, 129), (64, 64)):
+        def mk():
+            return (rng.integers(-1000, 1000, shape) if kind == "i" else rng.uniform(-1, 1, shape)).astype(dtype)
+        ah, bh, ch = mk(), mk(), mk()
+        for views in ("dense", "strided"):
+            if views == "strided" and len(shape) == 1:
+                continue
+            sl = (lambda x: x) if views == "dense" else (lambda x: x.slice(s_[::-1, ::2]))
+            hs = (lambda x: x) if views == "dense" else (lambda x: x[::-1, ::2])
+            a, b, c = Array.from_numpy(ah), Array.from_numpy(bh), Array.from_numpy(ch)
+            got = Zip.from_(sl(a)).and_(sl(b)).and_(sl(c)).for_each_fold("a=b*c+a", "sum")
+            want = ah.copy()
+            wv = hs(want)
+            assert oracle.zip_(7, wv, [hs(bh), hs(ch), wv]) == 0
+            assert_bit_equal(a.to_numpy(), want, f"for_each_fold {views}: written array")
+            if kind == "i":
+                with np.errstate(over="ignore"):
+                    assert got == wv.sum(dtype=dtype)
+            else:
+                tol = (1e-5 if dtype == np.float32 else 1e-12) * np.sqrt(wv.size) * max(np.abs(wv).mean(), 1e-30)
+                assert abs(float(got) - wv.astype(np.float64).sum()) <= tol
+            for fold, fn in (("min", np.min), ("max", np.max)):
+                a2 = Array.from_numpy(ah)
+                g2 = Zip.from_(sl(a2)).and_(sl(b)).and_(sl(c)).for_each_fold("a=b+c", fold)
+                assert g2 == fn(hs(bh) + hs(ch))
+                assert_bit_equal(sl(a2).to_numpy(), (hs(bh) + hs(ch)).astype(dtype), "for_each_fold min/max: written array")
