@@ -60,6 +60,14 @@ def run_extras(nd, ctx, torch, dist, rank, world, local, peak_gbs):
 
     med, best = _time(ctx, c1_zip, 40, 4)
     rec("C1_zip_a=b*c+a_f32_4096^2", 4 * 4 * n * n, med, best)
+
+    # one event pair around 12 launches (three passes over the four buffer sets): programmatic dependent launch overlaps each
+    # kernel's launch with its predecessor's drain, which an event between every two launches prevents
+    def c1_zip_x12():
+        for _ in range(12):
+            c1_zip()
+    med, best = _time(ctx, c1_zip_x12, 10, 2)
+    rec("C1_zip_a=b*c+a_f32_4096^2_12_back_to_back", 12 * 4 * 4 * n * n, med, best)
     import ctypes as C
     from ndarray_b200._ffi import lib, check
     o1 = Array.zeros((n,), np.float32, ctx=ctx)
