@@ -438,7 +438,11 @@ bool gemm_f32_eligible(const GemmArgs &g)
 {
     if (getenv("NDB_GEMM_F32_GENERIC")) return false;
     if (g.m < 64 || g.n < 64 || g.k < 32) return false;
-    if ((double)g.m * (double)g.n * (double)g.k < 128.0 * 128.0 * 128.0) return false;
+    {
+        // below this many multiply-adds the FFMA tile kernel (gemm_any) is used instead; NDB_GEMM_F32_MIN_CUBE = edge of the cube
+        const double edge = getenv("NDB_GEMM_F32_MIN_CUBE") ? atof(getenv("NDB_GEMM_F32_MIN_CUBE")) : 128.0;
+        if ((double)g.m * (double)g.n * (double)g.k < edge * edge * edge) return false;
+    }
     if (g.m > (1 << 30) || g.n > (1 << 30) || g.k > (1 << 30)) return false;
     return true;
 }
