@@ -259,9 +259,13 @@ def run_extras(nd, ctx, torch, dist, rank, world, local, peak_gbs):
                     t1 = nvlink_kib()
                     tx, rx = (t1[0] - t0[0]) * 1024 / reps, (t1[1] - t0[1]) * 1024 / reps
                     expect = (world - 1) * n * 24  # Welford (n, mean, M2) per column to every other rank
-                    out["C3_var_axis0_fused_nvlink_bytes_per_launch"] = {
-                        "tx": round(tx), "rx": round(rx), "expected_payload": expect, "hbm_bytes_read_per_rank": 8 * rows * n,
-                        "source": "NVML NVLINK_THROUGHPUT_DATA_TX/RX (all links of this GPU), rank 0, 200 launches"}
+                    rec_nv = {"expected_payload": expect, "hbm_bytes_read_per_rank": 8 * rows * n,
+                              "source": "NVML NVLINK_THROUGHPUT_DATA_TX/RX (all links of this GPU), rank 0, 200 launches"}
+                    if tx == 0 and rx == 0:
+                        rec_nv["counters"] = "unavailable: the NVML NVLink throughput fields read 0 on this (virtualised) box"
+                    else:
+                        rec_nv.update({"tx": round(tx), "rx": round(rx)})
+                    out["C3_var_axis0_fused_nvlink_bytes_per_launch"] = rec_nv
             except Exception as e:  # noqa: BLE001
                 out["C3_var_axis0_fused_nvlink_bytes_per_launch"] = {"error": repr(e)}
             ctx.sync()
