@@ -1,7 +1,7 @@
 //! ndarray 0.17.2 on the host cores, for the five BASELINE configs.  Prints one JSON object per case with
-//! the same algorithmic byte / flop counts bench.py uses, so the numbers sit beside `profiles/r01_bench_*.json`.
+//! the same algorithmic byte / flop counts bench.py uses, so the numbers sit beside `profiles/r0N_bench_*.json`.
 //!
-//!   cargo run --release -- c1 | c2 | c3 | c4 | all        (RAYON_NUM_THREADS selects the thread count)
+//!   cargo run --release -- c1 | c2 | c3 | c4 | c5 | all   (RAYON_NUM_THREADS selects the thread count)
 //!
 //! ndarray has no parallel `sum_axis` / `var_axis` / `fold_axis`: those are timed serial, as a user of the crate gets them;
 //! the global sum uses the documented parallel idiom (`axis_iter().into_par_iter().map(sum).sum()`, tests/par_rayon.rs:19).
@@ -120,10 +120,42 @@ fn c4() {
     println!("{{\"impl\": \"ndarray-0.17.2\", \"case\": \"C4_gemm_f32_8192^3\", \"TFLOP/s\": {:.3}, \"ms\": {:.1}}}", 2.0 * (n as f64).powi(3) / t / 1e12, t * 1e3);
 }
 
+/// splitmix64 output `i` of a generator seeded with `seed`, top 24 bits -> [-1, 1): the harness's index-addressable generator
+/// (ndarray_b200/csrc/rng.cu, oracle orc_counter_fill), so this program sees the same data as bench.py.
+fn counter_f32(seed: u64, i: u64) -> f32 {
+    let mut z = seed.wrapping_add((i + 1).wrapping_mul(0x9E3779B97F4A7C15));
+    z = (z ^ (z >> 30)).wrapping_mul(0xBF58476D1CE4E5B9);
+    z = (z ^ (z >> 27)).wrapping_mul(0x94D049BB133111EB);
+    z ^= z >> 31;
+    ((z >> 40) as u32 as f32) * (1.0 / 8388608.0) - 1.0
+}
+
+/// Config 5, the round-2 bench headline: f32 [rows, 65536] `a = b*c + a` (par_for_each), then the parallel global sum idiom of
+/// tests/par_rayon.rs:19.  `rows` = 8192 is the bounded sample bench.py's CPU arm uses (1/8 of the 2^32-element problem);
+/// pass 65536 as the second argument for the whole thing (48 GiB of host memory).
+fn c5(rows: usize) {
+    let cols = 65536usize;
+    let fill = |seed: u64| Array2::from_shape_fn((rows, cols), |(i, j)| counter_f32(seed, (i * cols + j) as u64));
+    let (mut a, b, c) = (fill(0x5EED0001), fill(0x5EED0002), fill(0x5EED0003));
+    let mut total = 0f32;
+    let t = time(
+        || {
+            Zip::from(&mut a).and(&b).and(&c).par_for_each(|a, &b, &c| *a = b * c + *a);
+            total = a.axis_iter(Axis(0)).into_par_iter().map(|r| r.sum()).sum::<f32>();
+        },
+        10,
+    );
+    std::hint::black_box(total);
+    report(&format!("C5_zip_global_sum_hbm_gbps_f32_{rows}x{cols}"), 20.0 * (rows * cols) as f64, t);
+}
+
 fn main() {
     let which = std::env::args().nth(1).unwrap_or_else(|| "all".into());
     if which == "c1" || which == "all" { c1(); }
     if which == "c2" || which == "all" { c2(); }
     if which == "c3" || which == "all" { c3(); }
     if which == "c4" || which == "all" { c4(); }
+    if which == "c5" || which == "all" {
+        c5(std::env::args().nth(2).and_then(|s| s.parse().ok()).unwrap_or(8192));
+    }
 }
