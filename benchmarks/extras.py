@@ -132,6 +132,85 @@ def run_extras(nd, ctx, torch, dist, rank, world, local, peak_gbs):
     xts, ys = x.t().slice(s_[::-2, :, :]), y.slice(s_[::2, :, :])
     med, best = _time(ctx, lambda: Zip.from_(o_half).and_(ys).and_(rowb).and_(xts).for_each("a=b*c+d"), 20, 3)
     rec("C2_combined_y[::2]*row+x.t()[::-2]", 3 * n ** 3 * 2 + 4 * n, med, best)
+    # ---- config 2's three view cases as ONE step (round 1's headline): device-resident, end to end through ndb_zip_host with
+    #      pinned host buffers, and the CPU stand-in on the same views - the case where the host is slow (strided traversal) -----
+    try:
+        half = o_full.slice(s_[: n // 2, :, :])
+        z1 = Zip.from_(o_full).and_(x.t()).and_(y)
+        z2 = Zip.from_(half).and_(x.slice(s_[::-2, :, :])).and_(y.slice(s_[::2, :, :]))
+        z3 = Zip.from_(o_full).and_(x).and_(row.broadcast((n, n, n)))
+        c2_bytes = 3 * n ** 3 * 4 + 3 * (n // 2) * n * n * 4 + 2 * n ** 3 * 4 + n * 4
+
+        def c2_step():
+            z1.for_each("a=b+c")
+            z2.for_each("a=b+c")
+            z3.for_each("a=b*c")
+        med, best = _time(ctx, c2_step, 20, 3)
+        rec("C2_step_three_view_zips(x.t()+y, s![..;-2]+s![..;2], x*row)", c2_bytes, med, best)
+        if rank == 0 and world == 1:
+            from ndarray_b200._ffi import View
+            import time as _t
+
+            def pinned(shape):
+                p = C.c_void_p()
+                nb = int(np.prod(shape)) * 4
+                check(lib().ndb_host_alloc(nb, C.byref(p)))
+                return np.ctypeslib.as_array((C.c_byte * nb).from_address(p.value)).view(np.float32).reshape(shape)
+
+            hx, hy, hrow, hout = pinned((n, n, n)), pinned((n, n, n)), pinned((n,)), pinned((n, n, n))
+            rng = np.random.default_rng(3)
+            hx[...] = rng.random((n, n, n), dtype=np.float32)
+            hy[...] = rng.random((n, n, n), dtype=np.float32)
+            hrow[...] = rng.random(n, dtype=np.float32)
+
+            def hv(a, shape=None, strides=None, offset=0):
+                v = View()
+                shape = a.shape if shape is None else shape
+                strides = [st // 4 for st in a.strides] if strides is None else strides
+                v.ptr = a.ctypes.data + offset * 4
+                v.ndim, v.dtype = len(shape), 0
+                for i, (d, st) in enumerate(zip(shape, strides)):
+                    v.dim[i], v.stride[i] = d, st
+                return v
+
+            nn = n * n
+            parts = [(2, (View * 3)(hv(hout), hv(hx, (n, n, n), (1, n, nn)), hv(hy))),
+                     (2, (View * 3)(hv(hout, (n // 2, n, n)), hv(hx, (n // 2, n, n), (-2 * nn, n, 1), (n - 1) * nn), hv(hy, (n // 2, n, n), (2 * nn, n, 1)))),
+                     (4, (View * 3)(hv(hout), hv(hx), hv(hrow, (n, n, n), (0, 0, 1))))]
+
+            def e2e():
+                for op, pv in parts:
+                    check(lib().ndb_zip_host(ctx.handle, op, None, 3, pv))
+            e2e()
+            t0 = _t.perf_counter()
+            for _ in range(3):
+                e2e()
+            dt = (_t.perf_counter() - t0) / 3
+            from oracle import oracle as orc
+            orc.build()
+            th = orc.max_threads()
+            rowb = np.broadcast_to(hrow, (n, n, n))
+            hhalf = hout[: n // 2]
+
+            def cpu():
+                orc.zip_(2, hout, [hx.transpose(2, 1, 0), hy], threads=th)
+                orc.zip_(2, hhalf, [hx[::-1][::2], hy[::2]], threads=th)
+                orc.zip_(4, hout, [hx, rowb], threads=th)
+            cpu()
+            t0 = _t.perf_counter()
+            for _ in range(3):
+                cpu()
+            dc = (_t.perf_counter() - t0) / 3
+            out["C2_step_end_to_end_vs_cpu"] = {
+                "e2e_GB/s": round(c2_bytes / dt / 1e9, 1), "e2e_ms": round(dt * 1e3, 1), "h2d_bytes": 2 * n ** 3 * 4 + 2 * (n // 2) * nn * 4 + n ** 3 * 4 + n * 4,
+                "d2h_bytes": n ** 3 * 4 + (n // 2) * nn * 4 + n ** 3 * 4, "cpu_stand_in_GB/s": round(c2_bytes / dc / 1e9, 1), "cpu_threads": th,
+                "e2e_over_cpu": round(dc / dt, 2),
+                "note": "strided views: the CPU traversal is cache-hostile, so even over PCIe the device path wins end to end; for the contiguous "
+                        "config 5 the CPU streams at DDR5 speed and the link loses (bench e2e)"}
+            for a_ in (hx, hy, hrow, hout):
+                lib().ndb_host_free(C.c_void_p(a_.ctypes.data))
+    except Exception as e:  # noqa: BLE001
+        out["C2_step"] = {"error": repr(e)}
     del x, y, row, o_full, tx, ty
     # ---- C3 ---------------------------------------------------------------------------------------
     n = 16384

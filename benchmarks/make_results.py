@@ -77,6 +77,11 @@ def main():
             out.append(f"| {k} | {v['GB/s']} GB/s ({v['ms'] * 1e3:.1f} µs) | {v.get('frac_of_measured_peak', '')} |")
         elif isinstance(v, dict) and "TFLOP/s" in v:
             out.append(f"| {k} | {v['TFLOP/s']} TFLOP/s" + (f" ({v['ms']} ms)" if "ms" in v else "") + " | |")
+    c2 = ex.get("C2_step_end_to_end_vs_cpu")
+    if isinstance(c2, dict) and "e2e_GB/s" in c2:
+        out += ["", f"Config 2's three view Zips end to end (`ndb_zip_host`, pinned host buffers): **{c2['e2e_GB/s']} GB/s** ({c2['e2e_ms']} ms per step) against "
+                f"{c2['cpu_stand_in_GB/s']} GB/s for the CPU stand-in on {c2['cpu_threads']} threads = **{c2['e2e_over_cpu']}x** — strided views are where the host is slow; "
+                "for the contiguous config 5 (the headline) the host streams at DDR5 speed and the PCIe link loses."]
     cs = ex.get("cpu_stand_in")
     if isinstance(cs, dict):
         out += ["", "CPU stand-ins for those configs on the same box (`cpu_stand_in`): " +
