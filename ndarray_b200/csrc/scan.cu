@@ -53,7 +53,8 @@ __global__ void __launch_bounds__(256) scan_cols(ScanArgs a)
     T *p = reinterpret_cast<T *>(a.base) + lane_offset(a, lane);
     T acc = p[0];
     int64_t i = 1;
-    for (; i + 3 < a.n; i += 4) {  // four independent loads in flight, combined in order
+    for (; i + 3 < a.n; i += 4) {  // four independent loads in flight, combined in order (a generic x[U] form with U = 4 / 8 / 16
+                                   // measured 4.3 / 5.2 / 5.6 TB/s against 5.75 for this one)
         const T x0 = p[i * a.s], x1 = p[(i + 1) * a.s], x2 = p[(i + 2) * a.s], x3 = p[(i + 3) * a.s];
         acc = comb<T, MUL>(acc, x0);
         p[i * a.s] = acc;
