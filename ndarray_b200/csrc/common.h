@@ -78,8 +78,7 @@ bool pdl_enabled();
 template <typename... KArgs, typename... Args>
 inline void launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args)
 {
-    cudaLaunchConfig_t cfg;
-    memset(&cfg, 0, sizeof(cfg));
+    cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid;
     cfg.blockDim = block;
     cfg.dynamicSmemBytes = smem;
