@@ -4,6 +4,8 @@ Each case draws a common logical shape (rank 1..5) and, per producer, a random r
 slices with steps in {-3..3}\\{0}, a random axis permutation, inverted axes, and (inputs only) axes broadcast from
 length 1.  The output view never aliases itself (no broadcast on the output).  Elementwise results are compared
 bit-for-bit; reductions along a random axis exactly for integers and to the north-star tolerance for floats."""
+import os
+
 import numpy as np
 import pytest
 
@@ -68,7 +70,8 @@ def random_shape(rng):
     return shape
 
 
-@pytest.mark.parametrize("seed", range(24))
+# NDB_FUZZ_SEEDS=N widens the sweep (used for long offline runs; the default keeps the suite short)
+@pytest.mark.parametrize("seed", range(int(os.environ.get("NDB_FUZZ_SEEDS", 24))))
 def test_fuzz_zip_views(nd, oracle, seed):
     rng = np.random.default_rng(1000 + seed)
     for _ in range(12):
@@ -92,7 +95,7 @@ def test_fuzz_zip_views(nd, oracle, seed):
                                                  f"in strides {[h.strides for h in hins]}")
 
 
-@pytest.mark.parametrize("seed", range(12))
+@pytest.mark.parametrize("seed", range(int(os.environ.get("NDB_FUZZ_SEEDS", 24)) // 2))
 def test_fuzz_reduce_axis_views(nd, oracle, seed):
     from ndarray_b200 import Axis
     rng = np.random.default_rng(5000 + seed)
@@ -121,3 +124,60 @@ def test_fuzz_reduce_axis_views(nd, oracle, seed):
                 st, wv = oracle.reduce_axis(5, hv, axis, 0.0)
                 assert st == 0
                 assert np.max(np.abs(gv.astype(np.float64) - wv.astype(np.float64)), initial=0.0) <= (1e-4 if dtype == np.float32 else 1e-11), what
+
+
+@pytest.mark.parametrize("seed", range(int(os.environ.get("NDB_FUZZ_SEEDS", 24)) // 2))
+def test_fuzz_folds_over_views(nd, oracle, seed):
+    """Zip::fold forms on random views: fold of op(inputs) (ndb_zip_fold), fold of the written values (ndb_zip_fold_write:
+    fused when dense, Zip + reduction otherwise) and fold_while over the traversal order - integers exact, the written arrays
+    bit-exact, float sums to the north-star tolerance."""
+    from ndarray_b200 import Zip, Op
+    rng = np.random.default_rng(9000 + seed)
+    for _ in range(8):
+        shape = [max(s, 1) for s in random_shape(rng)]
+        dtype = [np.float32, np.float64, np.int32, np.int64][int(rng.integers(0, 4))]
+        kind = np.dtype(dtype).kind
+        ob, ofn = random_view_fn(rng, shape, allow_broadcast=False)
+        mo = Mirror(nd, rand(rng, ob, dtype) if kind == "f" else (rand(rng, ob, dtype) >> 12).astype(dtype))
+        ho, do = mo.view(ofn)
+        hins, dins = [], []
+        for _i in range(2):
+            ib, ifn = random_view_fn(rng, shape, allow_broadcast=True)
+            base = rand(rng, ib, dtype) if kind == "f" else (rand(rng, ib, dtype) >> 12).astype(dtype)
+            m = Mirror(nd, base)
+            h, d = m.view(ifn)
+            hins.append(h)
+            dins.append(d)
+        n = int(np.prod(shape))
+        tol = (1e-5 if dtype == np.float32 else 1e-12) * np.sqrt(n) * 2.0
+        # fold of op(inputs): nothing is written
+        want_vals = hins[0] + hins[1]
+        got = Zip.from_(dins[0]).and_(dins[1]).fold(None, Op.ADD, "sum")
+        if kind == "i":
+            with np.errstate(over="ignore"):
+                assert got == want_vals.sum(dtype=dtype), (seed, shape)
+        else:
+            assert abs(float(got) - want_vals.astype(np.float64).sum()) <= tol * max(1.0, float(np.abs(want_vals).mean()))
+        assert Zip.from_(dins[0]).and_(dins[1]).fold(None, Op.ADD, "max") == want_vals.max()
+        # fold of the written values
+        assert oracle.zip_(4, ho, hins, []) == 0
+        got = Zip.from_(do).and_(dins[0]).and_(dins[1]).for_each_fold("a=b*c", "sum")
+        assert_bit_equal(mo.download(), mo.host, f"seed {seed} fold_write {np.dtype(dtype).name} shape {shape}")
+        if kind == "i":
+            with np.errstate(over="ignore"):
+                assert got == ho.sum(dtype=dtype)
+        else:
+            assert abs(float(got) - ho.astype(np.float64).sum()) <= tol * max(1.0, float(np.abs(ho).mean()))
+        # fold_while over the traversal order of a C-order copy: stop at the first value below the threshold
+        flat = np.ascontiguousarray(hins[0])
+        from ndarray_b200 import Array
+        dflat = Array.from_numpy(flat)
+        thr = dtype(np.sort(flat.ravel())[max(0, flat.size // 3 - 1)]) if flat.size else dtype(0)
+        seq = flat.ravel()
+        hit = np.nonzero(seq < thr)[0]
+        acc, done = Zip.from_(dflat).fold_while(dtype(0), Op.COPY, "max", 27, thr)
+        if len(hit):
+            first = int(hit[0])
+            assert done and acc == (max(dtype(0), seq[:first].max()) if first else dtype(0)), (seed, shape)
+        else:
+            assert not done and acc == max(dtype(0), seq.max())
