@@ -520,7 +520,24 @@ def main():
     }
 
     # ---- end to end through the host-buffer C-ABI call -----------------------------------------------------
-    if not args.no_e2e:
+    def host_mem_ok():
+        """Pinning 48 GiB on a box that does not have it would invite the OOM killer: check before, on every rank alike."""
+        try:
+            avail = next(int(ln.split()[1]) * 1024 for ln in open("/proc/meminfo") if ln.startswith("MemAvailable:"))
+        except Exception:
+            return True, None
+        need = 3 * n_total * 4  # all ranks of this host together
+        ok = avail > need * 1.25 + (8 << 30)
+        if dist is not None:
+            box = [ok]
+            dist.broadcast_object_list(box, src=0)
+            ok = box[0]
+        return ok, (avail, need)
+
+    mem_ok, mem = host_mem_ok()
+    if not args.no_e2e and not mem_ok:
+        line["e2e"] = {"skipped": f"host has {mem[0] >> 30} GiB available, the end-to-end leg pins {mem[1] >> 30} GiB: not attempted"}
+    elif not args.no_e2e:
         try:
             line["e2e"] = run_e2e(ctx, L, torch, dist, dev, a, b, c, fill, rows, lo, world, rank, STEP_BYTES, n_total, want_rows, sample,
                                   parity, barrier, max_over_ranks, View, check)
