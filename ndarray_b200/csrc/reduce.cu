@@ -870,132 +870,6 @@ __global__ void __launch_bounds__(256) zip2_reduce_flat(const T *x, const T *y, 
     if (threadIdx.x == 0) reinterpret_cast<Acc<T, R> *>(partial)[blockIdx.x] = acc;
 }
 
-// Fused Zip + reduction over STRIDED producers (collapsed N-d, any signed strides): reduce_R(op(x[i...], y[i...])) with no
-// scratch array - Zip::all / Zip::any / Zip::fold on views.  The geometry is the planner's, with the first producer playing the
-// part of the "output" (its fastest axis becomes the inner axis); virtual blocks are (row, 1024-element chunk of the inner
-// axis) like red_all_rows.  Scalar loads: coalesced for producers whose inner stride is 1.
-template <int NIN>
-struct ZipRedArgs {
-    const char *ptr[NIN];
-    int ndim;
-    int64_t dim[NDB_MAX_NDIM];
-    int64_t stride[NIN][NDB_MAX_NDIM];
-    int64_t n_rows, inner_chunks;
-};
-
-template <typename T, int OP, int NIN, int R>
-__global__ void __launch_bounds__(256) zip_reduce_rows(ZipRedArgs<NIN> a, T s0, T s1, int *flag, void *partial)
-{
-    pdl_enter();
-    __shared__ Acc<T, R> smem[32];
-    const int inner = a.ndim - 1;
-    const int64_t len = a.dim[inner];
-    const int64_t total_vb = a.n_rows * a.inner_chunks;
-    Acc<T, R> acc;
-    acc.reset();
-    for (int64_t vb = blockIdx.x; vb < total_vb; vb += gridDim.x) {
-        const int64_t row = vb / a.inner_chunks;
-        const int64_t ch = vb - row * a.inner_chunks;
-        int64_t off[NIN];
-#pragma unroll
-        for (int p = 0; p < NIN; ++p) off[p] = 0;
-        int64_t lin = row;
-        for (int d = inner - 1; d >= 0; --d) {
-            const int64_t q = lin / a.dim[d];
-            const int64_t i = lin - q * a.dim[d];
-            lin = q;
-#pragma unroll
-            for (int p = 0; p < NIN; ++p) off[p] += i * a.stride[p][d];
-        }
-        const int64_t i0 = ch * 1024 + threadIdx.x;
-        T x[4][NIN];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int64_t i = i0 + j * 256;
-            if (i < len) {
-#pragma unroll
-                for (int p = 0; p < NIN; ++p) x[j][p] = reinterpret_cast<const T *>(a.ptr[p])[off[p] + i * a.stride[p][inner]];
-            }
-        }
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int64_t i = i0 + j * 256;
-            if (i < len) acc.add(apply_op<T, OP, NIN>(x[j], s0, s1, flag));
-        }
-    }
-    acc = block_reduce(acc, smem);
-    if (threadIdx.x == 0) reinterpret_cast<Acc<T, R> *>(partial)[blockIdx.x] = acc;
-}
-
-template <typename T, int OP, int NIN, int R>
-static int zip_reduce_rows_launch(ndb_ctx *ctx, const ZipPlan &z, const void *scalars, void *out_host)
-{
-    ZipRedArgs<NIN> a;
-    memset(&a, 0, sizeof(a));
-    a.ndim = z.ndim;
-    for (int d = 0; d < z.ndim; ++d) {
-        a.dim[d] = z.dim[d];
-        for (int p = 0; p < NIN; ++p) a.stride[p][d] = z.stride[p][d];
-    }
-    for (int p = 0; p < NIN; ++p) a.ptr[p] = z.ptr[p];
-    const int inner = z.ndim - 1;
-    a.inner_chunks = (z.dim[inner] + 1023) / 1024;
-    a.n_rows = z.total / z.dim[inner];
-    T s0 = T(0), s1 = T(0);
-    const int ns = op_scalars(OP);
-    if (ns >= 1 && scalars) s0 = ((const T *)scalars)[0];
-    if (ns >= 2 && scalars) s1 = ((const T *)scalars)[1];
-    const int max_blocks = ctx->sm_count * 8;
-    NDB_TRY(ensure_workspace(ctx, (size_t)max_blocks * sizeof(Acc<T, R>) + 4096));
-    void *dev_scalar = (char *)ctx->workspace + ctx->workspace_bytes - 64;
-    const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>(max_blocks, a.n_rows * a.inner_chunks));
-    launch_pdl(zip_reduce_rows<T, OP, NIN, R>, blocks, 256, 0, ctx->stream, a, s0, s1, ctx->dev_flag, ctx->workspace);
-    NDB_CHECK_LAUNCH();
-    launch_pdl(red_all_finish<T, R>, 1, 256, 0, ctx->stream, ctx->workspace, blocks, (T *)dev_scalar, T(1), 0);
-    NDB_CHECK_LAUNCH();
-    NDB_CUDA(cudaMemcpyAsync(ctx->host_scalar, dev_scalar, sizeof(T), cudaMemcpyDeviceToHost, ctx->stream));
-    NDB_CUDA(cudaStreamSynchronize(ctx->stream));
-    memcpy(out_host, ctx->host_scalar, sizeof(T));
-    return NDB_OK;
-}
-
-template <typename T>
-static int zip_reduce_rows_typed(ndb_ctx *ctx, const ZipPlan &z, int op, int redop, const void *scalars, void *out_host)
-{
-#define NDB_ZRR(OPC, NINC, RC, RT) \
-    if (op == OPC && redop == RC) return zip_reduce_rows_launch<T, OPC, NINC, RT>(ctx, z, scalars, out_host);
-    if (z.n_parts == 1) {
-        NDB_ZRR(NDB_OP_COPY, 1, NDB_RED_SUM, R_SUM) NDB_ZRR(NDB_OP_COPY, 1, NDB_RED_MIN, R_MIN) NDB_ZRR(NDB_OP_COPY, 1, NDB_RED_MAX, R_MAX)
-    } else if (z.n_parts == 2) {
-        NDB_ZRR(NDB_OP_ADD, 2, NDB_RED_SUM, R_SUM) NDB_ZRR(NDB_OP_SUB, 2, NDB_RED_SUM, R_SUM) NDB_ZRR(NDB_OP_MUL, 2, NDB_RED_SUM, R_SUM)
-        NDB_ZRR(NDB_OP_ADD, 2, NDB_RED_MIN, R_MIN) NDB_ZRR(NDB_OP_ADD, 2, NDB_RED_MAX, R_MAX)
-        NDB_ZRR(NDB_OP_SUB, 2, NDB_RED_MIN, R_MIN) NDB_ZRR(NDB_OP_SUB, 2, NDB_RED_MAX, R_MAX)
-        NDB_ZRR(NDB_OP_MUL, 2, NDB_RED_MIN, R_MIN) NDB_ZRR(NDB_OP_MUL, 2, NDB_RED_MAX, R_MAX)
-        NDB_ZRR(NDB_OP_EQ, 2, NDB_RED_MIN, R_MIN) NDB_ZRR(NDB_OP_EQ, 2, NDB_RED_MAX, R_MAX)
-        NDB_ZRR(NDB_OP_NE, 2, NDB_RED_MIN, R_MIN) NDB_ZRR(NDB_OP_NE, 2, NDB_RED_MAX, R_MAX)
-        NDB_ZRR(NDB_OP_LT, 2, NDB_RED_MIN, R_MIN) NDB_ZRR(NDB_OP_LT, 2, NDB_RED_MAX, R_MAX)
-        NDB_ZRR(NDB_OP_LE, 2, NDB_RED_MIN, R_MIN) NDB_ZRR(NDB_OP_LE, 2, NDB_RED_MAX, R_MAX)
-        NDB_ZRR(NDB_OP_GT, 2, NDB_RED_MIN, R_MIN) NDB_ZRR(NDB_OP_GT, 2, NDB_RED_MAX, R_MAX)
-        NDB_ZRR(NDB_OP_GE, 2, NDB_RED_MIN, R_MIN) NDB_ZRR(NDB_OP_GE, 2, NDB_RED_MAX, R_MAX)
-    }
-#undef NDB_ZRR
-    return NDB_ERR_UNSUPPORTED;
-}
-
-// `z` is the plan of the INPUT producers alone (the first one in the output's seat); NDB_ERR_UNSUPPORTED (no error text) when
-// no fused kernel covers the case - the caller then materialises op(inputs) and reduces that
-int zip_reduce_strided(ndb_ctx *ctx, const ZipPlan &z, int op, int redop, const void *scalars, void *out_host)
-{
-    if (z.kernel == NDB_KERNEL_NOOP || z.kernel == NDB_KERNEL_TILE) return NDB_ERR_UNSUPPORTED;
-    switch (z.dtype) {
-    case NDB_F32: return zip_reduce_rows_typed<float>(ctx, z, op, redop, scalars, out_host);
-    case NDB_F64: return zip_reduce_rows_typed<double>(ctx, z, op, redop, scalars, out_host);
-    case NDB_I32: return zip_reduce_rows_typed<int32_t>(ctx, z, op, redop, scalars, out_host);
-    case NDB_I64: return zip_reduce_rows_typed<int64_t>(ctx, z, op, redop, scalars, out_host);
-    }
-    return NDB_ERR_UNSUPPORTED;
-}
-
 template <typename T, int OP, int R>
 static int zip2_reduce_launch(ndb_ctx *ctx, const void *x, const void *y, int64_t n, void *out_host)
 {

@@ -116,19 +116,6 @@ static int zip_then_reduce(ndb_ctx *ctx, int op, const void *scalars, int n_inpu
         }
         clear_error();
     }
-    if (n_inputs <= 2 && !getenv("NDB_ZIP_REDUCE_SCRATCH")) {
-        // strided producers: one fused pass over the views themselves (the first producer sits in the planner's output seat
-        // only to choose the inner axis; nothing is written).  A producer with a zero stride cannot sit there, so those
-        // cases, transposed-against-each-other pairs and other ops take the scratch path below.
-        const int plan_op = n_inputs == 1 ? NDB_OP_FILL : NDB_OP_COPY;  // arity n_inputs - 1
-        ZipPlan z;
-        if (op_scalars(op) == 0 && make_zip_plan(plan_op, n_inputs, inputs, &z) == NDB_OK) {
-            z.op = op;
-            const int st = zip_reduce_strided(ctx, z, op, redop, scalars, out_host);
-            if (st != NDB_ERR_UNSUPPORTED) return st;
-        }
-        clear_error();
-    }
     void *tmp = nullptr;
     NDB_CUDA(cudaMallocAsync(&tmp, (size_t)total * dtype_size(out.dtype), ctx->stream));
     out.ptr = tmp;

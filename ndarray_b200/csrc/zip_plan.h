@@ -24,7 +24,6 @@ int make_zip_plan(int op, int n_parts, const ndb_view *parts, ZipPlan *zp);
 // fused Zip + reduction over two dense aligned producers (reduce.cu); NDB_ERR_UNSUPPORTED if no kernel for (op, redop)
 int zip2_reduce_dense(ndb_ctx *ctx, int op, int redop, int dtype, const void *x, const void *y, int64_t n, void *out_host);
 
-int zip_reduce_strided(ndb_ctx *ctx, const ZipPlan &z, int op, int redop, const void *scalars, void *out_host);
 int zip_fold_dense(ndb_ctx *ctx, const ZipPlan &z, int redop, const void *scalars, void *out_dev, bool peer);
 
 bool is_layout_c(const ndb_view *v);
