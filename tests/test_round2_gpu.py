@@ -377,3 +377,60 @@ def test_zip_for_each_fold_fused(nd, oracle, dtype):
                 g2 = Zip.from_(sl(a2)).and_(sl(b)).and_(sl(c)).for_each_fold("a=b+c", fold)
                 assert g2 == fn(hs(bh) + hs(ch))
                 assert_bit_equal(sl(a2).to_numpy(), (hs(bh) + hs(ch)).astype(dtype), "for_each_fold min/max: written array")
+
+
+def test_config2_full_size_against_the_oracle(nd, oracle):
+    """C2 at 512^3, every view case of SURVEY 8d, WHOLE outputs bit-exact against the oracle's Zip traversal (threads only
+    split the outer axis, the arithmetic per element is ndarray's): (i) x.t() + y, (ii) s![..;-2,..,..] + s![..;2,..,..] and the
+    inner-axis variant s![..,..,..;-2], (iii) x * row.broadcast, (iv) all three views in one Zip."""
+    from ndarray_b200 import Array, Zip, s_
+    n = 512
+    xh = oracle.counter_fill(np.empty((n, n, n), np.float32), 11, 0, 8)
+    yh = oracle.counter_fill(np.empty((n, n, n), np.float32), 12, 0, 8)
+    rowh = oracle.counter_fill(np.empty(n, np.float32), 13, 0, 1)
+    x, y, row = Array.from_numpy(xh), Array.from_numpy(yh), Array.from_numpy(rowh)
+    out = Array.uninit((n, n, n), np.float32)
+    want = np.empty((n, n, n), np.float32)
+    Zip.from_(out).and_(x.t()).and_(y).for_each("a=b+c")
+    assert oracle.zip_(2, want, [xh.transpose(2, 1, 0), yh], threads=8) == 0
+    assert_bit_equal(out.to_numpy(), want, "C2 (i) transposed")
+    half, wh = out.slice(s_[: n // 2, :, :]), want[: n // 2]
+    Zip.from_(half).and_(x.slice(s_[::-2, :, :])).and_(y.slice(s_[::2, :, :])).for_each("a=b+c")
+    assert oracle.zip_(2, wh, [xh[::-1][::2], yh[::2]], threads=8) == 0
+    assert_bit_equal(half.to_numpy(), wh, "C2 (ii) negative outer step")
+    inner, wi = out.slice(s_[:, :, : n // 2]), want[:, :, : n // 2]
+    Zip.from_(inner).and_(x.slice(s_[:, :, ::-2])).and_(y.slice(s_[:, :, ::2])).for_each("a=b+c")
+    assert oracle.zip_(2, wi, [xh[:, :, ::-1][:, :, ::2], yh[:, :, ::2]], threads=8) == 0
+    assert_bit_equal(inner.to_numpy(), wi, "C2 (ii) negative inner step")
+    Zip.from_(out).and_(x).and_broadcast(row).for_each("a=b*c")
+    assert oracle.zip_(4, want, [xh, np.broadcast_to(rowh, (n, n, n))], threads=8) == 0
+    assert_bit_equal(out.to_numpy(), want, "C2 (iii) broadcast row")
+    Zip.from_(half).and_(y.slice(s_[::2, :, :])).and_(row.broadcast((n // 2, n, n))).and_(x.t().slice(s_[::-2, :, :])).for_each("a=b*c+d")
+    assert oracle.zip_(7, wh, [yh[::2], np.broadcast_to(rowh, (n // 2, n, n)), xh.transpose(2, 1, 0)[::-1][::2]], threads=8) == 0
+    assert_bit_equal(half.to_numpy(), wh, "C2 (iv) all three views in one Zip")
+
+
+def test_config3_full_size_against_the_oracle(nd, oracle):
+    """C3 at 16384^2 against the ORACLE (ndarray's own algorithms, not numpy): i64 sum_axis and fold_axis(min) on both axes
+    bit-exact; f64 sum_axis / mean_axis / var_axis(ddof=1) on both axes within 1e-12 * sqrt(n) * scale of the oracle's
+    reference-order result (Axis(1) of the oracle's Welford strides through memory: a few seconds)."""
+    from ndarray_b200 import Array, Axis
+    n = 16384
+    hi = oracle.counter_fill(np.empty((n, n), np.int64), 21, 0, 8)
+    a = Array.from_numpy(hi)
+    for ax in (0, 1):
+        st, want = oracle.reduce_axis(0, hi, ax)
+        assert st == 0 and np.array_equal(a.sum_axis(Axis(ax)).to_numpy(), want), ("i64 sum_axis", ax)
+        assert np.array_equal(a.fold_axis(Axis(ax), np.iinfo(np.int64).max, "min").to_numpy(), hi.min(axis=ax)), ("i64 fold min", ax)
+    del a, hi
+    hf = oracle.counter_fill(np.empty((n, n), np.float64), 22, 0, 8)
+    f = Array.from_numpy(hf)
+    tol = 1e-12 * np.sqrt(n)
+    for ax in (0, 1):
+        st, want = oracle.reduce_axis(0, hf, ax)
+        assert st == 0 and np.max(np.abs(f.sum_axis(Axis(ax)).to_numpy() - want)) <= tol * 8 * np.abs(hf).mean() * np.sqrt(n), ("f64 sum_axis", ax)
+        st, want = oracle.reduce_axis(4, hf, ax)
+        assert st == 0 and np.max(np.abs(f.mean_axis(Axis(ax)).to_numpy() - want)) <= tol, ("f64 mean_axis", ax)
+    for ax in (0, 1):
+        st, want = oracle.reduce_axis(5, hf, ax, 1.0)
+        assert st == 0 and np.max(np.abs(f.var_axis(Axis(ax), 1.0).to_numpy() - want)) <= tol, ("f64 var_axis", ax)
