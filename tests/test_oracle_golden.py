@@ -512,3 +512,20 @@ def test_config5_streaming_sums_match_the_materialised_form():
     s, sa, f = orc.c5_sums(1, 2, 3, 77, n, 3, True)
     assert abs(s - a.astype(np.float64).sum()) < 1e-9 and abs(sa - np.abs(a.astype(np.float64)).sum()) < 1e-9
     assert f == orc.reduce_all(0, a)
+
+
+def test_counter_generator_against_the_committed_fixture():
+    """tests/golden/counter_rng.json (made by tests/golden/make_counter_rng_golden.py, a pure-Python splitmix64) pins the
+    oracle's generator for all four element types and several seeds / offsets, including offsets beyond 2^32."""
+    import json
+    from pathlib import Path
+    fx = json.loads((Path(__file__).parent / "golden" / "counter_rng.json").read_text())
+    assert len(fx["cases"]) >= 20
+    for c in fx["cases"]:
+        n = len(c["i64"])
+        f32 = orc.counter_fill(np.empty(n, np.float32), c["seed"], c["first"], 1)
+        assert f32.view(np.uint32).tolist() == c["f32_bits"], c
+        f64 = orc.counter_fill(np.empty(n, np.float64), c["seed"], c["first"], 1)
+        assert [float(x).hex() for x in f64] == c["f64"], c
+        assert orc.counter_fill(np.empty(n, np.int32), c["seed"], c["first"], 1).tolist() == c["i32"], c
+        assert orc.counter_fill(np.empty(n, np.int64), c["seed"], c["first"], 1).tolist() == c["i64"], c

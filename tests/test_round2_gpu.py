@@ -434,3 +434,25 @@ def test_config3_full_size_against_the_oracle(nd, oracle):
     for ax in (0, 1):
         st, want = oracle.reduce_axis(5, hf, ax, 1.0)
         assert st == 0 and np.max(np.abs(f.var_axis(Axis(ax), 1.0).to_numpy() - want)) <= tol, ("f64 var_axis", ax)
+
+
+def test_counter_generator_against_the_committed_fixture_on_device(nd):
+    """The device generator against tests/golden/counter_rng.json (independent pure-Python splitmix64), all element types."""
+    import json
+    from pathlib import Path
+    from ndarray_b200 import Array
+    from ndarray_b200._ffi import lib, check
+    fx = json.loads((Path(__file__).parent / "golden" / "counter_rng.json").read_text())
+    ctx = nd.default_context()
+    for c in fx["cases"]:
+        n = len(c["i64"])
+        for dt, key in ((np.float32, "f32_bits"), (np.float64, "f64"), (np.int32, "i32"), (np.int64, "i64")):
+            d = Array.uninit((n,), dt, ctx=ctx)
+            check(lib().ndb_fill_counter_rng(ctx.handle, C.byref(d.v), c["seed"], c["first"]))
+            got = d.to_numpy()
+            if key == "f32_bits":
+                assert got.view(np.uint32).tolist() == c[key], c
+            elif key == "f64":
+                assert [float(x).hex() for x in got] == c[key], c
+            else:
+                assert got.tolist() == c[key], c
