@@ -354,21 +354,46 @@ def run_extras(nd, ctx, torch, dist, rank, world, local, peak_gbs):
         if peers is not None:
             peer_section()
         torch.cuda.empty_cache()
-    # ---- C4 at N GPUs: A and C row-sharded (8192 rows per rank, weak), B broadcast from rank 0 EVERY step ----------
+    # ---- C4 at N GPUs: A and C row-sharded, B broadcast from rank 0 EVERY step.  Weak (8192 rows per rank, as in round 1) and
+    #      STRONG (the 8192^3 problem of config 4: 8192 / N rows per rank), the latter also through the C ABI alone
+    #      (ndb_gemm_rowsharded: the library's own NCCL communicator, no torch collective) ---------------------------------
     if dist is not None and world > 1:
         from ndarray_b200 import parallel as par
         n = 8192
+        comm = None
+        try:
+            comm = par.Comm(ctx, dist)
+        except Exception as e:  # noqa: BLE001
+            out["ndb_comm"] = {"error": repr(e)}
         for tdt, name in ((torch.float64, "f64"), (torch.float32, "f32")):
             ta, tb, tc = (torch.randn(n, n, device=dev, dtype=tdt) for _ in range(3))
             A, B, Cm = (tarr(t) for t in (ta, tb, tc))
+            mib = n * n * ta.element_size() >> 20
             for chunks in (1, 8):
                 med, best = _time(ctx, lambda: par.general_mat_mul_rowsharded(1.0, A, B, 0.0, Cm, dist, 0, chunks), 3, 1)
                 t = torch.tensor([med], device=dev, dtype=torch.float64)
                 dist.all_reduce(t, op=dist.ReduceOp.MAX)
                 out[f"C4_gemm_{name}_rowsharded_{world}gpu_bcast_chunks{chunks}"] = {
                     "TFLOP/s_aggregate": round(world * 2.0 * n ** 3 / (float(t.item()) * 1e-3) / 1e12, 1), "ms": round(float(t.item()), 3),
-                    "collective": "ncclBroadcast of B (%d MiB) inside the timed step" % (n * n * ta.element_size() >> 20)}
+                    "scaling": "weak: 8192 rows per rank", "collective": "ncclBroadcast of B (%d MiB) inside the timed step" % mib}
+            rows = n // world
+            As, Cs = A.slice_axis(0, nd.Slice(0, rows, 1)), Cm.slice_axis(0, nd.Slice(0, rows, 1))
+            variants = [("torch_nccl", lambda: par.general_mat_mul_rowsharded(1.0, As, B, 0.0, Cs, dist, 0, 1))]
+            if comm is not None:
+                variants.append(("c_abi_ndb_gemm_rowsharded", lambda: par.gemm_rowsharded(1.0, As, B, 0.0, Cs, 0)))
+            for label, fn in variants:
+                med, best = _time(ctx, fn, 5, 2)
+                t = torch.tensor([med], device=dev, dtype=torch.float64)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                out[f"C4_gemm_{name}_8192^3_strong_{world}gpu_{label}"] = {
+                    "TFLOP/s_aggregate": round(2.0 * n ** 3 / (float(t.item()) * 1e-3) / 1e12, 1), "ms": round(float(t.item()), 3),
+                    "scaling": "strong: 8192^3 in all, %d rows of A and C per rank" % rows,
+                    "collective": "broadcast of B (%d MiB) inside the timed step" % mib}
             del ta, tb, tc
+        if comm is not None:
+            ctx.sync()
+            dist.barrier()
+            comm.close()
         torch.cuda.empty_cache()
     # ---- C4 through ndarray's own plugin boundary: cblas_{d,s}gemm with HOST pointers (what `features = ["blas"]` calls;
     #      pageable host memory like ndarray's Vec, H2D of A and B and D2H of C inside the timed call) -----------------
