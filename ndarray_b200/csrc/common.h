@@ -136,6 +136,9 @@ struct ndb_ctx {
     void *scan_chain = nullptr;
     size_t scan_chain_bytes = 0;
     uint32_t scan_epoch = 0;
+    // stream-K f64 GEMM (gemm_f64_tma.cu): ticket, one flag per stream-K CTA (all zero between launches) and the partial tiles
+    void *streamk = nullptr;
+    size_t streamk_bytes = 0;
     // NCCL communicator owned by the library (dist.cu; libnccl is dlopen'ed on first use)
     void *nccl_comm = nullptr;
     int comm_rank = -1, comm_world = 0;

@@ -379,6 +379,7 @@ int ndb_ctx_destroy(ndb_ctx *ctx)
         if (ctx->stage[i]) cudaFree(ctx->stage[i]);
     if (ctx->tickets) cudaFree(ctx->tickets);
     if (ctx->scan_chain) cudaFree(ctx->scan_chain);
+    if (ctx->streamk) cudaFree(ctx->streamk);
     if (ctx->dev_flag) cudaFree(ctx->dev_flag);
     if (ctx->host_flag) cudaFreeHost(ctx->host_flag);
     if (ctx->host_scalar) cudaFreeHost(ctx->host_scalar);

@@ -370,6 +370,14 @@ static int ensure_scan_chain(ndb_ctx *ctx, size_t bytes)
     return NDB_OK;
 }
 
+// The chained kernel's epoch is a launch ARGUMENT: a captured graph would replay it and find last replay's packets already
+// "valid".  While the stream is capturing the chunked (two-pass) form is used instead.
+static bool stream_is_capturing(ndb_ctx *ctx)
+{
+    cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+    return cudaStreamIsCapturing(ctx->stream, &st) != cudaSuccess || st != cudaStreamCaptureStatusNone;
+}
+
 template <typename T>
 int scan_dispatch(ndb_ctx *ctx, int op, const ScanArgs &a, bool lanes)
 {
@@ -385,13 +393,17 @@ int scan_dispatch(ndb_ctx *ctx, int op, const ScanArgs &a, bool lanes)
         } else if (mul) launch_pdl(scan_lanes<T, true>, blocks, 256, 0, ctx->stream, a);
         else launch_pdl(scan_lanes<T, false>, blocks, 256, 0, ctx->stream, a);
     } else if (a.n >= 512 && a.n_lanes < (int64_t)ctx->sm_count * 512 && !getenv("NDB_SCAN_NO_CHUNKS") && !getenv("NDB_SCAN_NO_CHAIN") &&
-               chain_eligible<T>(a)) {
+               chain_eligible<T>(a) && !stream_is_capturing(ctx)) {
         constexpr int W = 16 / (int)sizeof(T);
         const int tiles = (int)(a.n_lanes / (32 * W)), chunks = (int)(a.n / SCAN_CHAIN_ROWS);
         const size_t need = 256 + (size_t)tiles * chunks * 32 * W * sizeof(ScanPacket<T>);
         NDB_TRY(ensure_scan_chain(ctx, need));
         unsigned *ticket = reinterpret_cast<unsigned *>(ctx->scan_chain);
         ScanPacket<T> *packets = reinterpret_cast<ScanPacket<T> *>((char *)ctx->scan_chain + 256);
+        if (ctx->scan_epoch == UINT32_MAX) {  // epochs only grow: start over from clean packets before the counter wraps
+            NDB_CUDA(cudaMemsetAsync(ctx->scan_chain, 0, ctx->scan_chain_bytes, ctx->stream));
+            ctx->scan_epoch = 0;
+        }
         const uint32_t epoch = ++ctx->scan_epoch;
         const dim3 grid((unsigned)tiles * (unsigned)chunks), block(32, 8, 1);
         if (mul) launch_pdl(scan_cols_chained<T, true>, grid, block, 0, ctx->stream, a, packets, ticket, epoch, tiles, chunks);

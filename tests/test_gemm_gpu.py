@@ -358,6 +358,70 @@ def test_f64_small_outputs_split_k_over_clusters(nd, monkeypatch):
             monkeypatch.delenv("NDB_GEMM_F64_SPLITK", raising=False)
 
 
+def test_f64_stream_k_matches_whole_tile_kernel(nd, monkeypatch):
+    """Stream-K (gemm_f64_tma_streamk: k-ranges cut across tile boundaries, partials handed over through global memory in
+    ticket order) against the one-tile-per-CTA kernel: same result within rounding on every layout combination, with tile
+    overhang, with alpha/beta, bit-identical between runs.  Shapes cover: the automatic case (more tiles than SMs with a
+    ragged last wave), a forced small case where one tile is shared by several CTAs (64 tiles over 148 CTAs), and data-
+    parallel tiles after the stream-K region (3 waves and a remainder)."""
+    rng = np.random.default_rng(21)
+    monkeypatch.setenv("NDB_GEMM_F64_TILE", "128")
+    for (m, k, n) in [(2048, 512, 2048), (1024, 1024, 1024), (1000, 520, 776), (3000, 256, 3100), (1664, 288, 1700), (640, 2048, 384)]:
+        a = rng.standard_normal((m, k))
+        b = rng.standard_normal((k, n))
+        c0 = rng.standard_normal((m, n))
+        ref = -2.3 * (a @ b) + math.pi * c0
+        for af, bf in ((False, False), (True, False), (False, True), (True, True)):
+            res = {}
+            for sk in ("0", "1"):
+                monkeypatch.setenv("NDB_GEMM_F64_STREAMK", sk)
+                runs = []
+                for _ in range(2):
+                    da = nd.Array.from_numpy(np.asfortranarray(a) if af else a)
+                    db = nd.Array.from_numpy(np.asfortranarray(b) if bf else b)
+                    dc = nd.Array.from_numpy(c0)
+                    nd.general_mat_mul(-2.3, da, db, math.pi, dc)
+                    runs.append(dc.to_numpy())
+                assert np.array_equal(runs[0], runs[1]), (m, k, n, af, bf, sk)
+                assert rel_norm(runs[0], ref) < 1e-12 * math.sqrt(k), (m, k, n, af, bf, sk)
+                res[sk] = runs[0]
+            assert rel_norm(res["1"], res["0"]) < 1e-14 * math.sqrt(k), (m, k, n, af, bf)
+    # beta == 0 never reads C on the stream-K path either (impl_linalg.rs:323-329)
+    monkeypatch.setenv("NDB_GEMM_F64_STREAMK", "1")
+    a = rng.standard_normal((1024, 1024))
+    b = rng.standard_normal((1024, 1024))
+    dc = nd.Array.from_numpy(np.full((1024, 1024), np.nan))
+    nd.general_mat_mul(1.0, nd.Array.from_numpy(a), nd.Array.from_numpy(b), 0.0, dc)
+    assert rel_norm(dc.to_numpy(), a @ b) < 1e-12 * 32
+    monkeypatch.delenv("NDB_GEMM_F64_STREAMK", raising=False)
+    monkeypatch.delenv("NDB_GEMM_F64_TILE", raising=False)
+    # the automatic choice: 2048^2 outputs are 256 tiles on 148 SMs
+    a = rng.standard_normal((2048, 1024))
+    b = rng.standard_normal((1024, 2048))
+    got = nd.Array.from_numpy(a).dot(nd.Array.from_numpy(b)).to_numpy()
+    assert rel_norm(got, a @ b) < 1e-12 * 32
+
+
+def test_f64_stream_k_replays_inside_a_captured_graph(nd, monkeypatch):
+    """The stream-K hand-over state (ticket, flags) returns to zero when the grid retires, so a captured launch can be
+    replayed: three replays over changing inputs, each checked."""
+    rng = np.random.default_rng(22)
+    ctx = nd.default_context()
+    n = 2048
+    a = rng.standard_normal((n, 256))
+    b = rng.standard_normal((256, n))
+    da, db = nd.Array.from_numpy(a), nd.Array.from_numpy(b)
+    dc = nd.Array.zeros((n, n), np.float64)
+    nd.general_mat_mul(1.0, da, db, 0.0, dc)  # first call outside the capture: allocations, attributes
+    with ctx.capture() as g:
+        nd.general_mat_mul(1.0, da, db, 0.0, dc)
+    for scale in (1.0, -3.0, 0.5):
+        da.assign(nd.Array.from_numpy(a * scale))
+        g.launch()
+        ctx.sync()
+        assert rel_norm(dc.to_numpy(), (a * scale) @ b) < 1e-12 * 16, scale
+
+
 def test_cblas_large_operands_bounce_pipeline(nd):
     """Operands above 4 MiB travel through the pinned bounce-buffer pipeline (several 16 MiB chunks each way, pageable
     numpy memory like ndarray's Vec): results and the ldc padding must survive the trip."""

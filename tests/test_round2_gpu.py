@@ -456,3 +456,26 @@ def test_counter_generator_against_the_committed_fixture_on_device(nd):
                 assert [float(x).hex() for x in got] == c[key], c
             else:
                 assert got.tolist() == c[key], c
+
+
+def test_scan_inside_a_captured_graph_replays_on_new_data(nd):
+    """A captured running sum must give the right answer on every replay: the chained kernel's epoch is a launch argument
+    (a replay would find last time's packets valid), so a capturing stream takes the two-pass form."""
+    from ndarray_b200 import Array, Op
+    ctx = nd.default_context()
+    rng = np.random.default_rng(43)
+    shape = (4096, 64)
+    src = Array.from_numpy(rng.integers(-5, 6, shape).astype(np.int64))
+    d = Array.zeros(shape, np.int64)
+    d.assign(src)
+    d.accumulate_axis_inplace(0, Op.ADD)  # outside the capture: scratch allocations
+    with ctx.capture() as g:
+        d.assign(src)
+        d.accumulate_axis_inplace(0, Op.ADD)
+    for rep in range(3):
+        h = rng.integers(-5, 6, shape).astype(np.int64)
+        src.assign(Array.from_numpy(h))
+        g.launch()
+        ctx.sync()
+        assert np.array_equal(d.to_numpy(), np.cumsum(h, axis=0)), rep
+    g.close()
