@@ -442,8 +442,8 @@ def test_cblas_large_operands_bounce_pipeline(nd):
 
 def test_cblas_pipelined_row_blocks(nd):
     """Large row-major products with an untransposed A take the pipelined path (B up whole, A and C in row blocks, a worker
-    thread draining C): every layout ndarray's `blas` feature produces must come back identical to the one-shot path's
-    result and within tolerance of the reference - row-major, column-major (exchanged into row-major inside), transposed B,
+    thread draining C): every layout ndarray's `blas` feature produces must come back equal to the one-shot path's
+    result (to rounding) and within tolerance of the reference - row-major, column-major (exchanged into row-major inside), transposed B,
     padded ldc with beta != 0, and a row count that is not a multiple of the block."""
     import os
     L = nd.lib()
@@ -476,7 +476,8 @@ def test_cblas_pipelined_row_blocks(nd):
         one, pipe = run(False, transb), run(True, transb)
         assert rel_norm(pipe[:, :n], ref) < 1e-12 * math.sqrt(k)
         assert np.array_equal(pipe[:, n:], c0[:, n:])          # padding untouched
-        assert np.array_equal(one, pipe)                        # row blocks change no row's arithmetic
+        # a block's tile count decides where stream-K cuts the k sum, so the two paths agree to rounding, not to the bit
+        assert rel_norm(one[:, :n], pipe[:, :n]) < 1e-14 * math.sqrt(k)
     # column-major C = A B with A (m x k) stored column-major is the row-major product C^T = B^T A^T: pipelined over B's columns
     af, bf = np.asfortranarray(a[:1100]), np.asfortranarray(rng.standard_normal((k, 4300)))
     cf = np.zeros((1100, 4300), order="F")
