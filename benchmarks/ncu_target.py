@@ -1,6 +1,6 @@
 """One small workload per invocation, for `ncu --set full` captures (kept short: ncu replays every kernel ~40x).
 
-  python benchmarks/ncu_target.py zip|c5|combined|reduce|gemm64|gemm32
+  python benchmarks/ncu_target.py zip|c5|combined|reduce|gemm64|gemm32|gemm64sk
 """
 import sys
 from pathlib import Path
@@ -71,6 +71,17 @@ def main():
         Cm = Array.zeros((n, n), dt)
         for _ in range(2):
             nd.general_mat_mul(1.0, A, B, 0.0, Cm)
+    elif which == "gemm64sk":
+        # a ragged last wave (256 tiles on 148 SMs): whole tiles, then stream-K
+        import os
+        n = 2048
+        A = Array.from_numpy(rng.standard_normal((n, n)))
+        B = Array.from_numpy(rng.standard_normal((n, n)))
+        Cm = Array.zeros((n, n), np.float64)
+        for mode in ("0", "1"):
+            os.environ["NDB_GEMM_F64_STREAMK"] = mode
+            for _ in range(2):
+                nd.general_mat_mul(1.0, A, B, 0.0, Cm)
     ctx.sync()
     print("done", which, "launches", nd.lib().ndb_launch_count())
 
