@@ -11,7 +11,8 @@ from benchmarks.gemm_probe import timeit
 
 ctx = nd.default_context()
 dev = torch.device("cuda", 0)
-for (m, k, n) in ((2048, 2048, 2048), (2560, 2560, 2560), (1792, 4096, 1792), (2048, 8192, 2048), (2304, 2048, 2304), (3072, 3072, 3072), (1536, 2048, 1536)):
+for (m, k, n) in ((2048, 2048, 2048), (2560, 2560, 2560), (1792, 4096, 1792), (2048, 8192, 2048), (2304, 2048, 2304), (3072, 3072, 3072), (1536, 2048, 1536),
+                  (1024, 8192, 8192)):  # the last one is one rank's share of config 4 on 8 GPUs (512 tiles = 3.46 waves)
     ta = torch.randn(m, k, device=dev, dtype=torch.float64)
     tb = torch.randn(k, n, device=dev, dtype=torch.float64)
     tc = torch.zeros(m, n, device=dev, dtype=torch.float64)

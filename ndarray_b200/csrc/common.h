@@ -146,6 +146,7 @@ struct ndb_ctx {
 
 namespace ndb {
 int ensure_workspace(ndb_ctx *ctx, size_t bytes);
+bool stream_is_capturing(ndb_ctx *ctx);  // true while ndb_graph_begin .. ndb_graph_end (or the caller's own capture) is recording ctx->stream
 int ensure_stage(ndb_ctx *ctx, int slot, size_t bytes);
 // pageable host <-> device through two pinned bounce buffers: a few host threads copy chunk i+1 while the DMA engine
 // moves chunk i (cudaMemcpy from pageable memory runs at ~12 GB/s on these boxes, this pipeline at the threads' memcpy rate).

@@ -114,6 +114,12 @@ int validate_view(const ndb_view *v, const char *what)
     return NDB_OK;
 }
 
+bool stream_is_capturing(ndb_ctx *ctx)
+{
+    cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+    return cudaStreamIsCapturing(ctx->stream, &st) != cudaSuccess || st != cudaStreamCaptureStatusNone;
+}
+
 int ensure_workspace(ndb_ctx *ctx, size_t bytes)
 {
     if (ctx->workspace_bytes >= bytes) return NDB_OK;

@@ -513,12 +513,15 @@ int ensure_streamk(ndb_ctx *ctx, size_t bytes)
     return NDB_OK;
 }
 
+size_t streamk_head(ndb_ctx *ctx) { return ((size_t)(64 + ctx->sm_count) * sizeof(unsigned) + 1023) & ~(size_t)1023; }
+size_t streamk_bytes(ndb_ctx *ctx) { return streamk_head(ctx) + (size_t)ctx->sm_count * 128 * 128 * sizeof(double); }
+
 int streamk_launch(ndb_ctx *ctx, const CUtensorMap &ma, const CUtensorMap &mb, const TmaArgs &p, bool a_kc, bool b_kc, int64_t out_tiles,
                    int64_t all_ktiles)
 {
     const int sms = ctx->sm_count;
-    const size_t head = ((size_t)(64 + sms) * sizeof(unsigned) + 1023) & ~(size_t)1023;
-    NDB_TRY(ensure_streamk(ctx, head + (size_t)sms * 128 * 128 * sizeof(double)));
+    const size_t head = streamk_head(ctx);
+    NDB_TRY(ensure_streamk(ctx, streamk_bytes(ctx)));
     StreamKArgs q;
     q.ticket = reinterpret_cast<unsigned *>(ctx->streamk);
     q.flags = q.ticket + 64;
@@ -592,6 +595,8 @@ int gemm_f64_tma_launch(ndb_ctx *ctx, const double *a, int64_t lda, bool a_kc, c
     bool streamk = tile == 128 && out_tiles > sms && out_tiles % sms != 0 && all_ktiles >= 8 &&
                    ((out_tiles + sms - 1) / sms) * sms * 100 > out_tiles * 102;
     if (const char *e = getenv("NDB_GEMM_F64_STREAMK")) streamk = atoi(e) != 0 && tile == 128 && out_tiles * all_ktiles >= 2 * sms;
+    // the hand-over buffer cannot be (re)allocated while the stream is being captured: whole tiles then
+    if (streamk && ctx->streamk_bytes < streamk_bytes(ctx) && stream_is_capturing(ctx)) streamk = false;
     if (streamk) return streamk_launch(ctx, ma, mb, p, a_kc, b_kc, out_tiles, all_ktiles);
     // the opt-in is per DEVICE (a process may hold one context per GPU); setting it twice from racing threads is harmless
     static std::atomic<uint64_t> attr_done{0};

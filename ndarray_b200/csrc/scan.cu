@@ -371,13 +371,7 @@ static int ensure_scan_chain(ndb_ctx *ctx, size_t bytes)
 }
 
 // The chained kernel's epoch is a launch ARGUMENT: a captured graph would replay it and find last replay's packets already
-// "valid".  While the stream is capturing the chunked (two-pass) form is used instead.
-static bool stream_is_capturing(ndb_ctx *ctx)
-{
-    cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
-    return cudaStreamIsCapturing(ctx->stream, &st) != cudaSuccess || st != cudaStreamCaptureStatusNone;
-}
-
+// "valid".  While the stream is capturing (stream_is_capturing, ctx.cu) the chunked two-pass form is used instead.
 template <typename T>
 int scan_dispatch(ndb_ctx *ctx, int op, const ScanArgs &a, bool lanes)
 {
