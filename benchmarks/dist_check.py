@@ -144,6 +144,20 @@ def run_checks(ctx, dist, rank, world, gemm: bool = True, peers=None):
         close(f"C ABI [{label}] std_axis0", par.reduce_axis0_sharded(csf, Red.STD, n0, 0.0).to_numpy(), f.std(axis=0), tol * 8)
         cw = par.shard_axis0(Array.from_numpy(wide, cctx), rank, world)
         close(f"C ABI [{label}] var_axis0 wide", par.reduce_axis0_sharded(cw, Red.VAR, n0, 1.0).to_numpy(), wide.var(axis=0, ddof=1), tol * 8)
+        # fewer rows than ranks: a rank with an EMPTY shard still takes part (min / max contribute the type's extreme)
+        rows_t = max(1, world // 2)
+        ti = rng.integers(-1000, 1000, size=(rows_t, 256), dtype=np.int64)
+        tf = rng.standard_normal((rows_t, 256))
+        sti = par.shard_axis0(Array.from_numpy(ti, cctx), rank, world)
+        stf = par.shard_axis0(Array.from_numpy(tf, cctx), rank, world)
+        for name, red, fn in (("min", Red.MIN, np.min), ("max", Red.MAX, np.max), ("sum", Red.SUM, np.sum)):
+            ok(f"C ABI [{label}] {name}_axis0 i64, {rows_t} rows on {world} ranks",
+               np.array_equal(par.reduce_axis0_sharded(sti, red, rows_t).to_numpy(), fn(ti, axis=0)))
+            ok(f"C ABI [{label}] {name}() i64, {rows_t} rows on {world} ranks", par.reduce_all_sharded(sti, red) == fn(ti))
+            if name != "sum":
+                ok(f"C ABI [{label}] {name}_axis0 f64, {rows_t} rows on {world} ranks",
+                   np.array_equal(par.reduce_axis0_sharded(stf, red, rows_t).to_numpy(), fn(tf, axis=0)))
+                ok(f"C ABI [{label}] {name}() f64, {rows_t} rows on {world} ranks", par.reduce_all_sharded(stf, red) == fn(tf))
         # a kept axis: no exchange, outputs sharded like the input
         kept = Array.uninit((csf.shape[0],), np.float64, ctx=cctx)
         from ndarray_b200._ffi import check as _check, lib as _lib

@@ -356,10 +356,14 @@ int ndb_gemm_rowsharded(ndb_ctx *ctx, const void *alpha, const ndb_view *a_local
  * ndb_reduce_axis (outputs are sharded like the input).  axis == 0: the fused cooperative kernel over the peer windows when
  * they are attached and the layout qualifies (ndb_reduce_axis_peer), else local partial + all-reduce (mean divides by
  * n_global afterwards), or for var/std per-shard Welford states + all-gather + Chan merge in rank order (deterministic).
- * Every rank receives the full result in `out`. */
+ * Every rank receives the full result in `out`.  A rank whose shard is EMPTY (fewer rows than ranks) still takes part and
+ * must make the call: it contributes the identity (min / max: the element type's extreme); only n_global == 0 - the same
+ * on every rank - gives NDB_ERR_EMPTY for mean / min / max, before anybody enters the exchange. */
 int ndb_reduce_axis_sharded(ndb_ctx *ctx, int redop, int axis, const ndb_view *in, const ndb_view *out, double ddof, int64_t n_global);
 /* sum() / product() / min / max over all shards, result (element type) to host on every rank: the kernel that finishes the
- * local tree also does the exchange when peer windows are attached, else an NCCL all-reduce of one element follows. */
+ * local tree also does the exchange when peer windows are attached, else an NCCL all-reduce of one element follows.
+ * An empty shard contributes the identity (min / max: the type's extreme, which is also the result when EVERY shard is
+ * empty - the entry point does not know the global length). */
 int ndb_reduce_all_sharded(ndb_ctx *ctx, int redop, const ndb_view *in, void *out_host);
 
 /* accumulate_axis_inplace (src/impl_methods.rs:3243) with op NDB_OP_ADD (running sum) or NDB_OP_MUL (cumprod,

@@ -156,6 +156,7 @@ int staged_h2d(ndb_ctx *ctx, void *dst_dev, const void *src_host, size_t bytes, 
 int staged_d2h(ndb_ctx *ctx, void *dst_host, const void *src_dev, size_t bytes, cudaStream_t st = nullptr, int set = 0);
 int welford_merge_gathered(ndb_ctx *ctx, int dtype, int world, const int64_t *counts_dev, const void *means_dev, const void *m2s_dev,
                            int64_t n_out, int64_t pitch, double ddof, int want_std, void *out_dev);  // reduce.cu
+int write_identity(ndb_ctx *ctx, int dtype, int redop, void *out_dev);  // reduce.cu: what an EMPTY shard contributes to an exchange
 struct PeerArgs;
 int peer_begin(ndb_ctx *ctx, int blocks, size_t bytes, PeerArgs *out);  // peer.cu
 struct DeviceGuard {

@@ -231,8 +231,10 @@ int ndb_reduce_all_sharded(ndb_ctx *ctx, int redop, const ndb_view *in, void *ou
     if (ctx->peer_world > 1 && ctx->peer_attached) {
         NDB_TRY(ndb_reduce_all_peer(ctx, redop, in, dev_scalar));
     } else {
-        // an empty shard contributes the identity of sum / product; min / max of an empty shard have none
-        NDB_TRY(ndb_reduce_all_dev(ctx, redop, in, dev_scalar));
+        // an empty shard contributes the identity (min / max: the type's extreme) - it must not return before the exchange,
+        // the other ranks would wait for it
+        if (view_len(in) == 0 && ctx->nccl_comm && ctx->comm_world > 1) NDB_TRY(write_identity(ctx, in->dtype, redop, dev_scalar));
+        else NDB_TRY(ndb_reduce_all_dev(ctx, redop, in, dev_scalar));
         if (ctx->nccl_comm && ctx->comm_world > 1) {
             static const int ops[4] = {NCCL_SUM, NCCL_PROD, NCCL_MIN, NCCL_MAX};
             NDB_NCCL(nccl().AllReduce(dev_scalar, dev_scalar, 1, nccl_dtype(in->dtype), ops[redop], (nccl_comm_t)ctx->nccl_comm, ctx->stream),
@@ -293,8 +295,9 @@ int ndb_reduce_axis_sharded(ndb_ctx *ctx, int redop, int axis, const ndb_view *i
     if (!welford) {
         // 2. local partial (sum for mean), all-reduce over the ranks, mean divides by the GLOBAL length
         const int local_op = redop == NDB_RED_MEAN ? NDB_RED_SUM : redop;
-        if ((local_op == NDB_RED_MIN || local_op == NDB_RED_MAX) && in->dim[0] == 0) {
-            set_error("reduce_axis_sharded: min/max need at least one row on every rank");
+        const bool minmax = local_op == NDB_RED_MIN || local_op == NDB_RED_MAX;
+        if (minmax && n_global == 0) {  // the same on every rank: nobody enters the exchange
+            set_error("reduction of a zero-length axis has no value (ndarray returns None)");
             return NDB_ERR_EMPTY;
         }
         void *tmp = nullptr;
@@ -303,7 +306,21 @@ int ndb_reduce_axis_sharded(ndb_ctx *ctx, int redop, int axis, const ndb_view *i
             NDB_CUDA(cudaMallocAsync(&tmp, (size_t)n_out * esz, ctx->stream));
             part = dense_like(out, tmp);
         }
-        int st = ndb_reduce_axis(ctx, local_op, 0, in, &part, 0.0);
+        int st;
+        if (minmax && in->dim[0] == 0) {
+            // this rank holds no rows of a non-empty axis: it still takes part, contributing the type's extreme
+            union { float f; double d; int32_t i; int64_t l; } ext;
+            const bool mn = local_op == NDB_RED_MIN;
+            switch (dt) {
+            case NDB_F32: ext.f = mn ? INFINITY : -INFINITY; break;
+            case NDB_F64: ext.d = mn ? INFINITY : -INFINITY; break;
+            case NDB_I32: ext.i = mn ? INT32_MAX : INT32_MIN; break;
+            default: ext.l = mn ? INT64_MAX : INT64_MIN; break;
+            }
+            st = ndb_zip(ctx, NDB_OP_FILL, &ext, 1, &part);
+        } else {
+            st = ndb_reduce_axis(ctx, local_op, 0, in, &part, 0.0);
+        }
         if (st == NDB_OK) {
             if (ctx->nccl_comm) {
                 static const int ops[4] = {NCCL_SUM, NCCL_PROD, NCCL_MIN, NCCL_MAX};

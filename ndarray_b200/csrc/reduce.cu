@@ -1156,21 +1156,49 @@ static int64_t view_len(const ndb_view *v)
     return n;
 }
 
-// identity written for empty inputs: sum -> 0, product -> 1 (tests/numeric.rs:57-75)
-static int write_identity(ndb_ctx *ctx, int dtype, int redop, void *out_dev)
+// identity written for empty inputs: sum -> 0, product -> 1 (tests/numeric.rs:57-75).  min / max have none in ndarray
+// (an empty fold returns its init); across ranks an EMPTY SHARD of a non-empty array still has to take part in the
+// exchange, and contributes the element type's extreme value (+inf / MAX for min, -inf / MIN for max).
+int write_identity(ndb_ctx *ctx, int dtype, int redop, void *out_dev)
 {
     union { float f; double d; int32_t i; int64_t l; } u;
     memset(&u, 0, sizeof(u));
-    const bool one = redop == NDB_RED_PROD;
-    switch (dtype) {
-    case NDB_F32: u.f = one ? 1.f : 0.f; break;
-    case NDB_F64: u.d = one ? 1.0 : 0.0; break;
-    case NDB_I32: u.i = one ? 1 : 0; break;
-    case NDB_I64: u.l = one ? 1 : 0; break;
+    switch (redop) {
+    case NDB_RED_PROD:
+        switch (dtype) {
+        case NDB_F32: u.f = 1.f; break;
+        case NDB_F64: u.d = 1.0; break;
+        case NDB_I32: u.i = 1; break;
+        default: u.l = 1; break;
+        }
+        break;
+    case NDB_RED_MIN:
+        switch (dtype) {
+        case NDB_F32: u.f = INFINITY; break;
+        case NDB_F64: u.d = INFINITY; break;
+        case NDB_I32: u.i = INT32_MAX; break;
+        default: u.l = INT64_MAX; break;
+        }
+        break;
+    case NDB_RED_MAX:
+        switch (dtype) {
+        case NDB_F32: u.f = -INFINITY; break;
+        case NDB_F64: u.d = -INFINITY; break;
+        case NDB_I32: u.i = INT32_MIN; break;
+        default: u.l = INT64_MIN; break;
+        }
+        break;
+    default: break;  // sum: all-zero bits
     }
-    memcpy(ctx->host_scalar, &u, sizeof(u));
-    NDB_CUDA(cudaMemcpyAsync(out_dev, ctx->host_scalar, dtype_size(dtype), cudaMemcpyHostToDevice, ctx->stream));
-    return NDB_OK;
+    // the value travels as a kernel parameter (a staged copy from ctx->host_scalar could be overtaken by the next call)
+    ndb_view one;
+    memset(&one, 0, sizeof(one));
+    one.ptr = out_dev;
+    one.dtype = dtype;
+    one.ndim = 1;
+    one.dim[0] = 1;
+    one.stride[0] = 1;
+    return ndb_zip(ctx, NDB_OP_FILL, &u, 1, &one);
 }
 
 static int reduce_all_dev_impl(ndb_ctx *ctx, int redop, const ndb_view *in, void *out_dev, bool peer = false)
@@ -1178,11 +1206,8 @@ static int reduce_all_dev_impl(ndb_ctx *ctx, int redop, const ndb_view *in, void
     NDB_TRY(validate_view(in, "reduce_all"));
     if (view_len(in) == 0) {
         if (peer) {
-            // an empty shard still has to take part in the exchange: contribute the identity
-            if (redop != NDB_RED_SUM && redop != NDB_RED_PROD) {
-                set_error("reduce_all: min/max of an empty shard");
-                return NDB_ERR_EMPTY;
-            }
+            // an empty shard still has to take part in the exchange (returning here would leave the other ranks waiting):
+            // it contributes the identity, for min / max the type's extreme
             NDB_TRY(write_identity(ctx, in->dtype, redop, out_dev));
             return ndb_peer_allreduce(ctx, redop, in->dtype, out_dev, out_dev, 1);
         }
