@@ -137,6 +137,8 @@ def run_checks(ctx, dist, rank, world, gemm: bool = True, peers=None):
             ok(f"C ABI [{label}] sum() i64", par.reduce_all_sharded(csa) == a.sum(dtype=np.int64))
             ok(f"C ABI [{label}] sum_axis0 i64", np.array_equal(par.reduce_axis0_sharded(csa, Red.SUM, n0).to_numpy(), a.sum(axis=0, dtype=np.int64)))
             ok(f"C ABI [{label}] fold_axis0 min i64", np.array_equal(par.reduce_axis0_sharded(csa, Red.MIN, n0).to_numpy(), a.min(axis=0)))
+            ok(f"C ABI [{label}] min() / max() i64", par.reduce_all_sharded(csa, Red.MIN) == a.min() and par.reduce_all_sharded(csa, Red.MAX) == a.max())
+        ok(f"C ABI [{label}] min() / max() f64", par.reduce_all_sharded(csf, Red.MIN) == f.min() and par.reduce_all_sharded(csf, Red.MAX) == f.max())
         close(f"C ABI [{label}] sum() f64", par.reduce_all_sharded(csf), f.sum(), tol * 300 * 8)
         close(f"C ABI [{label}] sum_axis0 f64", par.reduce_axis0_sharded(csf, Red.SUM, n0).to_numpy(), f.sum(axis=0), tol * 8)
         close(f"C ABI [{label}] mean_axis0", par.reduce_axis0_sharded(csf, Red.MEAN, n0).to_numpy(), f.mean(axis=0), tol)

@@ -744,13 +744,16 @@ __global__ void __launch_bounds__(256) red_all_finish_peer(const void *partial, 
     peer_arrive(pa);
     peer_wait(pa);
     if (threadIdx.x == 0) {
+        // every slot holds a value (an empty shard sent the identity / the type's extreme), so min / max states are seeded
         Acc<T, R> tot;
         tot.reset();
         tot.s = __ldcg(reinterpret_cast<const T *>(peer_slot(pa, pa.rank, 0)));
+        tot.valid = true;
         for (int r = 1; r < pa.world; ++r) {
             Acc<T, R> b;
             b.reset();
             b.s = __ldcg(reinterpret_cast<const T *>(peer_slot(pa, pa.rank, r)));
+            b.valid = true;
             tot.merge(b);
         }
         *out = tot.s;
