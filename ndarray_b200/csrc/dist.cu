@@ -360,9 +360,17 @@ int ndb_reduce_axis_sharded(ndb_ctx *ctx, int redop, int axis, const ndb_view *i
     ndb_view vmean = dense_like(out, mean), vm2 = dense_like(out, m2);
     int st = ndb_welford_axis(ctx, 0, in, &vmean, &vm2);
     if (st == NDB_OK) {
+        // this shard's row count, as a kernel parameter: the call returns without synchronising, and a copy staged through
+        // ctx->host_scalar could still be pending when the next call overwrites that buffer
         const int64_t rows = in->dim[0];
-        memcpy(ctx->host_scalar, &rows, sizeof(rows));
-        if (cudaMemcpyAsync(cnt, ctx->host_scalar, sizeof(rows), cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) st = NDB_ERR_CUDA;
+        ndb_view vc;
+        memset(&vc, 0, sizeof(vc));
+        vc.ptr = cnt;
+        vc.dtype = NDB_I64;
+        vc.ndim = 1;
+        vc.dim[0] = 1;
+        vc.stride[0] = 1;
+        st = ndb_zip(ctx, NDB_OP_FILL, &rows, 1, &vc);
     }
     if (st == NDB_OK) {
         if (ctx->nccl_comm) {
