@@ -339,3 +339,63 @@ def test_rust_ffi_declares_exactly_the_header():
     used = set(re.findall(r"ffi::((?:ndb|cblas)_[a-z0-9_]+)\s*\(", lib_rs))
     assert used <= set(rust), sorted(used - set(rust))
     assert len(used) >= 40  # the crate actually covers the ABI, not a corner of it
+
+
+def test_streamk_partition_invariants():
+    """A model of the range arithmetic shared by `streamk_launch` (host: region size, grid) and `gemm_f64_tma_streamk`
+    (device: ticket -> [it0, it1), segments, owner / contributor roles) in csrc/gemm_f64_tma.cu, checked over random shapes
+    for the properties the hand-over protocol relies on: every (tile, k-slab) is computed exactly once; every tile has
+    exactly one owner (the CTA holding its first slab); only a CTA's FIRST segment can start inside a tile, so a CTA parks at
+    most one partial and never waits before doing so; the contributors an owner walks (tickets w+1.. while their range
+    starts before the tile's end) are exactly the CTAs that parked a partial for that tile, each consumed once - so every
+    flag raised is lowered again and the buffer is clean when the grid retires."""
+    import random
+
+    def check(out_tiles, kt, sms):
+        sk_tiles = sms + out_tiles % sms if out_tiles > sms else out_tiles
+        iters = sk_tiles * kt
+        grid = sms + out_tiles - sk_tiles
+        cover, parked, owners = {}, {}, {}
+        for w in range(grid):
+            if w < sms:
+                it0, it1 = iters * w // sms, iters * (w + 1) // sms
+            else:
+                it0 = (sk_tiles + (w - sms)) * kt
+                it1 = it0 + kt
+            assert it1 > it0
+            it, first = it0, True
+            while it < it1:
+                tile = it // kt
+                kb = it - tile * kt
+                nseg = min(it1 - it, kt - kb)
+                for k in range(kb, kb + nseg):
+                    assert (tile, k) not in cover
+                    cover[(tile, k)] = w
+                if kb == 0:
+                    assert tile not in owners
+                    owners[tile] = (w, nseg)
+                else:
+                    assert first and w not in parked
+                    parked[w] = tile
+                it += nseg
+                first = False
+        assert len(cover) == out_tiles * kt and len(owners) == out_tiles
+        consumed = set()
+        for tile, (w, nseg) in owners.items():
+            if nseg < kt:
+                c = w + 1
+                while c < sms and iters * c // sms < (tile + 1) * kt:
+                    assert parked.get(c) == tile and c not in consumed
+                    consumed.add(c)
+                    c += 1
+        assert consumed == set(parked)
+
+    rng = random.Random(1)
+    for sms in (148, 132, 2, 3, 7):
+        for _ in range(150):
+            out_tiles, kt = rng.randint(1, 5 * sms + 3), rng.randint(1, 300)
+            sk_tiles = sms + out_tiles % sms if out_tiles > sms else out_tiles
+            if sk_tiles * kt >= 2 * sms:  # the launcher's floor: no CTA gets an empty range
+                check(out_tiles, kt, sms)
+    for out_tiles, kt in ((256, 64), (400, 80), (196, 128), (512, 256), (56, 17), (15, 64), (600, 8), (182, 9)):
+        check(out_tiles, kt, 148)  # the shapes of benchmarks/gemm_streamk.py and test_f64_stream_k_matches_whole_tile_kernel
