@@ -86,6 +86,11 @@ def main():
     if isinstance(cs, dict):
         out += ["", "CPU stand-ins for those configs on the same box (`cpu_stand_in`): " +
                 "; ".join(f"{k}: {v.get('GB/s', v.get('TFLOP/s'))} {'GB/s' if 'GB/s' in v else 'TFLOP/s'}" for k, v in cs.items() if isinstance(v, dict)) + "."]
+    for title, name in (("## general_mat_mul across sizes, ours vs cuBLAS (`benchmarks/gemm_sizes.py`)", "r02_gemm_sizes.log"),
+                        ("## f64 general_mat_mul on ragged-wave shapes: whole tiles / stream-K / cuBLAS (`benchmarks/gemm_streamk.py`)", "r02_gemm_streamk.log")):
+        f = P / name
+        if f.exists():
+            out += ["", title, "", "```"] + [ln for ln in f.read_text().splitlines() if ln.startswith(("f64", "f32"))] + ["```"]
     (ROOT / "RESULTS.md").write_text("\n".join(out) + "\n")
     print("wrote RESULTS.md,", len(out), "lines")
 
